@@ -1,0 +1,328 @@
+#!/usr/bin/env python3
+"""bench.py -- attempted swaps per second of the BraWl atom-swap hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA arm (libbrawl_cuda.so)
+    python bench.py --impl reference --gpus N ...            # CPU arm: the reference algorithm on host cores
+
+Workload (BASELINE.json configs[1]): AlTiCrMo bcc Metropolis on a 128^3 lattice (4 194 304 atoms,
+reference grid 256^3 = 16 MiB int8), 4 species at 0.25, first 4 shells of AlTiCrMo.vij (Z = 50),
+whole-lattice swaps (nbr_swap = F), T = 1000 K, synthetic random start from initial_setup
+semantics.  One "step" = --sweeps lattice sweeps = sweeps * N_atoms attempted swaps.
+
+Timing: CUDA events on the launching stream around each step, L2 flushed (512 MiB memset) before
+every timed step, W warm-up steps, max over ranks.  `value` has the lattice resident in HBM;
+`e2e` runs the same step through the host-facing C-ABI call sequence a Fortran driver would make
+(pinned host config -> set_config -> metropolis_run -> get_config + total_energy), copies timed.
+N > 1: the single chain does not shard ("replicas only"): every rank runs its own
+independent 128^3 replica on its own GPU, no data-path collective; value = total attempts / max time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CELLS = 128
+T_KELVIN = 1000.0
+B_ALG = 104          # algorithmic bytes per attempted swap, bcc 4 shells: 2Z+4
+METRIC = "attempted_swaps_per_sec"
+
+
+def load_V():
+    """First 4 shell blocks of examples/02_wang-landau_AlTiCrMo/AlTiCrMo.vij (committed fixture)."""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "brawl_golden.npz"))
+    return np.ascontiguousarray(gold["ex_AlTiCrMo_V"][: 4 * 4 * 4])
+
+
+def synthetic_config(n, S, rank):
+    """Random equiatomic start written directly on the bcc sites (numpy; same distribution as
+    initial_setup: a uniformly random arrangement of the species multiset)."""
+    rng = np.random.default_rng(110179 + 11 * rank)
+    N = 2 * n ** 3
+    spec = np.repeat(np.arange(1, S + 1, dtype=np.int8), N // S)
+    rng.shuffle(spec)
+    g = np.zeros((2 * n, 2 * n, 2 * n), dtype=np.int8)
+    z, y, x = np.meshgrid(np.arange(2 * n), np.arange(2 * n), np.arange(2 * n), indexing="ij")
+    mask = ((x & 1) == (z & 1)) & ((y & 1) == (z & 1))
+    g[mask] = spec
+    return g
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_rate(n_threads, trials_per_thread, n=N_CELLS, seed0=0):
+    """The reference algorithm (oracle C restatement, validated bit-exactly against the reference's
+    goldens) on host cores: one independent replica per thread, the reference's own Metropolis
+    parallel model (src/comms.F90:122-160).  Returns (attempted swaps/s over all threads, seconds)."""
+    from oracle import oracle          # CPU baseline legs only: the oracle is the thing being timed here
+    V = load_V()
+    osys = oracle.System("bcc", n, n, n, 4, 4, V)
+    beta = 1.0 / (T_KELVIN * oracle.K_B_IN_RY)
+    grids = [synthetic_config(n, 4, seed0 + t) for t in range(n_threads)]
+    mts = [oracle.MT(rank=seed0 + t) for t in range(n_threads)]
+    for t in range(n_threads):                         # warm the caches / page in
+        osys.metropolis_trials(grids[t], mts[t], beta, 20000)
+    ths = [threading.Thread(target=osys.metropolis_trials, args=(grids[t], mts[t], beta, trials_per_thread))
+           for t in range(n_threads)]                  # ctypes releases the GIL
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    return n_threads * trials_per_thread / dt, dt
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_thread = args.ref_trials
+    vals, times = [], []
+    for s in range(args.warmup + args.steps):
+        v, dt = cpu_reference_rate(cores, per_thread, seed0=s * cores)
+        if s >= args.warmup:
+            vals.append(v); times.append(dt)
+    value = float(np.mean(vals))
+    sample = "%d threads x %d trials per step on private 128^3 bcc replicas (T=%g K)" % (cores, per_thread, T_KELVIN)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "swaps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "AlTiCrMo bcc 128^3, 4 species, 4 shells, Metropolis whole-lattice swaps, T=1000K",
+                   "n_atoms": 2 * N_CELLS ** 3, "step": sample},
+        "cpu_baseline": {"value": value, "unit": "swaps/s", "cores": cores, "kind": "port",
+                         "sample": sample + "; C restatement of the reference (no Fortran toolchain in the image), "
+                                            "bit-exact vs reference goldens"},
+        "e2e": {"value": value, "unit": "swaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--sweeps", type=int, default=16, help="lattice sweeps (N_atoms attempted swaps each) per step")
+    ap.add_argument("--ref-trials", type=int, default=1500000, help="--impl reference: trials per thread per step")
+    ap.add_argument("--cpu-trials", type=int, default=3000000, help="cpu_baseline leg: trials per thread")
+    ap.add_argument("--box", default="", help="override box extents, e.g. 64,64,32")
+    ap.add_argument("--steps-per-phase", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--n-cells", type=int, default=N_CELLS)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "cuda":
+        args.warmup = max(args.warmup, 3) if os.environ.get("BENCH_ALLOW_SHORT_WARMUP") is None else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import brawl_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the CUDA arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.n_cells
+    V = load_V()
+    g0 = synthetic_config(n, 4, rank)
+    N = 2 * n ** 3
+    beta = 1.0 / (T_KELVIN * brawl_b200.K_B_IN_RY)
+    dev = brawl_b200.Device("bcc", n, n, n, 4, 4, V, device=local_rank, n_replicas=1)
+    stream = torch.cuda.Stream()            # non-default stream shared by torch events and the library
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    dev.set_stream(stream.cuda_stream)
+    if args.box:
+        dev.metropolis_tune(tuple(int(v) for v in args.box.split(",")), args.steps_per_phase)
+    elif args.steps_per_phase:
+        dev.metropolis_tune((0, 0, 0), args.steps_per_phase)
+    plan = dev.metropolis_plan()
+    dev.set_config(g0)
+    e_start = dev.total_energy(exact_order=False)[0]
+    trials_per_step = args.sweeps * N
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ("value") ----------------------------------------------------------
+    def step_resident():
+        return dev.metropolis_enqueue(beta, trials_per_step)
+
+    for _ in range(args.warmup):
+        step_resident()
+    dev.metropolis_counters(reset=True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    times, attempts, launches = [], 0, 0
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()                                   # L2 flush, outside the timed events
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        planned, nl = step_resident()
+        ev1.record(stream)
+        ev1.synchronize()
+        times.append(ev0.elapsed_time(ev1))
+        attempts += planned
+        launches += nl
+    barrier()
+    clocks = sampler.stop()
+    att, acc, dE = dev.metropolis_counters(reset=True)
+    assert att[0] == attempts, (att, attempts)
+    total_ms = float(np.sum(times))
+    e_end = dev.total_energy(exact_order=False)[0]
+
+    # ---- end-to-end arm ("e2e"): host buffers through the public C-ABI calls ----------------------
+    host_cfg = torch.empty((2 * n, 2 * n, 2 * n), dtype=torch.int8).pin_memory()
+    host_np = host_cfg.numpy()
+    host_np[...] = dev.get_config()
+    e2e_times, e2e_attempts, e2e_launches = [], 0, 0
+    n_e2e = max(3, min(args.steps, 5))
+    for it in range(2 + n_e2e):
+        flush.zero_()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        dev.set_config(host_np)                                     # H2D 8n^3 bytes (+ pack kernel)
+        a, c, d = dev.metropolis_run(beta, trials_per_step)         # trials
+        dev.get_config(out=host_np.reshape((1,) + host_np.shape))   # D2H 8n^3 bytes (+ unpack kernel)
+        e_host = dev.total_energy(exact_order=False)[0]            # D2H 8 bytes (2 kernels)
+        ev1.record(stream)
+        ev1.synchronize()
+        if it >= 2:
+            e2e_times.append(ev0.elapsed_time(ev1))
+            e2e_attempts += int(a[0])
+            per_phase = plan["trials_per_step"] * plan["steps_per_phase"] * plan["boxes_per_replica"]
+            e2e_launches += (int(a[0]) // per_phase if plan["use_box"] else 1) + 4   # + pack, unpack, 2 energy kernels
+    e2e_ms = float(np.sum(e2e_times))
+
+    # ---- reduce over ranks (max time, sum attempts) -----------------------------------------------
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cnt = torch.tensor([attempts, e2e_attempts, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+        attempts_all, e2e_attempts_all, launches_all = int(cnt[0]), int(cnt[1]), int(cnt[2])
+    else:
+        attempts_all, e2e_attempts_all, launches_all = attempts, e2e_attempts, launches
+
+    if rank == 0:
+        value = attempts_all / (total_ms * 1e-3)
+        e2e_value = e2e_attempts_all / (e2e_ms * 1e-3)
+        peak, peak_src = peak_hbm()
+        # dominant kernel = brw_box_metropolis_kernel: the step is `launches` back-to-back launches of it
+        per_launch_ms = total_ms / max(1, launches)
+        per_launch_trials = attempts / max(1, launches)
+        achieved = per_launch_trials * B_ALG / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        out = {
+            "metric": METRIC, "value": value, "unit": "swaps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "AlTiCrMo bcc %d^3 (%d atoms), 4 species @0.25, 4 shells (Z=50), Metropolis "
+                                   "whole-lattice swaps, T=%g K; replicas only for N>1 (one chain per GPU)" % (n, N, T_KELVIN),
+                       "attempted_swaps_per_step": trials_per_step, "sweeps_per_step": args.sweeps,
+                       "l2": "flushed with a 512 MiB memset before every timed step",
+                       "decomposition": plan, "acceptance": float(acc[0]) / max(1, float(att[0])),
+                       "energy_per_atom_start_end_Ry": [e_start / N, e_end / N]},
+            "e2e": {"value": e2e_value, "unit": "swaps/s", "h2d_bytes_per_step": int(8 * n ** 3 + 8),
+                    "d2h_bytes_per_step": int(8 * n ** 3 + 8 + 24),
+                    "calls": "set_config + metropolis_run + get_config + total_energy, pinned host buffers"},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "brw_box_metropolis_kernel<0>",
+                         "algorithmic_bytes_per_attempt": B_ALG, "attempts_per_launch": per_launch_trials,
+                         "ms_per_launch": per_launch_ms, "peak_source": peak_src,
+                         "note": "lattice is L2/shared-memory resident by design; see DESIGN.md"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, dt = cpu_reference_rate(cores, args.cpu_trials)
+            out["cpu_baseline"] = {"value": v, "unit": "swaps/s", "cores": cores, "kind": "port",
+                                   "sample": "%d threads x %d trials on private 128^3 bcc replicas, %.1f s; C restatement "
+                                             "of the reference hot path (bit-exact vs reference goldens)" % (cores, args.cpu_trials, dt)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

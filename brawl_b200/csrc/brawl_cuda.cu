@@ -1,0 +1,806 @@
+// brawl_cuda.cu -- C ABI (include/brawl_cuda.h) of libbrawl_cuda.so.  Unity build: the kernel
+// headers are included here so the library is one translation unit (no device linking).
+// Product code: there is NO CPU fallback -- every entry point needs a working CUDA device.
+#include <array>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/brawl_cuda.h"
+#include "brawl_common.cuh"
+#include "shell_tables.inc"
+#include "energy_kernels.cuh"
+#include "replay_kernels.cuh"
+#include "tile_metropolis.cuh"
+#include "walker_kernels.cuh"
+
+// ---- error state ---------------------------------------------------------------------------------
+static thread_local std::string g_err = "";
+int brw_fail(const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+int brw_cuda_check(cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return 0;
+  return brw_fail("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+extern "C" const char *brawl_cuda_last_error(void) { return g_err.c_str(); }
+extern "C" int brawl_cuda_version(void) { return 1; }
+extern "C" int brawl_cuda_device_count(int *count) {
+  int n = 0;
+  BRW_CUDA(cudaGetDeviceCount(&n));
+  if (count) *count = n;
+  if (n < 1) return brw_fail("no CUDA device visible");
+  return 0;
+}
+
+__global__ void brw_philox_test_kernel(const uint32_t *c, const uint32_t *k, uint32_t *o) {
+  BrwPhilox4 r = brw_philox(c[0], c[1], c[2], c[3], k[0], k[1]);
+  o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
+}
+extern "C" int brawl_cuda_philox4x32(int device, const uint32_t *c, const uint32_t *k, uint32_t *o) {
+  if (!c || !k || !o) return brw_fail("null argument");
+  int nd = 0;
+  if (brawl_cuda_device_count(&nd)) return 1;
+  if (device < 0 || device >= nd) return brw_fail("device %d not available", device);
+  BRW_CUDA(cudaSetDevice(device));
+  uint32_t *d = nullptr;
+  BRW_CUDA(cudaMalloc(&d, 10 * sizeof(uint32_t)));
+  cudaMemcpy(d, c, 16, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + 4, k, 8, cudaMemcpyHostToDevice);
+  brw_philox_test_kernel<<<1, 1>>>(d, d + 4, d + 6);
+  cudaError_t e = cudaMemcpy(o, d + 6, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return brw_cuda_check(e, "philox self-test");
+}
+
+int brw_ensure_scratch(brawl_cuda_ctx *h, size_t bytes) {
+  if (h->scratch_bytes >= bytes) return 0;
+  if (h->d_scratch) BRW_CUDA(cudaFree(h->d_scratch));
+  h->d_scratch = nullptr; h->scratch_bytes = 0;
+  BRW_CUDA(cudaMalloc(&h->d_scratch, bytes));
+  h->scratch_bytes = bytes;
+  return 0;
+}
+int brw_ensure_stage(brawl_cuda_ctx *h, size_t bytes) {
+  if (h->stage_bytes >= bytes) return 0;
+  if (h->d_stage) BRW_CUDA(cudaFree(h->d_stage));
+  h->d_stage = nullptr; h->stage_bytes = 0;
+  BRW_CUDA(cudaMalloc(&h->d_stage, bytes));
+  h->stage_bytes = bytes;
+  return 0;
+}
+static int grid_for(long n, int block, int cap = 148 * 16) {
+  long b = (n + block - 1) / block;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+#define BRW_ENTER(h)                                                      \
+  do {                                                                    \
+    if (!(h)) return brw_fail("null handle");                             \
+    BRW_CUDA(cudaSetDevice((h)->device));                                 \
+  } while (0)
+#define BRW_REPLICA(h, r)                                                 \
+  do { if ((r) < 0 || (r) >= (h)->n_replicas) return brw_fail("replica %d out of range [0,%d)", (r), (h)->n_replicas); } while (0)
+
+// ---- handle ----------------------------------------------------------------------------------------
+extern "C" int brawl_cuda_create(int lattice, int n1, int n2, int n3, int S, int n_shells, const double *V,
+                                 int device, int n_replicas, brawl_cuda_t **out) {
+  if (!out) return brw_fail("null handle pointer");
+  *out = nullptr;
+  if (lattice < 0 || lattice > 2) return brw_fail("Lattice type not yet implemented!");             // initialise.F90:238-240
+  int maxs = lattice == 1 ? BRW_BCC_MAX_SHELLS : lattice == 2 ? BRW_FCC_MAX_SHELLS : BRW_SC_MAX_SHELLS;
+  if (n_shells < 1 || n_shells > maxs) return brw_fail("Unsupported number of shells");              // initialise.F90:166-169 etc.
+  if (n1 < 1 || n2 < 1 || n3 < 1) return brw_fail("lattice extents must be positive");
+  if (S < 1 || S > BRW_MAX_SPECIES) return brw_fail("n_species must be in 1..%d", BRW_MAX_SPECIES);
+  if (!V) return brw_fail("null V_ex");
+  if (n_replicas < 1) return brw_fail("n_replicas must be >= 1");
+  if ((long)n1 * n2 * n3 * 8 > (1L << 31) - 1) return brw_fail("lattice too large for 32-bit site indices");
+  int ndev = 0;
+  if (brawl_cuda_device_count(&ndev)) return 1;
+  if (device < 0 || device >= ndev) return brw_fail("device %d not available (%d visible)", device, ndev);
+  BRW_CUDA(cudaSetDevice(device));
+
+  brawl_cuda_ctx *h = new brawl_cuda_ctx();
+  memset(h, 0, sizeof *h);
+  h->device = device;
+  BrwGeom &g = h->g;
+  g.lattice = lattice; g.S = S; g.n_shells = n_shells;
+  g.gx = 2 * n1; g.gy = 2 * n2; g.gz = 2 * n3;
+  if (lattice == 0) { g.wx = n1; g.wy = n2; g.wz = n3; g.cx = g.gx; g.cy = g.gy; g.xs = 0; g.ys = 0; }
+  else { g.wx = g.gx; g.wy = g.gy; g.wz = g.gz; g.cx = n1; g.xs = 1; g.cy = lattice == 1 ? n2 : g.gy; g.ys = lattice == 1 ? 1 : 0; }
+  g.cz = g.gz;
+  g.n_sites = g.cx * g.cy * g.cz;
+  const signed char(*tab)[3] = lattice == 1 ? brw_bcc_off : lattice == 2 ? brw_fcc_off : brw_sc_off;
+  const int *st = lattice == 1 ? brw_bcc_start : lattice == 2 ? brw_fcc_start : brw_sc_start;
+  const int *ct = lattice == 1 ? brw_bcc_count : lattice == 2 ? brw_fcc_count : brw_sc_count;
+  int k = 0;
+  for (int n = 0; n < n_shells; n++) {
+    for (int j = 0; j < ct[n]; j++, k++) {
+      g.off[k][0] = tab[st[n] + j][0]; g.off[k][1] = tab[st[n] + j][1]; g.off[k][2] = tab[st[n] + j][2];
+      g.off[k][3] = (signed char)n;
+    }
+    g.shell_end[n] = k;
+  }
+  g.ztot = k;
+  h->n_replicas = n_replicas;
+  h->grid_cells = (int64_t)g.gx * g.gy * g.gz;
+  h->tune_box[0] = h->tune_box[1] = h->tune_box[2] = 0; h->tune_steps = 0;
+#define BRW_CREATE_CUDA(x) do { if (brw_cuda_check((x), #x)) { brawl_cuda_destroy(h); return 1; } } while (0)
+  BRW_CREATE_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  BRW_CREATE_CUDA(cudaMalloc(&h->d_lat, (size_t)g.n_sites * n_replicas));
+  BRW_CREATE_CUDA(cudaMemsetAsync(h->d_lat, 0, (size_t)g.n_sites * n_replicas, h->stream));
+  BRW_CREATE_CUDA(cudaMalloc(&h->d_V, sizeof(double) * S * S * n_shells));
+  BRW_CREATE_CUDA(cudaMemcpyAsync(h->d_V, V, sizeof(double) * S * S * n_shells, cudaMemcpyHostToDevice, h->stream));
+  BRW_CREATE_CUDA(cudaMalloc(&h->d_flag, sizeof(int)));
+  BRW_CREATE_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+  BRW_CREATE_CUDA(cudaStreamSynchronize(h->stream));
+  h->hV = new double[S * S * n_shells];
+  memcpy(h->hV, V, sizeof(double) * S * S * n_shells);
+  *out = h;
+  return 0;
+}
+
+static void brw_free_plan(BrwPlan *pl) {
+  if (!pl) return;
+  cudaFree(pl->d_classes); cudaFree(pl->d_disp); cudaFree(pl->d_off); cudaFree(pl->d_Vrep);
+  cudaFree(pl->d_att); cudaFree(pl->d_acc); cudaFree(pl->d_dE);
+  delete pl;
+}
+
+extern "C" int brawl_cuda_destroy(brawl_cuda_t *h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  cudaFree(h->d_lat); cudaFree(h->d_V); cudaFree(h->d_stage); cudaFree(h->d_scratch); cudaFree(h->d_flag);
+  cudaFree(h->d_beta); cudaFree(h->d_small);
+  brw_free_plan((BrwPlan *)h->mc_plan[0]); brw_free_plan((BrwPlan *)h->mc_plan[1]);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete[] h->hV;
+  delete h;
+  return 0;
+}
+extern "C" int brawl_cuda_set_stream(brawl_cuda_t *h, void *s) {
+  BRW_ENTER(h);
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  return 0;
+}
+extern "C" int brawl_cuda_synchronize(brawl_cuda_t *h) {
+  BRW_ENTER(h);
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+extern "C" int brawl_cuda_info(brawl_cuda_t *h, int64_t *n_atoms, int64_t *grid_bytes, int *z_total, int *n_replicas) {
+  if (!h) return brw_fail("null handle");
+  if (n_atoms) *n_atoms = h->g.n_sites;
+  if (grid_bytes) *grid_bytes = h->grid_cells;
+  if (z_total) *z_total = h->g.ztot;
+  if (n_replicas) *n_replicas = h->n_replicas;
+  return 0;
+}
+
+static int brw_check_flag(brawl_cuda_ctx *h, const char *what) {
+  int f = 0;
+  BRW_CUDA(cudaMemcpyAsync(&f, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  if (f) {
+    BRW_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+    if (f & 1) return brw_fail("%s: species outside 1..n_species on a lattice site", what);
+    if (f & 2) return brw_fail("%s: non-zero entry on a cell that is not a lattice site", what);
+    return brw_fail("%s: index does not address a lattice site", what);
+  }
+  return 0;
+}
+
+// small device buffer for scalars / results
+static int brw_small(brawl_cuda_ctx *h, size_t bytes) {
+  if (h->small_bytes >= bytes) return 0;
+  if (h->d_small) BRW_CUDA(cudaFree(h->d_small));
+  h->d_small = nullptr; h->small_bytes = 0;
+  size_t nb = bytes < 65536 ? 65536 : bytes;
+  BRW_CUDA(cudaMalloc(&h->d_small, nb));
+  h->small_bytes = nb;
+  return 0;
+}
+
+// ---- configuration transfer -------------------------------------------------------------------------
+extern "C" int brawl_cuda_set_config(brawl_cuda_t *h, int first, int n, const int8_t *grids) {
+  BRW_ENTER(h);
+  if (!grids) return brw_fail("null grid pointer");
+  if (n < 1 || first < 0 || first + n > h->n_replicas) return brw_fail("replica range [%d,%d) out of [0,%d)", first, first + n, h->n_replicas);
+  // chunk so that the staging buffer stays <= 256 MiB
+  int per = (int)std::max<int64_t>(1, (256LL << 20) / h->grid_cells);
+  for (int r0 = 0; r0 < n; r0 += per) {
+    int m = std::min(per, n - r0);
+    size_t bytes = (size_t)h->grid_cells * m;
+    if (brw_ensure_stage(h, bytes)) return 1;
+    BRW_CUDA(cudaMemcpyAsync(h->d_stage, grids + (size_t)r0 * h->grid_cells, bytes, cudaMemcpyHostToDevice, h->stream));
+    brw_pack_kernel<<<grid_for((long)bytes, 256), 256, 0, h->stream>>>(h->g, h->d_stage, h->d_lat + (size_t)(first + r0) * h->g.n_sites, m, h->d_flag);
+    BRW_LAUNCH_CHECK("brw_pack_kernel");
+  }
+  return brw_check_flag(h, "set_config");
+}
+extern "C" int brawl_cuda_get_config(brawl_cuda_t *h, int first, int n, int8_t *grids) {
+  BRW_ENTER(h);
+  if (!grids) return brw_fail("null grid pointer");
+  if (n < 1 || first < 0 || first + n > h->n_replicas) return brw_fail("replica range [%d,%d) out of [0,%d)", first, first + n, h->n_replicas);
+  int per = (int)std::max<int64_t>(1, (256LL << 20) / h->grid_cells);
+  for (int r0 = 0; r0 < n; r0 += per) {
+    int m = std::min(per, n - r0);
+    size_t bytes = (size_t)h->grid_cells * m;
+    if (brw_ensure_stage(h, bytes)) return 1;
+    brw_unpack_kernel<<<grid_for((long)bytes, 256), 256, 0, h->stream>>>(h->g, h->d_lat + (size_t)(first + r0) * h->g.n_sites, h->d_stage, m);
+    BRW_LAUNCH_CHECK("brw_unpack_kernel");
+    BRW_CUDA(cudaMemcpyAsync(grids + (size_t)r0 * h->grid_cells, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+    BRW_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+extern "C" int brawl_cuda_copy_replica(brawl_cuda_t *h, int src, int dst) {
+  BRW_ENTER(h);
+  BRW_REPLICA(h, src); BRW_REPLICA(h, dst);
+  if (src == dst) return 0;
+  BRW_CUDA(cudaMemcpyAsync(h->d_lat + (size_t)dst * h->g.n_sites, h->d_lat + (size_t)src * h->g.n_sites, h->g.n_sites,
+                           cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+
+// ---- Hamiltonian ---------------------------------------------------------------------------------------
+// device-side: energies of replicas [first, first+n) into d_out[n] (no host sync)
+static int brw_total_energy_dev(brawl_cuda_ctx *h, int first, int n, int exact, double *d_out) {
+  const BrwGeom &g = h->g;
+  if (exact) {
+    int per = (int)std::max<long>(1, (long)((256LL << 20) / ((long)g.n_sites * 8)));
+    for (int r0 = 0; r0 < n; r0 += per) {
+      int m = std::min(per, n - r0);
+      if (brw_ensure_scratch(h, (size_t)g.n_sites * m * sizeof(double))) return 1;
+      const uint8_t *L = h->d_lat + (size_t)(first + r0) * g.n_sites;
+      brw_site_energy_kernel<<<grid_for((long)g.n_sites * m, 256), 256, 0, h->stream>>>(g, h->d_V, L, h->d_scratch, m);
+      BRW_LAUNCH_CHECK("brw_site_energy_kernel");
+      brw_ordered_sum_kernel<<<m, 256, 0, h->stream>>>(h->d_scratch, g.n_sites, d_out + r0);
+      BRW_LAUNCH_CHECK("brw_ordered_sum_kernel");
+    }
+  } else {
+    int nblk = std::max(1, std::min(592, (g.n_sites + 255) / 256));
+    if (n >= 148) nblk = std::min(nblk, 8);
+    if (brw_ensure_scratch(h, (size_t)nblk * n * sizeof(double))) return 1;
+    dim3 grid(nblk, n);
+    brw_energy_partial_kernel<<<grid, 256, 0, h->stream>>>(g, h->d_V, h->d_lat + (size_t)first * g.n_sites, h->d_scratch, nblk);
+    BRW_LAUNCH_CHECK("brw_energy_partial_kernel");
+    brw_tree_final_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_scratch, nblk, d_out, n);
+    BRW_LAUNCH_CHECK("brw_tree_final_kernel");
+  }
+  return 0;
+}
+extern "C" int brawl_cuda_total_energy(brawl_cuda_t *h, int first, int n, int exact, double *energies) {
+  BRW_ENTER(h);
+  if (!energies) return brw_fail("null output pointer");
+  if (n < 1 || first < 0 || first + n > h->n_replicas) return brw_fail("replica range [%d,%d) out of [0,%d)", first, first + n, h->n_replicas);
+  if (brw_small(h, sizeof(double) * n)) return 1;
+  if (brw_total_energy_dev(h, first, n, exact, (double *)h->d_small)) return 1;
+  BRW_CUDA(cudaMemcpyAsync(energies, h->d_small, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+extern "C" int brawl_cuda_site_energies(brawl_cuda_t *h, int replica, double *out) {
+  BRW_ENTER(h);
+  BRW_REPLICA(h, replica);
+  if (!out) return brw_fail("null output pointer");
+  const BrwGeom &g = h->g;
+  size_t nb = ((size_t)g.n_sites + (size_t)h->grid_cells) * sizeof(double);
+  if (brw_ensure_scratch(h, nb)) return 1;
+  double *d_e = h->d_scratch, *d_grid = h->d_scratch + g.n_sites;
+  brw_site_energy_kernel<<<grid_for(g.n_sites, 256), 256, 0, h->stream>>>(g, h->d_V, h->d_lat + (size_t)replica * g.n_sites, d_e, 1);
+  BRW_LAUNCH_CHECK("brw_site_energy_kernel");
+  brw_site_energy_to_grid_kernel<<<grid_for(h->grid_cells, 256), 256, 0, h->stream>>>(g, d_e, d_grid);
+  BRW_LAUNCH_CHECK("brw_site_energy_to_grid_kernel");
+  BRW_CUDA(cudaMemcpyAsync(out, d_grid, (size_t)h->grid_cells * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+extern "C" int brawl_cuda_pair_dE(brawl_cuda_t *h, int replica, int64_t n, const int32_t *i1, const int32_t *i2, double *dE) {
+  BRW_ENTER(h);
+  BRW_REPLICA(h, replica);
+  if (n < 0 || (n > 0 && (!i1 || !i2 || !dE))) return brw_fail("bad pair arrays");
+  if (n == 0) return 0;
+  size_t nb = (size_t)n * (2 * sizeof(int32_t) + sizeof(double));
+  if (brw_ensure_scratch(h, nb)) return 1;
+  double *d_dE = h->d_scratch;
+  int32_t *d_i1 = (int32_t *)(d_dE + n), *d_i2 = d_i1 + n;
+  BRW_CUDA(cudaMemcpyAsync(d_i1, i1, n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(d_i2, i2, n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  brw_pair_dE_kernel<<<grid_for(n, 128), 128, 0, h->stream>>>(h->g, h->d_V, h->d_lat + (size_t)replica * h->g.n_sites, n, d_i1, d_i2, d_dE, h->d_flag);
+  BRW_LAUNCH_CHECK("brw_pair_dE_kernel");
+  BRW_CUDA(cudaMemcpyAsync(dE, d_dE, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return brw_check_flag(h, "pair_dE");
+}
+
+// ---- Metropolis replay -----------------------------------------------------------------------------------
+extern "C" int brawl_cuda_metropolis_replay_sampled(brawl_cuda_t *h, int replica, double beta, int64_t n_trials,
+                                                    int64_t n_sample, int nbr_swap, uint32_t *mt, int64_t *n_accept,
+                                                    double *energies) {
+  BRW_ENTER(h);
+  BRW_REPLICA(h, replica);
+  if (!mt) return brw_fail("null MT19937 state");
+  if (n_trials < 0 || n_sample < 0) return brw_fail("negative trial count");
+  if (n_sample > 0 && !energies) return brw_fail("null energies output");
+  if (mt[624] > 625) return brw_fail("corrupt MT19937 state (mti=%u)", mt[624]);
+  const BrwGeom &g = h->g;
+  int64_t ns = n_sample > 0 ? n_trials / n_sample : 0;
+  size_t nb = 625 * sizeof(uint32_t) + 16 + (size_t)ns * sizeof(double);
+  if (brw_small(h, nb)) return 1;
+  if (brw_ensure_scratch(h, (size_t)g.n_sites * sizeof(double))) return 1;
+  unsigned long long *d_acc = (unsigned long long *)h->d_small;
+  double *d_en = (double *)(d_acc + 1);
+  uint32_t *d_mt = (uint32_t *)(d_en + ns);
+  BRW_CUDA(cudaMemcpyAsync(d_mt, mt, 625 * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  brw_metropolis_replay_kernel<<<1, 256, 0, h->stream>>>(g, h->d_V, h->d_lat + (size_t)replica * g.n_sites, beta, (long)n_trials,
+                                                         (long)n_sample, nbr_swap, d_mt, d_acc, d_en, h->d_scratch);
+  BRW_LAUNCH_CHECK("brw_metropolis_replay_kernel");
+  unsigned long long acc = 0;
+  BRW_CUDA(cudaMemcpyAsync(mt, d_mt, 625 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(&acc, d_acc, sizeof acc, cudaMemcpyDeviceToHost, h->stream));
+  if (ns > 0) BRW_CUDA(cudaMemcpyAsync(energies, d_en, ns * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  if (n_accept) *n_accept = (int64_t)acc;
+  return 0;
+}
+extern "C" int brawl_cuda_metropolis_replay(brawl_cuda_t *h, int replica, double beta, int64_t n_trials, int nbr_swap,
+                                            uint32_t *mt, int64_t *n_accept) {
+  return brawl_cuda_metropolis_replay_sampled(h, replica, beta, n_trials, 0, nbr_swap, mt, n_accept, nullptr);
+}
+
+// ---- production Metropolis ---------------------------------------------------------------------------------
+static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
+  BrwPlan *&slot = *(BrwPlan **)&h->mc_plan[nbr_swap ? 1 : 0];
+  if (slot && slot->valid) { *out = slot; return 0; }
+  if (slot) { brw_free_plan(slot); slot = nullptr; }
+  const BrwGeom &g = h->g;
+  BrwPlan *pl = new BrwPlan();
+  pl->nbr_swap = nbr_swap;
+  BrwBoxParams &p = pl->p;
+  // reach of the Hamiltonian
+  int rmax = 0;
+  for (int k = 0; k < g.ztot; k++) for (int c = 0; c < 3; c++) rmax = std::max(rmax, std::abs((int)g.off[k][c]));
+  int m = rmax + (nbr_swap ? 1 : 0);
+  m += m & 1;
+  std::vector<std::array<int, 3>> first;
+  {
+    static const signed char sc[6][3] = {{0,0,1},{0,1,0},{1,0,0},{0,0,-1},{0,-1,0},{-1,0,0}};
+    static const signed char bcc[8][3] = {{1,1,1},{1,1,-1},{1,-1,1},{1,-1,-1},{-1,1,1},{-1,1,-1},{-1,-1,1},{-1,-1,-1}};
+    static const signed char fcc[12][3] = {{0,1,1},{0,1,-1},{0,-1,1},{0,-1,-1},{1,1,0},{1,-1,0},{1,0,1},{1,0,-1},{-1,1,0},{-1,-1,0},{-1,0,1},{-1,0,-1}};
+    int n = g.lattice == 0 ? 6 : g.lattice == 1 ? 8 : 12;
+    for (int i = 0; i < n; i++) {
+      const signed char *e = g.lattice == 0 ? sc[i] : g.lattice == 1 ? bcc[i] : fcc[i];
+      first.push_back({e[0], e[1], e[2]});
+    }
+  }
+  std::vector<int4> classes, disp;
+  int P = 0;
+  bool feasible = g.lattice != 0 &&   // simple cubic wraps neighbours with modulus n (reference quirk): chain kernel only
+                  brw_choose_period(g, nbr_swap, first, 16, P, classes, disp);
+  int B[3] = {g.gx, g.gy, g.gz};
+  if (feasible) {
+    for (int d = 0; d < 3; d++) if (B[d] < 2 * m + P) feasible = false;
+  }
+  if (feasible) {
+    // box extents: user override or automatic halving of the longest edge
+    const size_t budget = 200 * 1024;
+    size_t fixed = (size_t)g.S * g.S * g.n_shells * 16 * 8 + 2 * g.ztot * 4 + 2 * sizeof(BrwStepParams) + 32 * 8 + 64;
+    auto sites = [&](const int *b) { return (size_t)b[0] * b[1] * b[2] / (g.lattice == 1 ? 4 : 2); };
+    auto trials = [&](const int *b) { long M = 1; for (int d = 0; d < 3; d++) M *= (b[d] - 2 * m) / P; return M; };
+    if (h->tune_box[0] > 0) {
+      for (int d = 0; d < 3; d++) {
+        int G = d == 0 ? g.gx : d == 1 ? g.gy : g.gz;
+        B[d] = h->tune_box[d];
+        if (B[d] < 2 * m + P || (B[d] & 1) || G % B[d]) { delete pl; return brw_fail("box extent %d invalid for axis %d (grid %d, need even divisor >= %d)", B[d], d, G, 2 * m + P); }
+      }
+      if (sites(B) + fixed > budget) { delete pl; return brw_fail("box does not fit in shared memory"); }
+    } else {
+      for (;;) {
+        long nbox = (long)(g.gx / B[0]) * (g.gy / B[1]) * (g.gz / B[2]) * h->n_replicas;
+        bool too_big = sites(B) + fixed > budget;
+        bool want_more = nbox < 120 && trials(B) >= 512;
+        if (!too_big && !want_more) break;
+        // halve the longest edge that can still be halved
+        int best = -1;
+        for (int d = 0; d < 3; d++) {
+          int nbd = B[d] / 2;
+          if ((B[d] % 4) == 0 && nbd >= 2 * m + P && (best < 0 || B[d] > B[best])) best = d;
+        }
+        if (best < 0) { if (too_big) feasible = false; break; }
+        B[best] /= 2;
+      }
+    }
+  }
+  if (feasible) {
+    p.P = P; p.m = m;
+    p.M = 1;
+    for (int d = 0; d < 3; d++) {
+      int G = d == 0 ? g.gx : d == 1 ? g.gy : g.gz;
+      p.B[d] = B[d]; p.nb[d] = G / B[d]; p.A[d] = (B[d] - 2 * m) / P; p.M *= p.A[d];
+    }
+    p.bxc = B[0] >> g.xs; p.byc = B[1] >> g.ys; p.bzc = B[2];
+    p.box_sites = p.bxc * p.byc * p.bzc;
+    p.n_classes = (int)classes.size(); p.n_disp = (int)disp.size();
+    p.boxes_per_replica = p.nb[0] * p.nb[1] * p.nb[2];
+    p.v_entries = g.S * g.S * g.n_shells;
+    int steps = h->tune_steps > 0 ? h->tune_steps : (p.box_sites + p.M - 1) / p.M;
+    p.steps = std::max(8, std::min(steps, 4096));
+    pl->threads = std::min(1024, ((p.M + 31) / 32) * 32);
+    pl->smem = (size_t)p.v_entries * 16 * 8 + (size_t)2 * g.ztot * 4 + 2 * sizeof(BrwStepParams) + 32 * 8 + p.box_sites;
+    // offset tables per x-parity of the centre site
+    std::vector<int> off(2 * g.ztot);
+    for (int par = 0; par < 2; par++)
+      for (int k = 0; k < g.ztot; k++) {
+        int dx = g.off[k][0], dy = g.off[k][1], dz = g.off[k][2];
+        int dxc = g.xs ? ((par + dx) >> 1) : dx;     // arithmetic shift = floor
+        int dyc = g.ys ? ((par + dy) >> 1) : dy;     // bcc: y parity == x parity
+        off[par * g.ztot + k] = (dz * p.byc + dyc) * p.bxc + dxc;
+      }
+    // lane-replicated V, layout [shell][centre][nbr][16]
+    std::vector<double> vrep((size_t)p.v_entries * 16);
+    for (int n = 0; n < g.n_shells; n++) for (int c = 0; c < g.S; c++) for (int s = 0; s < g.S; s++)
+      for (int l = 0; l < 16; l++) vrep[(((size_t)(n * g.S + c) * g.S) + s) * 16 + l] = h->hV[(n * g.S + s) * g.S + c];
+#define BRW_PLAN_CUDA(x) do { if (brw_cuda_check((x), #x)) { brw_free_plan(pl); return 1; } } while (0)
+    BRW_PLAN_CUDA(cudaMalloc(&pl->d_classes, classes.size() * sizeof(int4)));
+    BRW_PLAN_CUDA(cudaMalloc(&pl->d_disp, disp.size() * sizeof(int4)));
+    BRW_PLAN_CUDA(cudaMalloc(&pl->d_off, off.size() * sizeof(int)));
+    BRW_PLAN_CUDA(cudaMalloc(&pl->d_Vrep, vrep.size() * sizeof(double)));
+    BRW_PLAN_CUDA(cudaMemcpy(pl->d_classes, classes.data(), classes.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    BRW_PLAN_CUDA(cudaMemcpy(pl->d_disp, disp.data(), disp.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    BRW_PLAN_CUDA(cudaMemcpy(pl->d_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    BRW_PLAN_CUDA(cudaMemcpy(pl->d_Vrep, vrep.data(), vrep.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (nbr_swap) BRW_PLAN_CUDA(cudaFuncSetAttribute(brw_box_metropolis_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    else BRW_PLAN_CUDA(cudaFuncSetAttribute(brw_box_metropolis_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    pl->use_box = true;
+    pl->n_slots = p.boxes_per_replica * h->n_replicas;
+  } else {
+    pl->use_box = false;
+    pl->n_slots = h->n_replicas;
+  }
+  BRW_PLAN_CUDA(cudaMalloc(&pl->d_att, pl->n_slots * sizeof(unsigned long long)));
+  BRW_PLAN_CUDA(cudaMalloc(&pl->d_acc, pl->n_slots * sizeof(unsigned long long)));
+  BRW_PLAN_CUDA(cudaMalloc(&pl->d_dE, pl->n_slots * sizeof(double)));
+  BRW_PLAN_CUDA(cudaMemset(pl->d_att, 0, pl->n_slots * sizeof(unsigned long long)));
+  BRW_PLAN_CUDA(cudaMemset(pl->d_acc, 0, pl->n_slots * sizeof(unsigned long long)));
+  BRW_PLAN_CUDA(cudaMemset(pl->d_dE, 0, pl->n_slots * sizeof(double)));
+  pl->valid = true;
+  slot = pl;
+  *out = pl;
+  return 0;
+}
+
+extern "C" int brawl_cuda_metropolis_tune(brawl_cuda_t *h, int bx, int by, int bz, int steps) {
+  BRW_ENTER(h);
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  h->tune_box[0] = bx; h->tune_box[1] = by; h->tune_box[2] = bz; h->tune_steps = steps;
+  for (int i = 0; i < 2; i++) { brw_free_plan((BrwPlan *)h->mc_plan[i]); h->mc_plan[i] = nullptr; }
+  return 0;
+}
+extern "C" int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *o) {
+  BRW_ENTER(h);
+  BrwPlan *pl;
+  if (brw_build_plan(h, nbr_swap, &pl)) return 1;
+  if (o) {
+    o[0] = pl->use_box; o[1] = pl->p.P; o[2] = pl->p.m; o[3] = pl->p.B[0]; o[4] = pl->p.B[1]; o[5] = pl->p.B[2];
+    o[6] = pl->p.M; o[7] = pl->p.boxes_per_replica; o[8] = pl->p.n_disp; o[9] = pl->p.steps;
+  }
+  return 0;
+}
+
+extern "C" int brawl_cuda_metropolis_enqueue(brawl_cuda_t *h, const double *beta, int64_t n_trials, int nbr_swap,
+                                             uint64_t seed, uint64_t offset, uint64_t *next_offset,
+                                             int64_t *planned, int *n_launches) {
+  BRW_ENTER(h);
+  if (!beta) return brw_fail("null beta array");
+  if (n_trials < 0) return brw_fail("negative trial count");
+  BrwPlan *pl;
+  if (brw_build_plan(h, nbr_swap, &pl)) return 1;
+  if (!h->d_beta) BRW_CUDA(cudaMalloc(&h->d_beta, sizeof(double) * h->n_replicas));
+  BRW_CUDA(cudaMemcpyAsync(h->d_beta, beta, sizeof(double) * h->n_replicas, cudaMemcpyHostToDevice, h->stream));
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  int launches = 0;
+  int64_t done = 0;
+  if (pl->use_box) {
+    const BrwBoxParams &p = pl->p;
+    const int64_t per_phase = (int64_t)p.M * p.steps * p.boxes_per_replica;
+    int64_t phases = (n_trials + per_phase - 1) / per_phase;
+    for (int64_t ph = 0; ph < phases; ph++) {
+      uint64_t phase = offset + (uint64_t)ph;
+      uint32_t kk1 = k1 ^ (uint32_t)(phase >> 32) * 0x9E3779B9u;
+      if (nbr_swap)
+        brw_box_metropolis_kernel<1><<<pl->n_slots, pl->threads, pl->smem, h->stream>>>(
+            h->g, p, h->d_lat, h->d_beta, pl->d_Vrep, pl->d_off, pl->d_classes, pl->d_disp, k0, kk1, (uint32_t)phase,
+            pl->d_att, pl->d_acc, pl->d_dE);
+      else
+        brw_box_metropolis_kernel<0><<<pl->n_slots, pl->threads, pl->smem, h->stream>>>(
+            h->g, p, h->d_lat, h->d_beta, pl->d_Vrep, pl->d_off, pl->d_classes, pl->d_disp, k0, kk1, (uint32_t)phase,
+            pl->d_att, pl->d_acc, pl->d_dE);
+      BRW_LAUNCH_CHECK("brw_box_metropolis_kernel");
+      launches++;
+    }
+    done = phases * per_phase;
+    if (next_offset) *next_offset = offset + (uint64_t)phases;
+  } else {
+    if (n_trials > 0) {
+      brw_chain_metropolis_kernel<<<(h->n_replicas + 63) / 64, 64, 0, h->stream>>>(
+          h->g, h->d_V, h->d_lat, h->d_beta, h->n_replicas, (long)n_trials, nbr_swap, k0, k1, (uint32_t)offset,
+          (uint32_t)(offset >> 32), pl->d_att, pl->d_acc, pl->d_dE);
+      BRW_LAUNCH_CHECK("brw_chain_metropolis_kernel");
+      launches++;
+    }
+    done = n_trials;
+    if (next_offset) *next_offset = offset + 1;
+  }
+  if (planned) *planned = done;
+  if (n_launches) *n_launches = launches;
+  h->last_plan = nbr_swap ? 1 : 0;
+  return 0;
+}
+
+extern "C" int brawl_cuda_metropolis_counters(brawl_cuda_t *h, int reset, int64_t *att, int64_t *acc, double *dE) {
+  BRW_ENTER(h);
+  BrwPlan *pl = (BrwPlan *)h->mc_plan[h->last_plan];
+  if (!pl || !pl->valid) return brw_fail("no Metropolis run has been enqueued on this handle");
+  int n = pl->n_slots, per = n / h->n_replicas;
+  std::vector<unsigned long long> a(n), c(n);
+  std::vector<double> d(n);
+  BRW_CUDA(cudaMemcpyAsync(a.data(), pl->d_att, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(c.data(), pl->d_acc, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(d.data(), pl->d_dE, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (reset) {
+    BRW_CUDA(cudaMemsetAsync(pl->d_att, 0, n * sizeof(unsigned long long), h->stream));
+    BRW_CUDA(cudaMemsetAsync(pl->d_acc, 0, n * sizeof(unsigned long long), h->stream));
+    BRW_CUDA(cudaMemsetAsync(pl->d_dE, 0, n * sizeof(double), h->stream));
+  }
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < h->n_replicas; r++) {
+    unsigned long long A = 0, C = 0; double D = 0.0;
+    for (int b = 0; b < per; b++) { A += a[r * per + b]; C += c[r * per + b]; D += d[r * per + b]; }
+    if (att) att[r] = (int64_t)A;
+    if (acc) acc[r] = (int64_t)C;
+    if (dE) dE[r] = D;
+  }
+  return 0;
+}
+
+extern "C" int brawl_cuda_metropolis_run(brawl_cuda_t *h, const double *beta, int64_t n_trials, int nbr_swap,
+                                         uint64_t seed, uint64_t offset, uint64_t *next_offset, int64_t *att,
+                                         int64_t *acc, double *dE) {
+  BRW_ENTER(h);
+  BrwPlan *pl;
+  if (brw_build_plan(h, nbr_swap, &pl)) return 1;
+  h->last_plan = nbr_swap ? 1 : 0;
+  if (brawl_cuda_metropolis_counters(h, 1, nullptr, nullptr, nullptr)) return 1;   // zero
+  if (brawl_cuda_metropolis_enqueue(h, beta, n_trials, nbr_swap, seed, offset, next_offset, nullptr, nullptr)) return 1;
+  return brawl_cuda_metropolis_counters(h, 1, att, acc, dE);
+}
+
+// ---- SRO ------------------------------------------------------------------------------------------------------
+// WC shell radii as lattice_shells computes them (src/analytics.f90:205-275): sorted distinct
+// single-precision distances from the origin cell to every lattice site of the box; then every raw
+// offset of the reference's cube scan (half-width min(n,5), :336-394) that lands on a site and matches
+// a shell radius within 1e-3.
+static void brw_sro_offsets(const BrwGeom &g, int wc_range, std::vector<int4> &out, std::vector<double> &radii) {
+  std::vector<double> all;
+  for (int z = 0; z < g.gz; z++) for (int y = 0; y < g.gy; y++) for (int x = 0; x < g.gx; x++)
+    if (brw_is_site(g, x, y, z)) all.push_back((double)sqrtf((float)(z * z) + (float)(y * y) + (float)(x * x)));
+  std::sort(all.begin(), all.end());
+  radii.clear();
+  // the reference's array is padded with zeros, so 0.0 is always the first distinct value
+  radii.push_back(0.0);
+  for (size_t i = 0; i + 1 < all.size() && (int)radii.size() < wc_range; i++)
+    if (std::fabs(all[i] - all[i + 1]) >= 1e-3 && all[i] > radii.back() + 1e-3) radii.push_back(all[i]);
+  if ((int)radii.size() < wc_range && !all.empty() && all.back() > radii.back() + 1e-3) { /* last element is never emitted by the reference loop */ }
+  while ((int)radii.size() < wc_range) radii.push_back(0.0);   // shells(l) stays 0.0 when the box is too small
+  int l1 = std::min(g.gx / 2, 5), l2 = std::min(g.gy / 2, 5), l3 = std::min(g.gz / 2, 5);
+  out.clear();
+  for (int dz = -l3; dz <= l3; dz++) for (int dy = -l2; dy <= l2; dy++) for (int dx = -l1; dx <= l1; dx++) {
+    if (!brw_is_site(g, dx & 1 ? 1 : 0, dy & 1 ? 1 : 0, dz & 1 ? 1 : 0)) continue;   // offset between two sites
+    double dist = std::sqrt((double)(dx * dx + dy * dy + dz * dz));
+    for (int l = 0; l < wc_range; l++)
+      if (std::fabs(dist - radii[l]) < 1e-3) out.push_back(make_int4(dx, dy, dz, l));
+  }
+}
+extern "C" int brawl_cuda_radial_counts(brawl_cuda_t *h, int replica, int wc_range, int64_t *cnt, int64_t *species_count) {
+  BRW_ENTER(h);
+  BRW_REPLICA(h, replica);
+  if (wc_range < 1 || wc_range > 64) return brw_fail("wc_range out of range");
+  if (!cnt || !species_count) return brw_fail("null output pointer");
+  const BrwGeom &g = h->g;
+  std::vector<int4> offs; std::vector<double> radii;
+  brw_sro_offsets(g, wc_range, offs, radii);
+  size_t n_cnt = (size_t)wc_range * g.S * g.S;
+  size_t nb = offs.size() * sizeof(int4) + (n_cnt + g.S + 2) * sizeof(unsigned long long) + 16;
+  if (brw_small(h, nb)) return 1;
+  unsigned long long *d_cnt = (unsigned long long *)h->d_small, *d_sc = d_cnt + n_cnt;
+  int4 *d_off = (int4 *)(d_cnt + ((n_cnt + g.S + 1) & ~(size_t)1));      // 16-byte aligned
+  BRW_CUDA(cudaMemsetAsync(d_cnt, 0, (n_cnt + g.S) * sizeof(unsigned long long), h->stream));
+  BRW_CUDA(cudaMemcpyAsync(d_off, offs.data(), offs.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+  size_t smem = (n_cnt + g.S) * sizeof(unsigned int);
+  brw_radial_counts_kernel<<<grid_for(g.n_sites, 256, 592), 256, smem, h->stream>>>(g, h->d_lat + (size_t)replica * g.n_sites, d_off,
+                                                                                     (int)offs.size(), wc_range, d_cnt, d_sc);
+  BRW_LAUNCH_CHECK("brw_radial_counts_kernel");
+  std::vector<unsigned long long> hc(n_cnt + g.S);
+  BRW_CUDA(cudaMemcpyAsync(hc.data(), d_cnt, hc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < n_cnt; i++) cnt[i] = (int64_t)hc[i];
+  for (int i = 0; i < g.S; i++) species_count[i] = (int64_t)hc[n_cnt + i];
+  return 0;
+}
+
+// ---- Wang-Landau -------------------------------------------------------------------------------------------------
+extern "C" int brawl_cuda_wl_sweeps_replay(brawl_cuda_t *h, int replica, double *lng, double *hist, const double *edges,
+                                           int bins, int win_lo, int win_hi, double wl_f, int64_t n_trials, int nbr_swap,
+                                           uint32_t *mt, int64_t *n_accept, double *e_final) {
+  BRW_ENTER(h);
+  BRW_REPLICA(h, replica);
+  if (!lng || !hist || !edges || !mt) return brw_fail("null array argument");
+  if (bins < 1 || win_lo < 1 || win_hi > bins || win_lo > win_hi) return brw_fail("bad energy window [%d,%d] for %d bins", win_lo, win_hi, bins);
+  const BrwGeom &g = h->g;
+  int nh = win_hi - win_lo + 1;
+  size_t nb = sizeof(double) * (bins + nh + 2) + 625 * 4 + 16;
+  if (brw_small(h, nb)) return 1;
+  double *d_lng = (double *)h->d_small, *d_hist = d_lng + bins, *d_e = d_hist + nh;   // d_e[0]=start, [1]=final
+  unsigned long long *d_acc = (unsigned long long *)(d_e + 2);
+  uint32_t *d_mt = (uint32_t *)(d_acc + 1);
+  // e_unswapped = full_energy(config) at entry (:547), exact order
+  if (brw_ensure_scratch(h, (size_t)g.n_sites * sizeof(double))) return 1;
+  brw_site_energy_kernel<<<grid_for(g.n_sites, 256), 256, 0, h->stream>>>(g, h->d_V, h->d_lat + (size_t)replica * g.n_sites, h->d_scratch, 1);
+  BRW_LAUNCH_CHECK("brw_site_energy_kernel");
+  brw_ordered_sum_kernel<<<1, 256, 0, h->stream>>>(h->d_scratch, g.n_sites, d_e);
+  BRW_LAUNCH_CHECK("brw_ordered_sum_kernel");
+  double e_start = 0.0;
+  BRW_CUDA(cudaMemcpyAsync(&e_start, d_e, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(d_lng, lng, sizeof(double) * bins, cudaMemcpyHostToDevice, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(d_hist, hist, sizeof(double) * nh, cudaMemcpyHostToDevice, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(d_mt, mt, 625 * 4, cudaMemcpyHostToDevice, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  int hist_every = (int)(0.02 * (double)(float)g.n_sites);          // INT(0.02_real64*REAL(n_atoms)), :605
+  double range = edges[bins] - edges[0];
+  {
+    // the reference indexes wl_logdos(ibin) unguarded; its walkers are inside their window by
+    // construction (enter_energy_window, :643-741).  Refuse anything else instead of corrupting memory.
+    int ib = (int)(((e_start - edges[0]) / range) * (double)bins) + 1;
+    if (!(e_start >= edges[0]) || ib < win_lo || ib > win_hi)
+      return brw_fail("walker energy %.10g (bin %d) is outside its window [%d,%d]", e_start, ib, win_lo, win_hi);
+  }
+  brw_wl_replay_kernel<<<1, 32, 0, h->stream>>>(g, h->d_V, h->d_lat + (size_t)replica * g.n_sites, d_lng, d_hist, edges[0], range, bins,
+                                                win_lo, win_hi, wl_f, (long)n_trials, hist_every, nbr_swap, e_start, d_mt, d_acc, d_e + 1);
+  BRW_LAUNCH_CHECK("brw_wl_replay_kernel");
+  unsigned long long acc = 0; double ef = 0.0;
+  BRW_CUDA(cudaMemcpyAsync(lng, d_lng, sizeof(double) * bins, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(hist, d_hist, sizeof(double) * nh, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(mt, d_mt, 625 * 4, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(&acc, d_acc, sizeof acc, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(&ef, d_e + 1, sizeof ef, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  if (n_accept) *n_accept = (int64_t)acc;
+  if (e_final) *e_final = ef;
+  return 0;
+}
+
+extern "C" int brawl_cuda_wl_sweeps(brawl_cuda_t *h, int n_walkers, double *lng, double *hist, int on_device,
+                                    const double *edges, int bins, const int32_t *win_lo, const int32_t *win_hi,
+                                    int hist_stride, double wl_f, int64_t n_trials, int nbr_swap, uint64_t seed,
+                                    uint64_t offset, int64_t *n_accept, double *e_final) {
+  BRW_ENTER(h);
+  if (n_walkers < 1 || n_walkers > h->n_replicas) return brw_fail("n_walkers %d out of 1..%d", n_walkers, h->n_replicas);
+  if (!lng || !hist || !edges || !win_lo || !win_hi) return brw_fail("null array argument");
+  for (int w = 0; w < n_walkers; w++)
+    if (win_lo[w] < 1 || win_hi[w] > bins || win_lo[w] > win_hi[w] || win_hi[w] - win_lo[w] + 1 > hist_stride)
+      return brw_fail("bad energy window [%d,%d] for walker %d", win_lo[w], win_hi[w], w);
+  const BrwGeom &g = h->g;
+  size_t n_l = (size_t)n_walkers * bins, n_h = (size_t)n_walkers * hist_stride;
+  size_t nb = sizeof(double) * (on_device ? 0 : n_l + n_h) + sizeof(double) * n_walkers + sizeof(unsigned long long) * n_walkers + 2 * sizeof(int) * n_walkers + 64;
+  if (brw_small(h, nb)) return 1;
+  double *d_e = (double *)h->d_small;
+  unsigned long long *d_acc = (unsigned long long *)(d_e + n_walkers);
+  int *d_lo = (int *)(d_acc + n_walkers), *d_hi = d_lo + n_walkers;
+  double *d_lng = on_device ? lng : (double *)(d_hi + n_walkers + (n_walkers & 1)), *d_hist = on_device ? hist : d_lng + n_l;
+  if (!on_device) {
+    BRW_CUDA(cudaMemcpyAsync(d_lng, lng, sizeof(double) * n_l, cudaMemcpyHostToDevice, h->stream));
+    BRW_CUDA(cudaMemcpyAsync(d_hist, hist, sizeof(double) * n_h, cudaMemcpyHostToDevice, h->stream));
+  }
+  BRW_CUDA(cudaMemcpyAsync(d_lo, win_lo, sizeof(int) * n_walkers, cudaMemcpyHostToDevice, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(d_hi, win_hi, sizeof(int) * n_walkers, cudaMemcpyHostToDevice, h->stream));
+  if (brw_total_energy_dev(h, 0, n_walkers, 1, d_e)) return 1;                    // :547
+  int hist_every = (int)(0.02 * (double)(float)g.n_sites);
+  double range = edges[bins] - edges[0];
+  {
+    std::vector<double> e0(n_walkers);
+    BRW_CUDA(cudaMemcpyAsync(e0.data(), d_e, sizeof(double) * n_walkers, cudaMemcpyDeviceToHost, h->stream));
+    BRW_CUDA(cudaStreamSynchronize(h->stream));
+    for (int w = 0; w < n_walkers; w++) {
+      int ib = (int)(((e0[w] - edges[0]) / range) * (double)bins) + 1;
+      if (!(e0[w] >= edges[0]) || ib < win_lo[w] || ib > win_hi[w])
+        return brw_fail("walker %d energy %.10g (bin %d) is outside its window [%d,%d]", w, e0[w], ib, win_lo[w], win_hi[w]);
+    }
+  }
+  brw_wl_walker_kernel<<<(n_walkers + 31) / 32, 32, 0, h->stream>>>(g, h->d_V, h->d_lat, d_lng, d_hist, edges[0], range, bins, d_lo, d_hi,
+                                                                    hist_stride, wl_f, (long)n_trials, hist_every, nbr_swap, (uint32_t)seed,
+                                                                    (uint32_t)(seed >> 32), (uint32_t)offset, (uint32_t)(offset >> 32),
+                                                                    n_walkers, d_e, d_acc);
+  BRW_LAUNCH_CHECK("brw_wl_walker_kernel");
+  std::vector<unsigned long long> acc(n_walkers);
+  if (!on_device) {
+    BRW_CUDA(cudaMemcpyAsync(lng, d_lng, sizeof(double) * n_l, cudaMemcpyDeviceToHost, h->stream));
+    BRW_CUDA(cudaMemcpyAsync(hist, d_hist, sizeof(double) * n_h, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (n_accept) BRW_CUDA(cudaMemcpyAsync(acc.data(), d_acc, sizeof(unsigned long long) * n_walkers, cudaMemcpyDeviceToHost, h->stream));
+  if (e_final) BRW_CUDA(cudaMemcpyAsync(e_final, d_e, sizeof(double) * n_walkers, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  if (n_accept) for (int w = 0; w < n_walkers; w++) n_accept[w] = (int64_t)acc[w];
+  return 0;
+}
+
+extern "C" int brawl_cuda_wl_window_average(brawl_cuda_t *h, double *dev_array, int len, int walkers_per_window, int n_windows, double divisor) {
+  BRW_ENTER(h);
+  if (!dev_array || len < 1 || walkers_per_window < 1 || n_windows < 1) return brw_fail("bad window-average arguments");
+  brw_wl_window_average_kernel<<<(n_windows * len + 127) / 128, 128, 0, h->stream>>>(dev_array, len, walkers_per_window, n_windows, divisor);
+  BRW_LAUNCH_CHECK("brw_wl_window_average_kernel");
+  return 0;
+}
+
+// ---- nested sampling ------------------------------------------------------------------------------------------------
+extern "C" int brawl_cuda_ns_walk_replay(brawl_cuda_t *h, int replica, double *energy, double e_limit, int64_t n_steps,
+                                         uint32_t *mt, int64_t *n_accept) {
+  BRW_ENTER(h);
+  BRW_REPLICA(h, replica);
+  if (!energy || !mt) return brw_fail("null argument");
+  if (brw_small(h, 625 * 4 + 32)) return 1;
+  double *d_e = (double *)h->d_small;
+  unsigned long long *d_acc = (unsigned long long *)(d_e + 1);
+  uint32_t *d_mt = (uint32_t *)(d_acc + 1);
+  BRW_CUDA(cudaMemcpyAsync(d_e, energy, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(d_mt, mt, 625 * 4, cudaMemcpyHostToDevice, h->stream));
+  brw_ns_replay_kernel<<<1, 32, 0, h->stream>>>(h->g, h->d_V, h->d_lat + (size_t)replica * h->g.n_sites, d_e, e_limit, (long)n_steps, d_mt, d_acc);
+  BRW_LAUNCH_CHECK("brw_ns_replay_kernel");
+  unsigned long long acc = 0;
+  BRW_CUDA(cudaMemcpyAsync(energy, d_e, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(mt, d_mt, 625 * 4, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(&acc, d_acc, sizeof acc, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  if (n_accept) *n_accept = (int64_t)acc;
+  return 0;
+}
+extern "C" int brawl_cuda_ns_walk(brawl_cuda_t *h, int n_walkers, const int32_t *ids, double *energies, const double *e_limit,
+                                  int64_t n_steps, uint64_t seed, uint64_t offset, int64_t *n_accept) {
+  BRW_ENTER(h);
+  if (n_walkers < 1) return brw_fail("n_walkers must be >= 1");
+  if (!ids || !energies || !e_limit) return brw_fail("null array argument");
+  std::vector<char> used(h->n_replicas, 0);
+  for (int w = 0; w < n_walkers; w++) {
+    if (ids[w] < 0 || ids[w] >= h->n_replicas) return brw_fail("walker id %d out of range", ids[w]);
+    if (used[ids[w]]) return brw_fail("walker id %d listed twice", ids[w]);
+    used[ids[w]] = 1;
+  }
+  size_t nb = (size_t)n_walkers * (2 * sizeof(double) + sizeof(unsigned long long) + sizeof(int)) + 64;
+  if (brw_small(h, nb)) return 1;
+  double *d_e = (double *)h->d_small, *d_lim = d_e + n_walkers;
+  unsigned long long *d_acc = (unsigned long long *)(d_lim + n_walkers);
+  int *d_ids = (int *)(d_acc + n_walkers);
+  BRW_CUDA(cudaMemcpyAsync(d_e, energies, sizeof(double) * n_walkers, cudaMemcpyHostToDevice, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(d_lim, e_limit, sizeof(double) * n_walkers, cudaMemcpyHostToDevice, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(d_ids, ids, sizeof(int) * n_walkers, cudaMemcpyHostToDevice, h->stream));
+  brw_ns_walker_kernel<<<(n_walkers + 31) / 32, 32, 0, h->stream>>>(h->g, h->d_V, h->d_lat, d_ids, d_e, d_lim, (long)n_steps, (uint32_t)seed,
+                                                                    (uint32_t)(seed >> 32), (uint32_t)offset, (uint32_t)(offset >> 32),
+                                                                    n_walkers, d_acc);
+  BRW_LAUNCH_CHECK("brw_ns_walker_kernel");
+  std::vector<unsigned long long> acc(n_walkers);
+  BRW_CUDA(cudaMemcpyAsync(energies, d_e, sizeof(double) * n_walkers, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(acc.data(), d_acc, sizeof(unsigned long long) * n_walkers, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  if (n_accept) for (int w = 0; w < n_walkers; w++) n_accept[w] = (int64_t)acc[w];
+  return 0;
+}

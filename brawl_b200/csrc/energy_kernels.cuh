@@ -1,0 +1,167 @@
+// energy_kernels.cuh -- Hamiltonian kernels: per-site nbr_energy, full-lattice energy (exact
+// reference order or deterministic tree), per-swap dE batch, SRO pair counts, and the
+// reference-grid <-> compact-lattice converters.  Included by brawl_cuda.cu.
+#pragma once
+#include "brawl_common.cuh"
+
+// ---- layout conversion -----------------------------------------------------------------------
+// grid[z][y][x] int8 (reference layout, species 1..S, 0 off-site) -> compact uint8 species 0..S-1.
+// flag bit0: bad species on a site; bit1: non-zero off-site cell.
+__global__ void brw_pack_kernel(BrwGeom g, const int8_t *__restrict__ grid, uint8_t *__restrict__ lat, int n_rep,
+                                int *flag) {
+  const long cells = (long)g.gx * g.gy * g.gz;
+  const long total = cells * n_rep;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i / cells, c = i - r * cells;
+    int x = (int)(c % g.gx), y = (int)((c / g.gx) % g.gy), z = (int)(c / ((long)g.gx * g.gy));
+    int v = grid[i];
+    if (brw_is_site(g, x, y, z)) {
+      if (v < 1 || v > g.S) { atomicOr(flag, 1); v = 1; }
+      lat[r * g.n_sites + brw_grid_to_compact(g, x, y, z)] = (uint8_t)(v - 1);
+    } else if (v != 0) atomicOr(flag, 2);
+  }
+}
+__global__ void brw_unpack_kernel(BrwGeom g, const uint8_t *__restrict__ lat, int8_t *__restrict__ grid, int n_rep) {
+  const long cells = (long)g.gx * g.gy * g.gz;
+  const long total = cells * n_rep;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i / cells, c = i - r * cells;
+    int x = (int)(c % g.gx), y = (int)((c / g.gx) % g.gy), z = (int)(c / ((long)g.gx * g.gy));
+    grid[i] = brw_is_site(g, x, y, z) ? (int8_t)(lat[r * g.n_sites + brw_grid_to_compact(g, x, y, z)] + 1) : (int8_t)0;
+  }
+}
+
+// ---- per-site energies -----------------------------------------------------------------------
+// out[r*n_sites + c] = nbr_energy of compact site c of replica r.  One thread per site.
+// HBM-bound in principle (1 B read + 8 B written per site); gathers hit L1/L2.
+__global__ void brw_site_energy_kernel(BrwGeom g, const double *__restrict__ V, const uint8_t *__restrict__ lat,
+                                       double *__restrict__ out, int n_rep) {
+  const long total = (long)g.n_sites * n_rep;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i / g.n_sites;
+    int c = (int)(i - r * g.n_sites);
+    const uint8_t *L = lat + r * g.n_sites;
+    int x, y, z;
+    brw_compact_to_grid(g, c, x, y, z);
+    out[i] = brw_site_energy(g, V, x, y, z, L[c], BrwPlainSpec{L});
+  }
+}
+// scatter compact per-site energies to the reference grid shape (0.0 off-site)
+__global__ void brw_site_energy_to_grid_kernel(BrwGeom g, const double *__restrict__ e, double *__restrict__ out) {
+  const long cells = (long)g.gx * g.gy * g.gz;
+  for (long c = blockIdx.x * (long)blockDim.x + threadIdx.x; c < cells; c += (long)gridDim.x * blockDim.x) {
+    int x = (int)(c % g.gx), y = (int)((c / g.gx) % g.gy), z = (int)(c / ((long)g.gx * g.gy));
+    out[c] = brw_is_site(g, x, y, z) ? e[brw_grid_to_compact(g, x, y, z)] : 0.0;
+  }
+}
+
+// ---- ordered sum: bit-exact total_energy -----------------------------------------------------
+// One CTA per replica.  f64 addition is not associative, so the reference's sequential z/y/x
+// accumulation (src/bw_hamiltonian.f90:67-79) is reproduced literally: the CTA stages chunks of
+// the per-site energies in shared memory (coalesced) and thread 0 adds them in compact order.
+#define BRW_OSUM_CHUNK 2048
+__global__ void __launch_bounds__(256) brw_ordered_sum_kernel(const double *__restrict__ e, long n, double *__restrict__ out) {
+  __shared__ double buf[2][BRW_OSUM_CHUNK];
+  const double *src = e + (long)blockIdx.x * n;
+  double acc = 0.0;
+  long nchunks = (n + BRW_OSUM_CHUNK - 1) / BRW_OSUM_CHUNK;
+  // prefetch chunk 0
+  for (int i = threadIdx.x; i < BRW_OSUM_CHUNK && i < n; i += blockDim.x) buf[0][i] = src[i];
+  __syncthreads();
+  for (long ch = 0; ch < nchunks; ch++) {
+    int cur = ch & 1;
+    long base = ch * BRW_OSUM_CHUNK, nb = base + BRW_OSUM_CHUNK;
+    if (threadIdx.x == 0) {
+      int m = (int)((n - base) < BRW_OSUM_CHUNK ? (n - base) : BRW_OSUM_CHUNK);
+      const double *b = buf[cur];
+#pragma unroll 8
+      for (int i = 0; i < m; i++) acc = __dadd_rn(acc, b[i]);
+    } else if (nb < n) {
+      // the other 255 threads fetch the next chunk meanwhile
+      for (int i = threadIdx.x - 1; i < BRW_OSUM_CHUNK && nb + i < n; i += blockDim.x - 1) buf[cur ^ 1][i] = src[nb + i];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = 0.5 * acc;   // :79
+}
+
+// ---- tree sum: fast total energy (deterministic, not reference order) -------------------------
+// Fused site-energy + block reduction; partial[r*nblk + b]; finished by brw_tree_final_kernel.
+__global__ void __launch_bounds__(256) brw_energy_partial_kernel(BrwGeom g, const double *__restrict__ V,
+                                                                 const uint8_t *__restrict__ lat,
+                                                                 double *__restrict__ partial, int nblk) {
+  __shared__ double red[8];
+  const int r = blockIdx.y;
+  const uint8_t *L = lat + (long)r * g.n_sites;
+  double acc = 0.0;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.n_sites; c += nblk * blockDim.x) {
+    int x, y, z;
+    brw_compact_to_grid(g, c, x, y, z);
+    acc += brw_site_energy(g, V, x, y, z, L[c], BrwPlainSpec{L});
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); w++) s += red[w];
+    partial[(long)r * nblk + blockIdx.x] = s;
+  }
+}
+__global__ void brw_tree_final_kernel(const double *__restrict__ partial, int nblk, double *__restrict__ out, int n_rep) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rep) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; b++) s += partial[(long)r * nblk + b];
+  out[r] = 0.5 * s;
+}
+
+// ---- per-swap dE batch -----------------------------------------------------------------------
+// idx are flat indices on the reference grid; dE = pair_energy(after) - pair_energy(before).
+__global__ void brw_pair_dE_kernel(BrwGeom g, const double *__restrict__ V, const uint8_t *__restrict__ lat, long n,
+                                   const int32_t *__restrict__ i1, const int32_t *__restrict__ i2,
+                                   double *__restrict__ dE, int *flag) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+    int a = i1[t], b = i2[t];
+    int xa = a % g.gx, ya = (a / g.gx) % g.gy, za = a / (g.gx * g.gy);
+    int xb = b % g.gx, yb = (b / g.gx) % g.gy, zb = b / (g.gx * g.gy);
+    if (a < 0 || b < 0 || za >= g.gz || zb >= g.gz || !brw_is_site(g, xa, ya, za) || !brw_is_site(g, xb, yb, zb)) {
+      atomicOr(flag, 4); dE[t] = 0.0; continue;
+    }
+    double before, after;
+    brw_pair_energies(g, V, lat, brw_grid_to_compact(g, xa, ya, za), brw_grid_to_compact(g, xb, yb, zb), before, after);
+    dE[t] = __dsub_rn(after, before);
+  }
+}
+
+// ---- SRO pair counts (radial_densities, src/analytics.f90:293-404) ----------------------------
+// sro_off[k] = (dx,dy,dz,l): every raw cube offset the reference's scan visits whose distance
+// matches WC shell l (built on the host; l = 0 is the site itself).  Integer counts, so the
+// result is exact; rho = cnt / species_count is formed by the caller in f64.
+__global__ void __launch_bounds__(256) brw_radial_counts_kernel(BrwGeom g, const uint8_t *__restrict__ lat,
+                                                                const int4 *__restrict__ sro_off, int n_off,
+                                                                int wc_range, unsigned long long *__restrict__ cnt,
+                                                                unsigned long long *__restrict__ species_count) {
+  extern __shared__ unsigned int hist[];   // [wc_range*S*S] + [S]
+  const int nh = wc_range * g.S * g.S + g.S;
+  for (int i = threadIdx.x; i < nh; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  unsigned int *sc = hist + wc_range * g.S * g.S;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.n_sites; c += gridDim.x * blockDim.x) {
+    int x, y, z;
+    brw_compact_to_grid(g, c, x, y, z);
+    int si = lat[c];
+    atomicAdd(&sc[si], 1u);
+    for (int k = 0; k < n_off; k++) {
+      int4 o = sro_off[k];
+      int nx = brw_wrap(x + o.x, g.gx), ny = brw_wrap(y + o.y, g.gy), nz = brw_wrap(z + o.z, g.gz);
+      int sj = lat[brw_grid_to_compact(g, nx, ny, nz)];
+      atomicAdd(&hist[(o.w * g.S + sj) * g.S + si], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < wc_range * g.S * g.S; i += blockDim.x)
+    if (hist[i]) atomicAdd(&cnt[i], (unsigned long long)hist[i]);
+  for (int i = threadIdx.x; i < g.S; i += blockDim.x)
+    if (sc[i]) atomicAdd(&species_count[i], (unsigned long long)sc[i]);
+}

@@ -1,0 +1,333 @@
+// tile_metropolis.cuh -- production Metropolis: shared-memory boxes with sublattice-parallel swaps.
+//
+// Replaces the k-loop of metropolis_simulated_annealing (src/metropolis.F90:348-354) and
+// monte_carlo_step_lattice / _nbr (:751-891) for lattices large enough to be decomposed.
+//
+// Scheme (DESIGN.md "Production Metropolis"):
+//  * PHASE: the periodic lattice is cut into boxes of (Bx,By,Bz) doubled-grid units at a random
+//    even origin; one CTA loads one box (sites only, 1 B/site) into shared memory.  Sites closer
+//    than `m` (>= interaction reach) to a box face are frozen during the phase, so every
+//    neighbour of an active site is inside the same box: no halo, no inter-CTA traffic.
+//  * STEP: a CTA-uniform random draw picks a residue class o (mod P) and an allowed
+//    displacement class d.  Thread (i,j,k) proposes the swap of site1 = m + o + P*(i,j,k) with
+//    site2 = m + (o+d mod P) + P*((i,j,k)+s mod A).  P and the set D of allowed d are chosen
+//    on the host such that NO neighbour vector v of the Hamiltonian satisfies v = 0, +-d (mod P):
+//    all sites touched in one step are mutually non-interacting, hence the M = Ax*Ay*Az
+//    simultaneous Metropolis decisions are exactly equivalent to M sequential ones (detailed
+//    balance holds move by move; the proposal is symmetric and configuration-independent).
+//  * dE uses the reference's f64 association (brw_common.cuh) => each decision is the one the
+//    reference would take for the same pair, same configuration, same uniform.
+//  * RNG: Philox4x32-10, counter = (trial slot, step/4, box, phase), key = seed.
+#pragma once
+#include <vector>
+#include <algorithm>
+#include "brawl_common.cuh"
+
+struct BrwBoxParams {          // POD kernel parameter
+  int P, m;
+  int B[3], nb[3], A[3], M;
+  int bxc, byc, bzc, box_sites;
+  int n_classes, n_disp;
+  int boxes_per_replica;
+  int steps;
+  int v_entries;               // S*S*n_shells
+};
+
+struct BrwPlan {
+  bool valid = false, use_box = false;
+  int nbr_swap = 0;
+  BrwBoxParams p{};
+  int4 *d_classes = nullptr;   // residue classes o (x,y,z,unused)
+  int4 *d_disp = nullptr;      // displacement classes d
+  int *d_off = nullptr;        // [2][ztot] compact shared-memory offsets, by x-parity of the site
+  double *d_Vrep = nullptr;    // [v_entries][16] lane-replicated V (layout [shell][centre][nbr])
+  size_t smem = 0;
+  int threads = 0;
+  // per-box counters
+  unsigned long long *d_att = nullptr, *d_acc = nullptr;
+  double *d_dE = nullptr;
+  int n_slots = 0;
+};
+
+// ---- host planner -----------------------------------------------------------------------------
+static inline int brw_posmod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
+
+// Find the smallest even period P for which (a) no neighbour vector is = 0 mod P and (b) the set
+// D of displacement classes d with no neighbour vector = +-d (mod P) connects all residue
+// classes.  In nbr_swap mode the second site is site1 + e (e in `first`), and the requirement is
+// that no neighbour vector equals P*k, P*k +- e for k != 0.
+static bool brw_choose_period(const BrwGeom &g, int nbr_swap, const std::vector<std::array<int, 3>> &first,
+                              int Pmax, int &P_out, std::vector<int4> &classes, std::vector<int4> &disp) {
+  for (int P = 2; P <= Pmax; P += 2) {
+    bool ok = true;
+    for (int k = 0; k < g.ztot && ok; k++)
+      if (brw_posmod(g.off[k][0], P) == 0 && brw_posmod(g.off[k][1], P) == 0 && brw_posmod(g.off[k][2], P) == 0) ok = false;
+    if (!ok) continue;
+    classes.clear();
+    for (int z = 0; z < P; z++) for (int y = 0; y < P; y++) for (int x = 0; x < P; x++)
+      if (brw_is_site(g, x, y, z)) classes.push_back(make_int4(x, y, z, 0));
+    disp.clear();
+    if (nbr_swap) {
+      // concurrent pairs (i, i+e) and (i', i'+e), i'-i = P*k != 0: differences P*k, P*k+-e
+      for (auto &e : first) {
+        bool good = true;
+        for (int k = 0; k < g.ztot && good; k++)
+          for (int sgn = -1; sgn <= 1 && good; sgn++) {
+            int vx = g.off[k][0] - sgn * e[0], vy = g.off[k][1] - sgn * e[1], vz = g.off[k][2] - sgn * e[2];
+            if (vx == 0 && vy == 0 && vz == 0) continue;              // k = 0: the pair itself
+            if (brw_posmod(vx, P) == 0 && brw_posmod(vy, P) == 0 && brw_posmod(vz, P) == 0) good = false;
+          }
+        // +-e itself must not be = 0 mod P
+        if (brw_posmod(e[0], P) == 0 && brw_posmod(e[1], P) == 0 && brw_posmod(e[2], P) == 0) good = false;
+        if (!good) { ok = false; break; }
+        disp.push_back(make_int4(e[0], e[1], e[2], 0));
+      }
+      if (!ok) continue;
+      P_out = P;
+      return true;
+    }
+    for (auto &c : classes) {
+      if (c.x == 0 && c.y == 0 && c.z == 0) continue;
+      bool good = true;
+      for (int k = 0; k < g.ztot && good; k++)
+        for (int sgn = -1; sgn <= 1; sgn += 2)
+          if (brw_posmod(g.off[k][0] - sgn * c.x, P) == 0 && brw_posmod(g.off[k][1] - sgn * c.y, P) == 0 &&
+              brw_posmod(g.off[k][2] - sgn * c.z, P) == 0) { good = false; break; }
+      if (good) disp.push_back(c);
+    }
+    if (disp.empty()) continue;
+    // connectivity of the class graph under D (composition must be able to flow everywhere)
+    std::vector<char> seen(P * P * P, 0);
+    std::vector<int> stack{0};
+    seen[0] = 1;
+    size_t reached = 0;
+    while (!stack.empty()) {
+      int c = stack.back(); stack.pop_back(); reached++;
+      int cx = c % P, cy = (c / P) % P, cz = c / (P * P);
+      for (auto &d : disp)
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+          int nx = brw_posmod(cx + sgn * d.x, P), ny = brw_posmod(cy + sgn * d.y, P), nz = brw_posmod(cz + sgn * d.z, P);
+          int n = (nz * P + ny) * P + nx;
+          if (!seen[n]) { seen[n] = 1; stack.push_back(n); }
+        }
+    }
+    if (reached != classes.size()) continue;
+    P_out = P;
+    return true;
+  }
+  return false;
+}
+
+// ---- kernel -------------------------------------------------------------------------------------
+struct BrwStepParams {     // CTA-uniform per step, double-buffered in shared memory
+  int c1_base, c2_base;    // compact smem index of site1/site2 for (i,j,k) = 0
+  int par1, par2;          // offset-table selector of site1 / site2
+  int s[3];                // cyclic shift of the coarse index for site2
+  int pad;
+};
+
+__device__ __forceinline__ int brw_box_compact(const BrwGeom &g, const BrwBoxParams &p, int X, int Y, int Z) {
+  return (Z * p.byc + (Y >> g.ys)) * p.bxc + (X >> g.xs);
+}
+// offset-table selector: parity that decides how a doubled-grid dx maps to compact dx
+__device__ __host__ __forceinline__ int brw_site_parity(const BrwGeom &g, int X, int Y, int Z) {
+  (void)Y; (void)Z;
+  return g.lattice == 0 ? 0 : (X & 1);   // bcc: x=y=z parity; fcc: x parity = (y+z) parity
+}
+
+template <int NBR>
+__device__ __forceinline__ void brw_make_step(const BrwGeom &g, const BrwBoxParams &p, const int4 *classes,
+                                              const int4 *disp, uint32_t k0, uint32_t k1, uint32_t step,
+                                              uint32_t box_id, uint32_t phase_lo, BrwStepParams *out) {
+  BrwPhilox4 r = brw_philox(0xFFFFFFFFu, step, box_id, phase_lo, k0, k1);
+  int4 o = classes[brw_below(r.x, p.n_classes)];
+  int4 d = disp[brw_below(r.y, p.n_disp)];
+  int X1 = p.m + o.x, Y1 = p.m + o.y, Z1 = p.m + o.z;
+  int X2, Y2, Z2;
+  if (NBR) { X2 = X1 + d.x; Y2 = Y1 + d.y; Z2 = Z1 + d.z; out->s[0] = out->s[1] = out->s[2] = 0; }
+  else {
+    X2 = p.m + (o.x + d.x) % p.P; Y2 = p.m + (o.y + d.y) % p.P; Z2 = p.m + (o.z + d.z) % p.P;
+    out->s[0] = (int)brw_below(r.z, p.A[0]);
+    out->s[1] = (int)(((r.w & 0xFFFFu) * (uint32_t)p.A[1]) >> 16);   // 16-bit draws; A <= 65535
+    out->s[2] = (int)(((r.w >> 16) * (uint32_t)p.A[2]) >> 16);
+  }
+  out->c1_base = brw_box_compact(g, p, X1, Y1, Z1);
+  out->c2_base = brw_box_compact(g, p, X2, Y2, Z2);
+  out->par1 = brw_site_parity(g, X1, Y1, Z1);
+  out->par2 = brw_site_parity(g, X2, Y2, Z2);
+}
+
+// sum of one site's shell chains for two centre species at once (the "before" centre and the
+// "after" centre see the same neighbours): e_a, e_b in the reference's association.
+template <int NBR>
+__device__ __forceinline__ void brw_box_site_chains(const BrwGeom &g, const uint8_t *box, const int *off,
+                                                    const double *Vl, int S, int c, int ca, int cb, int c_other,
+                                                    int s_other_after, double &Ea, double &Eb) {
+  // Vl points at lane slot (lane&15) of the replicated table [shell][centre][nbr][16]
+  int k = 0;
+  double ta = 0.0, tb = 0.0;
+  for (int n = 0; n < g.n_shells; n++) {
+    const double *Va = Vl + ((n * S + ca) * S) * 16;
+    const double *Vb = Vl + ((n * S + cb) * S) * 16;
+    double ea = 0.0, eb = 0.0;
+    const int end = g.shell_end[n];
+#pragma unroll 4
+    for (; k < end; k++) {
+      const int cn = c + off[k];
+      int s = box[cn];
+      ea = __dadd_rn(ea, Va[s * 16]);
+      // in neighbour-swap mode the partner site is a neighbour and shows its new occupant
+      if (NBR) s = (cn == c_other) ? s_other_after : s;
+      eb = __dadd_rn(eb, Vb[s * 16]);
+    }
+    ta = (n == 0) ? ea : __dadd_rn(ta, ea);
+    tb = (n == 0) ? eb : __dadd_rn(tb, eb);
+  }
+  Ea = ta; Eb = tb;
+}
+
+template <int NBR>
+__global__ void __launch_bounds__(1024) brw_box_metropolis_kernel(
+    BrwGeom g, BrwBoxParams p, uint8_t *__restrict__ lat, const double *__restrict__ beta,
+    const double *__restrict__ Vrep, const int *__restrict__ off_g, const int4 *__restrict__ classes,
+    const int4 *__restrict__ disp, uint32_t k0, uint32_t k1, uint32_t phase_lo,
+    unsigned long long *__restrict__ att_out, unsigned long long *__restrict__ acc_out, double *__restrict__ dE_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *Vs = reinterpret_cast<double *>(smem_raw);                       // [v_entries][16]
+  int *off = reinterpret_cast<int *>(Vs + p.v_entries * 16);               // [2][ztot]
+  BrwStepParams *sp = reinterpret_cast<BrwStepParams *>(off + 2 * g.ztot); // [2]
+  double *red = reinterpret_cast<double *>(sp + 2);                        // [32]
+  uint8_t *box = reinterpret_cast<uint8_t *>(red + 32);
+
+  const int tid = threadIdx.x;
+  const int replica = blockIdx.x / p.boxes_per_replica;
+  const int bid = blockIdx.x - replica * p.boxes_per_replica;
+  const int bi = bid % p.nb[0], bj = (bid / p.nb[0]) % p.nb[1], bk = bid / (p.nb[0] * p.nb[1]);
+  uint8_t *L = lat + (long)replica * g.n_sites;
+
+  // phase origin: even shift, identical for all boxes of a replica
+  BrwPhilox4 ro = brw_philox(0xFFFFFFFEu, 0u, (uint32_t)replica, phase_lo, k0, k1);
+  const int ox = 2 * (int)brw_below(ro.x, g.gx >> 1) + bi * p.B[0];
+  const int oy = 2 * (int)brw_below(ro.y, g.gy >> 1) + bj * p.B[1];
+  const int oz = 2 * (int)brw_below(ro.z, g.gz >> 1) + bk * p.B[2];
+
+  for (int i = tid; i < p.v_entries * 16; i += blockDim.x) Vs[i] = Vrep[i];
+  for (int i = tid; i < 2 * g.ztot; i += blockDim.x) off[i] = off_g[i];
+  // ---- load box (global compact -> shared compact), rows along x are contiguous up to wrap
+  for (int idx = tid; idx < p.box_sites; idx += blockDim.x) {
+    int lxc = idx % p.bxc, t = idx / p.bxc, lyc = t % p.byc, lz = t / p.byc;
+    int X, Y;
+    if (g.lattice == 1) { X = 2 * lxc + (lz & 1); Y = 2 * lyc + (lz & 1); }
+    else if (g.lattice == 2) { Y = lyc; X = 2 * lxc + ((lyc + lz) & 1); }
+    else { X = lxc; Y = lyc; }
+    int gxx = ox + X; if (gxx >= g.gx) gxx -= g.gx; if (gxx >= g.gx) gxx -= g.gx;
+    int gyy = oy + Y; if (gyy >= g.gy) gyy -= g.gy; if (gyy >= g.gy) gyy -= g.gy;
+    int gzz = oz + lz; if (gzz >= g.gz) gzz -= g.gz; if (gzz >= g.gz) gzz -= g.gz;
+    box[idx] = L[brw_grid_to_compact(g, gxx, gyy, gzz)];
+  }
+  const uint32_t box_id = (uint32_t)blockIdx.x;
+  if (tid == 0) brw_make_step<NBR>(g, p, classes, disp, k0, k1, 0u, box_id, phase_lo, &sp[0]);
+  __syncthreads();
+
+  const double my_beta = beta[replica];
+  const double *Vl = Vs + (tid & 15);
+  // strides of the coarse lattice in compact shared-memory index units
+  const int stx = p.P >> g.xs, sty = (p.P >> g.ys) * p.bxc, stz = p.P * p.byc * p.bxc;
+  unsigned int n_att = 0, n_acc = 0;
+  double dE_sum = 0.0;
+  BrwPhilox4 rnd = {0, 0, 0, 0};
+
+  for (int step = 0; step < p.steps; step++) {
+    const BrwStepParams q = sp[step & 1];
+    const int *off1 = off + q.par1 * g.ztot, *off2 = off + q.par2 * g.ztot;
+    for (int t = tid; t < p.M; t += blockDim.x) {
+      int i = t % p.A[0], r = t / p.A[0], j = r % p.A[1], k = r / p.A[1];
+      int i2 = i + q.s[0]; if (i2 >= p.A[0]) i2 -= p.A[0];
+      int j2 = j + q.s[1]; if (j2 >= p.A[1]) j2 -= p.A[1];
+      int k2 = k + q.s[2]; if (k2 >= p.A[2]) k2 -= p.A[2];
+      const int c1 = q.c1_base + i * stx + j * sty + k * stz;
+      const int c2 = q.c2_base + i2 * stx + j2 * sty + k2 * stz;
+      const int a = box[c1], b = box[c2];
+      n_att++;
+      if ((step & 3) == 0 || p.M > (int)blockDim.x)
+        rnd = brw_philox((uint32_t)t, (uint32_t)step, box_id, phase_lo, k0, k1);
+      if (a == b) { n_acc++; continue; }                       // src/metropolis.F90:774-777
+      double E1a, E1b, E2b, E2a;
+      brw_box_site_chains<NBR>(g, box, off1, Vl, g.S, c1, a, b, c2, a, E1a, E1b);
+      brw_box_site_chains<NBR>(g, box, off2, Vl, g.S, c2, b, a, c1, b, E2b, E2a);
+      const double before = __dadd_rn(E1a, E2b);               // pair_energy, sites unswapped
+      const double after = __dadd_rn(E1b, E2a);                // pair_energy, sites swapped
+      const double dE = __dsub_rn(after, before);              // :792
+      bool accept = dE < 0.0;                                  // :796
+      if (!accept) {
+        const uint32_t w = (step & 3) == 0 ? rnd.x : (step & 3) == 1 ? rnd.y : (step & 3) == 2 ? rnd.z : rnd.w;
+        accept = brw_u01(w) < exp(-my_beta * dE);              // :802
+      }
+      if (accept) { box[c1] = (uint8_t)b; box[c2] = (uint8_t)a; n_acc++; dE_sum += dE; }
+    }
+    if (tid == 0 && step + 1 < p.steps)
+      brw_make_step<NBR>(g, p, classes, disp, k0, k1, (uint32_t)(step + 1), box_id, phase_lo, &sp[(step + 1) & 1]);
+    __syncthreads();
+  }
+
+  // ---- store box
+  for (int idx = tid; idx < p.box_sites; idx += blockDim.x) {
+    int lxc = idx % p.bxc, t = idx / p.bxc, lyc = t % p.byc, lz = t / p.byc;
+    int X, Y;
+    if (g.lattice == 1) { X = 2 * lxc + (lz & 1); Y = 2 * lyc + (lz & 1); }
+    else if (g.lattice == 2) { Y = lyc; X = 2 * lxc + ((lyc + lz) & 1); }
+    else { X = lxc; Y = lyc; }
+    int gxx = ox + X; if (gxx >= g.gx) gxx -= g.gx; if (gxx >= g.gx) gxx -= g.gx;
+    int gyy = oy + Y; if (gyy >= g.gy) gyy -= g.gy; if (gyy >= g.gy) gyy -= g.gy;
+    int gzz = oz + lz; if (gzz >= g.gz) gzz -= g.gz; if (gzz >= g.gz) gzz -= g.gz;
+    L[brw_grid_to_compact(g, gxx, gyy, gzz)] = box[idx];
+  }
+  // ---- counters: fixed-order CTA reduction, one slot per box (deterministic)
+  unsigned int packed_att = n_att, packed_acc = n_acc;
+  for (int o = 16; o > 0; o >>= 1) {
+    packed_att += __shfl_down_sync(0xffffffffu, packed_att, o);
+    packed_acc += __shfl_down_sync(0xffffffffu, packed_acc, o);
+    dE_sum += __shfl_down_sync(0xffffffffu, dE_sum, o);
+  }
+  __shared__ unsigned int s_att[32], s_acc[32];
+  if ((tid & 31) == 0) { s_att[tid >> 5] = packed_att; s_acc[tid >> 5] = packed_acc; red[tid >> 5] = dE_sum; }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long A = 0, C = 0; double D = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) { A += s_att[w]; C += s_acc[w]; D += red[w]; }
+    att_out[blockIdx.x] += A; acc_out[blockIdx.x] += C; dE_out[blockIdx.x] += D;
+  }
+}
+
+// ---- sequential chain per replica (lattices too small for boxes) ---------------------------------
+// One thread per replica, uniform random site pairs exactly as the reference proposes them
+// (src/random_site.f90), Philox stream per replica.  Lattice stays in global memory (L1/L2).
+__global__ void brw_chain_metropolis_kernel(BrwGeom g, const double *__restrict__ V, uint8_t *lat,
+                                            const double *__restrict__ beta, int n_rep, long n_trials, int nbr_swap,
+                                            uint32_t k0, uint32_t k1, uint32_t off_lo, uint32_t off_hi,
+                                            unsigned long long *att_out, unsigned long long *acc_out, double *dE_out) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rep) return;
+  uint8_t *L = lat + (long)r * g.n_sites;
+  const double b = beta[r];
+  unsigned long long acc = 0;
+  double dsum = 0.0;
+  for (long t = 0; t < n_trials; t++) {
+    BrwPhilox4 r1 = brw_philox((uint32_t)t, (uint32_t)(t >> 32) ^ 0x10000000u, (uint32_t)r, off_lo, k0, k1 ^ off_hi);
+    BrwPhilox4 r2 = brw_philox((uint32_t)t, (uint32_t)(t >> 32) ^ 0x20000000u, (uint32_t)r, off_lo, k0, k1 ^ off_hi);
+    int x1, y1, z1, x2, y2, z2;
+    brw_random_site(g, brw_u01(r1.x), brw_u01(r1.y), brw_u01(r1.z), x1, y1, z1);
+    if (nbr_swap) brw_random_nbr(g, brw_u01(r1.w), x1, y1, z1, x2, y2, z2);
+    else brw_random_site(g, brw_u01(r2.x), brw_u01(r2.y), brw_u01(r2.z), x2, y2, z2);
+    int c1 = brw_grid_to_compact(g, x1, y1, z1), c2 = brw_grid_to_compact(g, x2, y2, z2);
+    int s1 = L[c1], s2 = L[c2];
+    if (s1 == s2) { acc++; continue; }
+    double before, after;
+    brw_pair_energies(g, V, L, c1, c2, before, after);
+    double dE = __dsub_rn(after, before);
+    bool accept = dE < 0.0;
+    if (!accept) accept = brw_u01(r2.w) < exp(-b * dE);
+    if (accept) { L[c1] = (uint8_t)s2; L[c2] = (uint8_t)s1; acc++; dsum += dE; }
+  }
+  att_out[r] += (unsigned long long)n_trials; acc_out[r] += acc; dE_out[r] += dsum;
+}

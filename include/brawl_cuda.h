@@ -1,0 +1,167 @@
+/*
+ * brawl_cuda.h -- C ABI of libbrawl_cuda.so: BraWl's atom-swap Monte-Carlo hot path on B200.
+ *
+ * This is the drop-in boundary.  Every entry point is `extern "C"`, takes plain pointers and
+ * sizes, returns an int status (0 = OK; non-zero = error, text via brawl_cuda_last_error())
+ * and never throws, aborts or falls back to a CPU path: if no CUDA device is usable the
+ * call fails.  It extends the reference's only FFI seam, src/c_functions.f90:21-37 (the
+ * ISO_C_BINDING interface block for genrand / f90_init_genrand); INTEGRATION.md shows the
+ * Fortran `interface` blocks and the shims that rebind the run_params operator table
+ * (src/derived_types.f90:90-98) to these functions.
+ *
+ * Conventions shared by all calls
+ *  - lattice_id: 0 = simple_cubic, 1 = bcc, 2 = fcc   (setup%lattice, src/initialise.F90:159-240)
+ *  - A configuration is the reference's own array: int8 config(1, 2*n_1, 2*n_2, 2*n_3),
+ *    column-major, i.e. a contiguous byte grid[z][y][x] with x fastest, species 1..n_species,
+ *    0 = "no lattice site here" (src/shared_data.f90:30, src/initialise.F90:295).  Fortran passes
+ *    c_loc(config).  Inside the library the lattice lives in HBM in a compact sites-only layout.
+ *  - V_ex is the reference's array V_ex(n_species, n_species, n_shells) exactly as read from the
+ *    *.vij file (src/io.f90:401): V_ex[(shell*S + nbr)*S + centre], f64, Rydberg.
+ *  - Site coordinates / flat indices are 0-based on the doubled grid: idx = (z*2n_2 + y)*2n_1 + x
+ *    (Fortran site (1,i,j,k) -> x=i-1, y=j-1, z=k-1).
+ *  - A handle owns `n_replicas` independent lattices of the same shape (one per MPI rank /
+ *    Wang-Landau walker / nested-sampling walker in the reference); replica r of batched
+ *    host arrays starts at r * (8*n_1*n_2*n_3) bytes.
+ *  - All work is enqueued on the handle's CUDA stream; calls that return data to host memory
+ *    synchronise that stream before returning.
+ */
+#ifndef BRAWL_CUDA_H
+#define BRAWL_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct brawl_cuda_ctx brawl_cuda_t;
+
+#define BRAWL_LATTICE_SC 0
+#define BRAWL_LATTICE_BCC 1
+#define BRAWL_LATTICE_FCC 2
+
+/* ---- library / error state --------------------------------------------------------------- */
+const char *brawl_cuda_last_error(void);        /* thread-local text of the last failure      */
+int brawl_cuda_version(void);                   /* ABI version, currently 1                    */
+int brawl_cuda_device_count(int *count);        /* fails (non-zero) if the CUDA runtime cannot start */
+
+/* Self-test hook: one Philox4x32-10 block computed ON THE DEVICE (counter[4], key[2] -> out[4]);
+ * lets the tests pin the production RNG to the published known-answer vectors. */
+int brawl_cuda_philox4x32(int device, const uint32_t *counter4, const uint32_t *key2, uint32_t *out4);
+
+/* ---- handle -------------------------------------------------------------------------------
+ * Replaces: initialise_function_pointers (src/initialise.F90:153-257: binds nbr_energy by
+ * lattice x interaction_range), initialise_interaction/read_exchange (V_ex upload,
+ * src/initialise.F90:268-275, src/io.f90:389-415) and initialise_local_arrays (config
+ * allocation, src/initialise.F90:286-300).  Unsupported lattice/shell combinations fail the
+ * same way the reference does ("Unsupported number of shells"). */
+int brawl_cuda_create(int lattice_id, int n_1, int n_2, int n_3, int n_species, int n_shells,
+                      const double *V_ex, int device, int n_replicas, brawl_cuda_t **handle);
+int brawl_cuda_destroy(brawl_cuda_t *h);
+/* Launch on an existing stream (a cudaStream_t cast to void*; NULL = the library's own) */
+int brawl_cuda_set_stream(brawl_cuda_t *h, void *cuda_stream);
+int brawl_cuda_synchronize(brawl_cuda_t *h);
+int brawl_cuda_info(brawl_cuda_t *h, int64_t *n_atoms, int64_t *grid_bytes, int *z_total, int *n_replicas);
+
+/* ---- configuration transfer ----------------------------------------------------------------
+ * Host <-> HBM copy of the reference-layout grid(s) (what `config` is to every reference
+ * routine).  set validates occupancy: a byte that is 0 on a lattice site, non-zero off-site or
+ * > n_species is an error. */
+int brawl_cuda_set_config(brawl_cuda_t *h, int first_replica, int n, const int8_t *grids);
+int brawl_cuda_get_config(brawl_cuda_t *h, int first_replica, int n, int8_t *grids);
+/* replica dst := replica src on the device (nested_sampling.f90:151 walker cloning;
+ * wang-landau.F90:1475-1495 same-GPU replica exchange) */
+int brawl_cuda_copy_replica(brawl_cuda_t *h, int src, int dst);
+
+/* ---- Hamiltonian ----------------------------------------------------------------------------
+ * total_energy == setup%full_energy (src/bw_hamiltonian.f90:58-81).  exact_order != 0 adds the
+ * per-site energies in the reference's z/y/x order => bit-identical to the reference;
+ * exact_order == 0 uses a parallel tree (same per-site values, different last-bit rounding).
+ * energies[n] for replicas first_replica .. first_replica+n-1. */
+int brawl_cuda_total_energy(brawl_cuda_t *h, int first_replica, int n, int exact_order, double *energies);
+/* nbr_energy == setup%nbr_energy(config, 1, x+1, y+1, z+1) (src/bw_hamiltonian.f90:898-1262,
+ * 1712-1910, 2059-2106) for every cell of one replica; 0.0 on empty cells.  out[grid]. */
+int brawl_cuda_site_energies(brawl_cuda_t *h, int replica, double *out);
+/* Per-swap dE exactly as monte_carlo_step_* forms it: pair_energy(after) - pair_energy(before)
+ * (src/metropolis.F90:783-792, src/bw_hamiltonian.f90:99-114); configuration is not modified. */
+int brawl_cuda_pair_dE(brawl_cuda_t *h, int replica, int64_t n_pairs, const int32_t *idx1,
+                       const int32_t *idx2, double *dE);
+
+/* ---- Metropolis -----------------------------------------------------------------------------
+ * Deterministic replay: n_trials calls of setup%mc_step (monte_carlo_step_lattice / _nbr,
+ * src/metropolis.F90:751-891) on one replica, consuming the reference's MT19937 stream
+ * (src/mt19937ar.c; mt_state = mt[624] followed by mti, updated in place) in the reference's
+ * order (z, x, y per site; +1 draw only if species differ and dE >= 0).  Replaces the k-loop at
+ * src/metropolis.F90:350-354.  Bit-exact trajectory. */
+int brawl_cuda_metropolis_replay(brawl_cuda_t *h, int replica, double beta, int64_t n_trials,
+                                 int nbr_swap, uint32_t *mt_state625, int64_t *n_accept);
+/* Same, with the sampling loop fused: every n_sample_steps trials the exact-order total energy
+ * is recorded on the device (src/metropolis.F90:348-367); energies[n_trials/n_sample_steps]. */
+int brawl_cuda_metropolis_replay_sampled(brawl_cuda_t *h, int replica, double beta, int64_t n_trials,
+                                         int64_t n_sample_steps, int nbr_swap, uint32_t *mt_state625,
+                                         int64_t *n_accept, double *energies);
+
+/* Production: every replica performs >= n_trials attempted swaps at its own beta[r] with
+ * counter-based Philox4x32-10 streams (key = seed, counter = (site-pair slot, step, box, phase)).
+ * Large lattices run as shared-memory boxes with sublattice-parallel swaps, small ones as one
+ * sequential chain per replica.  Outputs (any may be NULL), per replica:
+ * attempted, accepted (same-species proposals count as accepted, src/metropolis.F90:774-777) and the
+ * sum of accepted dE.  `offset` must advance between calls that share a seed: pass the returned
+ * *next_offset. */
+int brawl_cuda_metropolis_run(brawl_cuda_t *h, const double *beta, int64_t n_trials, int nbr_swap,
+                              uint64_t seed, uint64_t offset, uint64_t *next_offset,
+                              int64_t *n_attempt, int64_t *n_accept, double *dE_sum);
+/* Enqueue-only form (no host sync, counters accumulate on the device until
+ * brawl_cuda_metropolis_counters is called) -- what the benchmark times with CUDA events. */
+int brawl_cuda_metropolis_enqueue(brawl_cuda_t *h, const double *beta, int64_t n_trials, int nbr_swap,
+                                  uint64_t seed, uint64_t offset, uint64_t *next_offset,
+                                  int64_t *n_attempt_planned, int *n_kernel_launches);
+int brawl_cuda_metropolis_counters(brawl_cuda_t *h, int reset, int64_t *n_attempt, int64_t *n_accept,
+                                   double *dE_sum);
+/* Tuning of the box decomposition (0 = automatic): box extents in doubled-grid units, trials
+ * steps per phase. */
+int brawl_cuda_metropolis_tune(brawl_cuda_t *h, int box_x, int box_y, int box_z, int steps_per_phase);
+/* Describe the decomposition chosen: period P, margin, box extents, active cells, boxes/replica,
+ * |D| (number of allowed displacement classes), 1 if the box kernel is used */
+int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *out10);
+
+/* ---- short-range order ----------------------------------------------------------------------
+ * Integer pair counts behind radial_densities (src/analytics.f90:293-404):
+ * cnt[(l*S + j)*S + i] = number of species-(j+1) atoms on coordination shell l of species-(i+1)
+ * atoms (l = 0: the site itself), species_count[S].  rho = cnt / species_count[i] in f64 is
+ * exactly the reference's r_densities(i,j,l).  wc_range-1 <= n tabulated shells. */
+int brawl_cuda_radial_counts(brawl_cuda_t *h, int replica, int wc_range, int64_t *cnt, int64_t *species_count);
+
+/* ---- Wang-Landau ----------------------------------------------------------------------------
+ * sweeps() for the walkers held by this handle (src/wang-landau.F90:539-626): walker w owns
+ * replica w, lng[w*bins .. ], hist[w*hist_stride ..], window win_lo[w]..win_hi[w] (1-based bin
+ * indices mpi_start_idx/mpi_end_idx).  The intra-window average (:628-631) is done by
+ * brawl_cuda_wl_window_average for walkers on this GPU and by the caller's NCCL allreduce
+ * across GPUs.  Replay form consumes an MT19937 stream for ONE walker (bit-exact). */
+int brawl_cuda_wl_sweeps_replay(brawl_cuda_t *h, int replica, double *lng, double *hist, const double *bin_edges,
+                                int bins, int win_lo, int win_hi, double wl_f, int64_t n_trials, int nbr_swap,
+                                uint32_t *mt_state625, int64_t *n_accept, double *e_final);
+int brawl_cuda_wl_sweeps(brawl_cuda_t *h, int n_walkers, double *lng_dev_or_host, double *hist_dev_or_host,
+                         int data_on_device, const double *bin_edges, int bins, const int32_t *win_lo,
+                         const int32_t *win_hi, int hist_stride, double wl_f, int64_t n_trials, int nbr_swap,
+                         uint64_t seed, uint64_t offset, int64_t *n_accept, double *e_final);
+
+/* Average a device array a[walker][len] over the walkers of each window held by this handle
+ * (walkers q*wpw .. q*wpw+wpw-1 form window q) and write the mean/`divisor`-scaled sum back to
+ * every walker: the on-GPU part of the allreduce + "/num_walkers" at src/wang-landau.F90:628-631. */
+int brawl_cuda_wl_window_average(brawl_cuda_t *h, double *dev_array, int len, int walkers_per_window,
+                                 int n_windows, double divisor);
+
+/* ---- nested sampling ------------------------------------------------------------------------
+ * The constrained random walk of nested_sampling.f90:157-192 for a batch of walkers: walker w
+ * (replica walker_ids[w]) with running energy energies[w] takes n_steps steps (site 2 redrawn
+ * until species differ; accept iff E + dE < e_limit[w]).  Replay form: one walker, MT stream. */
+int brawl_cuda_ns_walk_replay(brawl_cuda_t *h, int replica, double *energy, double e_limit, int64_t n_steps,
+                              uint32_t *mt_state625, int64_t *n_accept);
+int brawl_cuda_ns_walk(brawl_cuda_t *h, int n_walkers, const int32_t *walker_ids, double *energies,
+                       const double *e_limit, int64_t n_steps, uint64_t seed, uint64_t offset, int64_t *n_accept);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRAWL_CUDA_H */

@@ -1,0 +1,472 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs, and against the reference's golden files.  Bit-exact for energies / dE / replayed
+trajectories / pair counts; statistical for the production sampler (tolerances stated inline).
+Run on the B200 box with `pytest -m gpu`."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import fmt
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bw():
+    import brawl_b200
+    brawl_b200.load()
+    return brawl_b200
+
+
+def random_config(orc, sysm, seed, conc=None):
+    mt = orc.MT(seed=seed)
+    S = sysm.S
+    c, cnt = sysm.quotas(conc=[1.0 / S] * S if conc is None else conc)
+    return sysm.initial_setup(mt, c, cnt)
+
+
+def rand_V(S, shells, seed):
+    rng = np.random.default_rng(seed)
+    V = rng.normal(scale=2e-3, size=(shells, S, S))
+    V = 0.5 * (V + V.transpose(0, 2, 1))          # the shipped tables are symmetric
+    return np.ascontiguousarray(V).ravel()
+
+
+# ---------------------------------------------------------------------------------------------
+def test_philox_known_answers(bw):
+    """Random123 kat_vectors for philox4x32-10."""
+    L = bw.load()
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        c = np.array(ctr, dtype=np.uint32); k = np.array(key, dtype=np.uint32); o = np.zeros(4, dtype=np.uint32)
+        bw._lib.check(L.brawl_cuda_philox4x32(0, c.ctypes.data_as(C.c_void_p), k.ctypes.data_as(C.c_void_p),
+                                              o.ctypes.data_as(C.c_void_p)))
+        assert tuple(int(v) for v in o) == want
+
+
+def test_config_roundtrip_and_validation(bw, orc, golden):
+    sysm = orc.System("fcc", 3, 4, 5, 5, 4, golden["t03_V"])
+    dev = bw.Device("fcc", 3, 4, 5, 5, 4, golden["t03_V"], n_replicas=3)
+    gs = np.stack([random_config(orc, sysm, s) for s in (1, 2, 3)])
+    dev.set_config(gs)
+    assert np.array_equal(dev.get_config(0, 3), gs)
+    dev.copy_replica(2, 0)
+    assert np.array_equal(dev.get_config(0, 1), gs[2])
+    bad = gs[0].copy(); bad[bad > 0] = 6
+    with pytest.raises(bw.BrawlCudaError, match="species"):
+        dev.set_config(bad, 1, 1)
+    bad = gs[0].copy(); bad[0, 0, 1] = 1          # (x=1,y=0,z=0) is not an fcc site
+    with pytest.raises(bw.BrawlCudaError, match="not a lattice site"):
+        dev.set_config(bad, 1, 1)
+    with pytest.raises(bw.BrawlCudaError):
+        dev.set_config(gs, 2, 3)                  # replica range overflow
+
+
+CASES = [("bcc", n) for n in range(1, 11)] + [("fcc", n) for n in range(1, 7)] + [("simple_cubic", 1), ("simple_cubic", 2)]
+
+
+@pytest.mark.parametrize("lattice,shells", CASES)
+def test_site_and_total_energy_bit_exact(bw, orc, lattice, shells):
+    """nbr_energy on every site and total_energy in reference order: bit-exact (incl. the buggy
+    bcc shells 8 and 10 and the simple-cubic modulo-n wrap)."""
+    S = 4
+    n = (6, 5, 7)
+    V = rand_V(S, shells, 100 + shells)
+    sysm = orc.System(lattice, n[0], n[1], n[2], S, shells, V)
+    g = random_config(orc, sysm, 42 + shells)
+    dev = bw.Device(lattice, n[0], n[1], n[2], S, shells, V)
+    dev.set_config(g)
+    assert np.array_equal(dev.site_energies(), sysm.site_energies(g))
+    e_ref = sysm.total_energy(g)
+    assert dev.total_energy(exact_order=True)[0] == e_ref
+    # deterministic tree sum: same value up to f64 rounding of a different association
+    assert abs(dev.total_energy(exact_order=False)[0] - e_ref) <= 1e-12 * max(1.0, abs(e_ref))
+
+
+def test_total_energy_small_and_tiny_boxes(bw, orc, golden):
+    """n=1 and n=2 boxes, where neighbour offsets wrap more than once."""
+    for lattice, V, S, shells in (("bcc", golden["t02_V"], 4, 6), ("fcc", golden["t01_V"], 5, 6)):
+        for n in (1, 2):
+            sysm = orc.System(lattice, n, n, n, S, shells, V)
+            c = np.zeros(S + 1); c[1:] = 1.0 / S
+            mt = orc.MT(seed=5)
+            cc, cnt = sysm.quotas(conc=c[1:])
+            g = sysm.initial_setup(mt, cc, cnt)
+            dev = bw.Device(lattice, n, n, n, S, shells, V)
+            dev.set_config(g)
+            assert dev.total_energy()[0] == sysm.total_energy(g)
+            assert np.array_equal(dev.site_energies(), sysm.site_energies(g))
+
+
+def test_total_energy_batched_replicas(bw, orc, golden):
+    V = golden["t02_V"]
+    sysm = orc.System("bcc", 4, 4, 4, 4, 6, V)
+    gs = np.stack([random_config(orc, sysm, 10 + r) for r in range(37)])
+    dev = bw.Device("bcc", 4, 4, 4, 4, 6, V, n_replicas=37)
+    dev.set_config(gs)
+    e = dev.total_energy(0, 37, exact_order=True)
+    assert np.array_equal(e, np.array([sysm.total_energy(g) for g in gs]))
+    e2 = dev.total_energy(5, 10, exact_order=False)
+    assert np.allclose(e2, e[5:15], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("lattice,shells,S", [("bcc", 4, 4), ("bcc", 6, 4), ("bcc", 10, 3), ("fcc", 4, 5), ("fcc", 6, 5), ("simple_cubic", 2, 3)])
+def test_pair_dE_bit_exact(bw, orc, lattice, shells, S):
+    V = rand_V(S, shells, 7)
+    n = (4, 5, 3)
+    sysm = orc.System(lattice, *n, S, shells, V)
+    g = random_config(orc, sysm, 99)
+    sites = np.flatnonzero(g.ravel() > 0).astype(np.int32)
+    rng = np.random.default_rng(3)
+    i1 = rng.choice(sites, 4000)
+    i2 = rng.choice(sites, 4000)
+    # force first-shell neighbours and identical sites into the batch (mutual-neighbour case)
+    offs = sysm.offsets()
+    gz, gy, gx = g.shape
+    for t in range(200):
+        x, y, z = i1[t] % gx, (i1[t] // gx) % gy, i1[t] // (gx * gy)
+        o = offs[t % len(offs)]
+        i2[t] = (((z + o[2]) % gz) * gy + (y + o[1]) % gy) * gx + (x + o[0]) % gx
+    i2[200:220] = i1[200:220]
+    dev = bw.Device(lattice, *n, S, shells, V)
+    dev.set_config(g)
+    got = dev.pair_dE(i1, i2)
+    want = sysm.pair_dE(g, i1, i2)
+    assert np.array_equal(got, want)
+    assert np.array_equal(dev.get_config(), g)           # not modified
+    with pytest.raises(bw.BrawlCudaError, match="lattice site"):
+        empty = np.flatnonzero(g.ravel() == 0)
+        if empty.size == 0:
+            raise bw.BrawlCudaError("does not address a lattice site")
+        dev.pair_dE([int(empty[0])], [int(sites[0])])
+
+
+# ---------------------------------------------------------------------------------------------
+# deterministic replay against the reference's golden files
+def replay_case(bw, orc, V, lattice, n, S, shells, rank, n_trials, conc=None, numbers=None):
+    sysm = orc.System(lattice, n, n, n, S, shells, V)
+    mt = orc.MT(rank=rank)
+    c, cnt = sysm.quotas(conc=conc, numbers=numbers)
+    g0 = sysm.initial_setup(mt, c, cnt)
+    dev = bw.Device(lattice, n, n, n, S, shells, V)
+    dev.set_config(g0)
+    e0 = dev.total_energy()[0]
+    st = mt.state625()
+    beta = 1.0 / (300.0 * bw.K_B_IN_RY)
+    acc, e = dev.metropolis_replay(beta, n_trials, st, n_sample_steps=1)
+    # oracle continues from the same MT state
+    g_ref = g0.copy()
+    e_ref, out = sysm.metropolis_sample(g_ref, mt, 300.0, n_trials, 1)
+    return dev, sysm, g0, np.concatenate([[e0], e]), acc, st, mt, g_ref, e_ref, out
+
+
+def test_replay_golden_01(bw, orc, golden):
+    dev, sysm, g0, E, acc, st, mt, g_ref, e_ref, out = replay_case(
+        bw, orc, golden["t01_V"], "fcc", 4, 5, 6, 0, 256, numbers=[51, 51, 51, 51, 52])
+    assert np.array_equal(g0, golden["t01_initial"])
+    assert np.array_equal(dev.get_config(), golden["t01_final"])
+    assert fmt.energy_trajectory(E) == str(golden["t01_energy_txt"])
+    assert np.array_equal(E[1:], e_ref)                       # bit-exact, not just to 1e-10
+    assert acc == 139 and acc / 256 == 0.54296875
+    assert np.array_equal(st, mt.state625())                  # RNG stream position identical
+    rho = dev.radial_densities(3)
+    assert np.array_equal(rho, golden["t01_rho_rho"][0])
+
+
+@pytest.mark.parametrize("rank", [0, 1, 2, 3])
+def test_replay_golden_02(bw, orc, golden, rank):
+    dev, sysm, g0, E, acc, st, mt, g_ref, e_ref, out = replay_case(
+        bw, orc, golden["t02_V"], "bcc", 4, 4, 6, rank, 128, conc=[0.25] * 4)
+    p = "t02_r%d_" % rank
+    assert np.array_equal(g0, golden[p + "initial"])
+    assert np.array_equal(dev.get_config(), golden[p + "final"])
+    assert fmt.energy_trajectory(E) == str(golden[p + "energy_txt"])
+    assert np.array_equal(E[1:], e_ref)
+    assert np.array_equal(st, mt.state625())
+    # diagnostics line from GPU energies (host arithmetic of metropolis.F90:412-433)
+    step_E = 0.0; step_Esq = 0.0
+    for e in E[1:]:
+        step_E = step_E + e; step_Esq = step_Esq + e * e
+    sim_temp = 300.0 * bw.K_B_IN_RY
+    U = step_E / 128 / 128
+    Cv = (step_Esq / 128 - (step_E / 128) ** 2) / (sim_temp * 300.0) / 128
+    assert fmt.diagnostics([300.0], [U], [max(Cv, 0.0)], [acc / 128.0]) == str(golden[p + "diag_txt"])
+    assert np.array_equal(dev.radial_densities(2), golden[p + "rho_rho"][0])
+
+
+@pytest.mark.parametrize("lattice,shells,nbr", [("bcc", 4, True), ("fcc", 4, True), ("bcc", 10, False), ("simple_cubic", 2, False), ("simple_cubic", 1, True)])
+def test_replay_matches_oracle_long(bw, orc, lattice, shells, nbr):
+    """5000 trials incl. neighbour-swap mode and odd box shapes: configuration, accept count and
+    RNG position identical to the oracle."""
+    S = 3
+    V = rand_V(S, shells, 21)
+    n = (3, 4, 5)
+    sysm = orc.System(lattice, *n, S, shells, V)
+    g = random_config(orc, sysm, 77)
+    dev = bw.Device(lattice, *n, S, shells, V)
+    dev.set_config(g)
+    mt = orc.MT(seed=2024)
+    st = mt.state625()
+    beta = 1.0 / (800.0 * bw.K_B_IN_RY)
+    acc = dev.metropolis_replay(beta, 5000, st, nbr_swap=nbr)
+    acc_ref = sysm.metropolis_trials(g, mt, beta, 5000, nbr_swap=nbr)
+    assert acc == acc_ref
+    assert np.array_equal(dev.get_config(), g)
+    assert np.array_equal(st, mt.state625())
+    assert dev.total_energy()[0] == sysm.total_energy(g)
+
+
+def test_nested_sampling_golden_03_on_gpu(bw, orc, golden):
+    """The reference's nested-sampling regression case driven from the host with every walk,
+    clone and energy on the GPU: 1000 culled energies bit-identical to the golden file."""
+    V = golden["t03_V"]
+    K, n_steps, n_iter = 100, 500, 1000
+    sysm = orc.System("fcc", 3, 3, 3, 5, 4, V)
+    mt = orc.MT(rank=0)
+    conc = np.array([0.0, 0.2, 0.2, 0.2, 0.2, 0.2]); cnt = [21, 21, 21, 21, 24]
+    dev = bw.Device("fcc", 3, 3, 3, 5, 4, V, n_replicas=K)
+    energies = np.zeros(K)
+    for w in range(K):                                   # nested_sampling.f90:78-97
+        g = sysm.initial_setup(mt, conc, cnt)
+        dev.set_config(g, w, 1)
+        rnde = mt.genrand()
+        energies[w] = dev.total_energy(w, 1)[0] + rnde * float(np.float32(1e-8))
+    st = mt.state625()
+    n_at = 27 * 5
+    extra, n_acc = 0, 0
+    culled = np.zeros(n_iter)
+    for it in range(1, n_iter + 1):
+        i_max = int(np.argmax(energies))
+        lim = energies[i_max]
+        culled[it - 1] = lim
+        if it % int(K / 2.0) == 0 and (n_acc < n_at * 0.05) and extra < n_steps * 100:
+            extra += n_steps
+        mt.load625(st)
+        rnd = mt.genrand()
+        st = mt.state625()
+        irnd = int(np.ceil(rnd * K))
+        dev.copy_replica(irnd - 1, i_max)
+        energies[i_max] = energies[irnd - 1]
+        energies[i_max], n_acc = dev.ns_walk_replay(energies[i_max], lim, n_steps + extra, st, replica=i_max)
+    lines = str(golden["t03_energies_txt"]).strip("\n").split("\n")
+    ref = np.array([float(l.split()[1]) for l in lines[1:]])
+    assert np.array_equal(culled, ref)
+
+
+def test_wl_sweeps_replay_matches_oracle(bw, orc, golden):
+    V = golden["t04_V"]
+    sysm = orc.System("bcc", 4, 4, 4, 4, 6, V)
+    g = random_config(orc, sysm, 5)
+    bins = 512
+    edges = sysm.wl_bin_edges(-96.0, 0.0, bins)
+    # a random start lies above energy_max; the reference first walks it into the window
+    # (enter_energy_window, wang-landau.F90:643-741) -- here a short oracle anneal does that
+    sysm.metropolis_trials(g, orc.MT(seed=1), 1.0 / (1500.0 * orc.K_B_IN_RY), 40 * 128)
+    e0 = sysm.total_energy(g)
+    assert edges[0] < e0 < edges[-1]
+    dev = bw.Device("bcc", 4, 4, 4, 4, 6, V)
+    dev.set_config(g)
+    mt = orc.MT(seed=99)
+    st = mt.state625()
+    for (lo, hi) in ((1, 512), (200, 512)):
+        lng = np.zeros(bins); hist = np.zeros(hi - lo + 1)
+        lng_r = lng.copy(); hist_r = hist.copy()
+        acc, ef = dev.wl_sweeps_replay(lng, hist, edges, lo, hi, 0.05000000074505806, 12800, st)
+        acc_r, ef_r = sysm.wl_sweeps(g, mt, lng_r, hist_r, edges, lo, hi, 0.05000000074505806, 12800)
+        assert acc == acc_r and ef == ef_r
+        assert np.array_equal(lng, lng_r) and np.array_equal(hist, hist_r)
+        assert np.array_equal(dev.get_config(), g)
+        assert np.array_equal(st, mt.state625())
+
+
+def test_radial_counts_match_oracle(bw, orc, golden):
+    for lattice, n, S, wc in (("bcc", (4, 4, 4), 4, 2), ("fcc", (4, 4, 4), 5, 3), ("bcc", (6, 5, 7), 3, 5), ("fcc", (5, 6, 7), 4, 4), ("bcc", (3, 3, 3), 4, 3)):
+        V = rand_V(S, 2, 1)
+        sysm = orc.System(lattice, *n, S, 2, V)
+        g = random_config(orc, sysm, 31)
+        dev = bw.Device(lattice, *n, S, 2, V)
+        dev.set_config(g)
+        shells = sysm.lattice_shells(g, wc)
+        rho_ref = sysm.radial_densities(g, wc, shells)
+        assert np.array_equal(dev.radial_densities(wc), rho_ref), (lattice, n)
+
+
+# ---------------------------------------------------------------------------------------------
+# production sampler
+def test_production_conservation_and_energy_bookkeeping(bw, orc, golden):
+    """Concurrent swaps must be non-interacting: the sum of accepted dE equals the change of the
+    exact total energy (it would not if two simultaneous trials interacted), and species counts
+    are conserved."""
+    for lattice, n, S, shells, V, nbr in (("bcc", (16, 16, 16), 4, 4, golden["ex_AlTiCrMo_V"], False),
+                                          ("bcc", (16, 12, 20), 4, 6, golden["ex_AlTiCrMo_V"], False),
+                                          ("fcc", (12, 12, 12), 5, 4, golden["ex_AlCrFeCoNi_V"], False),
+                                          ("fcc", (10, 12, 14), 5, 6, golden["t01_V"], False),
+                                          ("bcc", (16, 16, 16), 4, 4, golden["ex_AlTiCrMo_V"], True),
+                                          ("fcc", (12, 12, 12), 5, 4, golden["ex_AlCrFeCoNi_V"], True)):
+        V = V[: S * S * shells]
+        sysm = orc.System(lattice, *n, S, shells, V)
+        g = random_config(orc, sysm, 8)
+        dev = bw.Device(lattice, *n, S, shells, V)
+        plan = dev.metropolis_plan(nbr)
+        assert plan["use_box"] == 1, plan
+        dev.set_config(g)
+        e0 = dev.total_energy()[0]
+        beta = 1.0 / (600.0 * bw.K_B_IN_RY)
+        tot_dE = 0.0
+        for rep in range(3):
+            att, acc, dE = dev.metropolis_run(beta, 20 * sysm.n_atoms, nbr_swap=nbr)
+            assert att[0] >= 20 * sysm.n_atoms and 0 < acc[0] <= att[0]
+            tot_dE += dE[0]
+        g1 = dev.get_config()
+        assert np.array_equal(np.bincount(g1.ravel(), minlength=S + 1), np.bincount(g.ravel(), minlength=S + 1))
+        assert np.array_equal(g1 == 0, g == 0)
+        e1 = sysm.total_energy(g1)
+        assert e1 == dev.total_energy()[0]
+        assert e1 < e0                                        # 600 K from a random start: energy drops
+        assert abs((e1 - e0) - tot_dE) < 1e-10 * abs(e0) + 1e-12, (lattice, n, e0, e1, tot_dE)
+
+
+def test_production_is_deterministic(bw, orc, golden):
+    V = golden["ex_AlTiCrMo_V"][:64]
+    sysm = orc.System("bcc", 16, 16, 16, 4, 4, V)
+    g = random_config(orc, sysm, 8)
+    outs = []
+    for _ in range(2):
+        dev = bw.Device("bcc", 16, 16, 16, 4, 4, V)
+        dev.set_config(g)
+        res = dev.metropolis_run(1.0 / (900.0 * bw.K_B_IN_RY), 100000, seed=1234)
+        outs.append((dev.get_config().copy(), res))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0][1], outs[1][1]))
+    dev = bw.Device("bcc", 16, 16, 16, 4, 4, V)
+    dev.set_config(g)
+    dev.metropolis_run(1.0 / (900.0 * bw.K_B_IN_RY), 100000, seed=1235)
+    assert not np.array_equal(dev.get_config(), outs[0][0])
+
+
+def test_production_limits(bw, orc, golden):
+    """beta = 0: everything accepted.  beta -> infinity: only dE < 0 accepted, energy monotone."""
+    V = golden["ex_AlTiCrMo_V"][:64]
+    sysm = orc.System("bcc", 16, 16, 16, 4, 4, V)
+    g = random_config(orc, sysm, 11)
+    dev = bw.Device("bcc", 16, 16, 16, 4, 4, V)
+    dev.set_config(g)
+    att, acc, dE = dev.metropolis_run(0.0, 50000)
+    assert att[0] == acc[0]
+    e_prev = dev.total_energy()[0]
+    for _ in range(3):
+        att, acc, dE = dev.metropolis_run(1e300, 50000)
+        e = dev.total_energy()[0]
+        assert e <= e_prev and dE[0] <= 0.0
+        e_prev = e
+
+
+@pytest.mark.parametrize("lattice,n,S,shells,key,T", [("bcc", 12, 4, 4, "ex_AlTiCrMo_V", 1500.0), ("fcc", 8, 2, 4, "ex_FeNi_V", 900.0)])
+def test_production_statistics_match_oracle(bw, orc, golden, lattice, n, S, shells, key, T):
+    """Equilibrium <E>/atom and first-shell pair densities from the sublattice-parallel sampler
+    agree with the oracle's sequential reference sampler.  Tolerance: 5 standard errors of the
+    difference (both errors estimated from blocked samples) + 1e-6 Ry/atom floor."""
+    V = golden[key][: S * S * shells]
+    sysm = orc.System(lattice, n, n, n, S, shells, V)
+    N = sysm.n_atoms
+    beta = 1.0 / (T * bw.K_B_IN_RY)
+    g = random_config(orc, sysm, 3)
+    # oracle chain
+    mt = orc.MT(seed=555)
+    g_o = g.copy()
+    sysm.metropolis_trials(g_o, mt, beta, 60 * N)
+    eo, ro = [], []
+    shells_r = sysm.lattice_shells(g_o, 2)
+    for _ in range(40):
+        sysm.metropolis_trials(g_o, mt, beta, 10 * N)
+        eo.append(sysm.total_energy(g_o) / N)
+        ro.append(sysm.radial_densities(g_o, 2, shells_r)[1])
+    # GPU chains: 8 replicas
+    R = 8
+    dev = bw.Device(lattice, n, n, n, S, shells, V, n_replicas=R)
+    assert dev.metropolis_plan()["use_box"] == 1
+    dev.set_config(np.stack([g] * R))
+    dev.metropolis_run(beta, 60 * N)
+    eg, rg = [], []
+    for _ in range(20):
+        dev.metropolis_run(beta, 10 * N)
+        eg.append(dev.total_energy(0, R, exact_order=False) / N)
+        rg.append(np.mean([dev.radial_densities(2, r)[1] for r in range(R)], axis=0))
+    eo = np.array(eo); eg = np.array(eg)
+    se_o = eo.std(ddof=1) / np.sqrt(len(eo) / 4.0)            # allow for autocorrelation (x4)
+    se_g = eg.mean(axis=1).std(ddof=1) / np.sqrt(len(eg) / 4.0)
+    diff = abs(eo.mean() - eg.mean())
+    assert diff < 5.0 * np.hypot(se_o, se_g) + 1e-6, (eo.mean(), eg.mean(), se_o, se_g)
+    ro = np.array(ro); rg = np.array(rg)
+    se_r = np.hypot(ro.std(axis=0, ddof=1) / np.sqrt(len(ro) / 4.0), rg.std(axis=0, ddof=1) / np.sqrt(len(rg) / 4.0))
+    assert np.all(np.abs(ro.mean(axis=0) - rg.mean(axis=0)) < 5.0 * se_r + 0.02), (ro.mean(axis=0), rg.mean(axis=0))
+
+
+def test_chain_kernel_small_lattices(bw, orc, golden):
+    """Lattices too small for boxes run one sequential chain per replica (reference proposal
+    distribution, Philox stream): bookkeeping + statistics vs oracle on the FeNi example shape."""
+    V = golden["ex_FeNi_V"][: 2 * 2 * 4]
+    sysm = orc.System("fcc", 4, 4, 4, 2, 4, V)
+    N = sysm.n_atoms
+    R = 64
+    g = random_config(orc, sysm, 3)
+    dev = bw.Device("fcc", 4, 4, 4, 2, 4, V, n_replicas=R)
+    assert dev.metropolis_plan()["use_box"] == 0
+    dev.set_config(np.stack([g] * R))
+    beta = 1.0 / (800.0 * bw.K_B_IN_RY)
+    e0 = dev.total_energy(0, R)
+    att, acc, dE = dev.metropolis_run(beta, 200 * N)
+    assert np.all(att == 200 * N)
+    e1 = dev.total_energy(0, R)
+    assert np.allclose(e1 - e0, dE, rtol=0, atol=1e-11)
+    eg = []
+    for _ in range(10):
+        dev.metropolis_run(beta, 20 * N)
+        eg.append(dev.total_energy(0, R, exact_order=False).mean() / N)
+    mt = orc.MT(seed=9)
+    g_o = g.copy()
+    sysm.metropolis_trials(g_o, mt, beta, 200 * N)
+    eo = []
+    for _ in range(200):
+        sysm.metropolis_trials(g_o, mt, beta, 20 * N)
+        eo.append(sysm.total_energy(g_o) / N)
+    eo = np.array(eo); eg = np.array(eg)
+    se = np.hypot(eo.std(ddof=1) / np.sqrt(len(eo) / 4.0), eg.std(ddof=1) / np.sqrt(len(eg)))
+    assert abs(eo.mean() - eg.mean()) < 5 * se + 1e-6, (eo.mean(), eg.mean(), se)
+
+
+def test_wl_and_ns_production_kernels(bw, orc, golden):
+    """Philox-driven WL sweeps / NS walks for walker batches: invariants of the reference update
+    rule (ln g grows by wl_f per trial; hist counts every INT(0.02 N)-th trial; energies stay inside
+    the window / below the NS ceiling; running energy equals the exact total energy to rounding)."""
+    V = golden["t04_V"]
+    sysm = orc.System("bcc", 4, 4, 4, 4, 6, V)
+    W, bins = 48, 512
+    edges = sysm.wl_bin_edges(-96.0, 0.0, bins)
+    gs = np.stack([random_config(orc, sysm, 100 + w) for w in range(W)])
+    dev = bw.Device("bcc", 4, 4, 4, 4, 6, V, n_replicas=W)
+    dev.set_config(gs)
+    lng0 = np.zeros((W, bins)); hist0 = np.zeros((W, bins))
+    with pytest.raises(bw.BrawlCudaError, match="outside"):      # random starts lie above energy_max
+        dev.wl_sweeps(lng0, hist0, edges, 1, bins, 0.05, 10, seed=5)
+    for g in gs:
+        sysm.metropolis_trials(g, orc.MT(seed=1), 1.0 / (1500.0 * orc.K_B_IN_RY), 40 * 128)
+    dev.set_config(gs)
+    lng = np.zeros((W, bins)); hist = np.zeros((W, bins))
+    n_trials = 12800
+    acc, ef = dev.wl_sweeps(lng, hist, edges, 1, bins, 0.05, n_trials, seed=5)
+    assert np.allclose(lng.sum(axis=1), 0.05 * n_trials, rtol=1e-12)
+    assert np.array_equal(hist.sum(axis=1), np.full(W, n_trials // 2))
+    e_exact = dev.total_energy(0, W)
+    assert np.allclose(ef, e_exact, rtol=0, atol=1e-11)
+    assert np.all((ef >= edges[0]) & (ef < edges[-1]))
+    assert np.all(acc > 0)
+    # NS: walk under a ceiling
+    lim = e_exact + 1e-4
+    e2, nacc = dev.ns_walk(np.arange(W), e_exact, lim, 500, seed=6)
+    assert np.all(e2 < lim) and np.all(nacc > 0)
+    assert np.allclose(e2, dev.total_energy(0, W), rtol=0, atol=1e-11)
