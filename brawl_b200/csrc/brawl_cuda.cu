@@ -11,6 +11,7 @@
 
 #include "../../include/brawl_cuda.h"
 #include "brawl_common.cuh"
+#define BRW_TABLE_QUAL static constexpr
 #include "shell_tables.inc"
 #include "energy_kernels.cuh"
 #include "replay_kernels.cuh"
@@ -360,6 +361,16 @@ extern "C" int brawl_cuda_metropolis_replay(brawl_cuda_t *h, int replica, double
 }
 
 // ---- production Metropolis ---------------------------------------------------------------------------------
+typedef void (*BrwFastKernel)(BrwGeom, BrwBoxParams, uint8_t *, const double *, const double *, const int4 *,
+                              const int4 *, uint32_t, uint32_t, uint32_t, unsigned long long *, unsigned long long *,
+                              double *);
+struct BrwFastEntry { int lat, nsh, px, py; BrwFastKernel fn; };
+#define BRW_FAST(LAT, NSH, PX, PY) {LAT, NSH, PX, PY, brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY>}
+static const BrwFastEntry brw_fast_table[] = {
+    BRW_FAST(1, 4, 32, 32), BRW_FAST(1, 6, 32, 32), BRW_FAST(1, 4, 16, 16), BRW_FAST(1, 6, 16, 16),
+    BRW_FAST(2, 4, 32, 64), BRW_FAST(2, 6, 32, 64), BRW_FAST(2, 4, 16, 32), BRW_FAST(2, 6, 16, 32),
+};
+
 static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
   BrwPlan *&slot = *(BrwPlan **)&h->mc_plan[nbr_swap ? 1 : 0];
   if (slot && slot->valid) { *out = slot; return 0; }
@@ -415,7 +426,7 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
         int best = -1;
         for (int d = 0; d < 3; d++) {
           int nbd = B[d] / 2;
-          if ((B[d] % 4) == 0 && nbd >= 2 * m + P && (best < 0 || B[d] > B[best])) best = d;
+          if ((B[d] % 4) == 0 && nbd >= 2 * m + P && (best < 0 || B[d] >= B[best])) best = d;   // ties: z, then y, then x
         }
         if (best < 0) { if (too_big) feasible = false; break; }
         B[best] /= 2;
@@ -462,6 +473,14 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
     BRW_PLAN_CUDA(cudaMemcpy(pl->d_Vrep, vrep.data(), vrep.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (nbr_swap) BRW_PLAN_CUDA(cudaFuncSetAttribute(brw_box_metropolis_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     else BRW_PLAN_CUDA(cudaFuncSetAttribute(brw_box_metropolis_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    if (!nbr_swap && !h->disable_fast && p.M <= 1024)
+      for (const BrwFastEntry &fe : brw_fast_table)
+        if (fe.lat == g.lattice && fe.nsh == g.n_shells && fe.px == p.bxc && fe.py == p.byc) {
+          pl->fast_fn = (void *)fe.fn;
+          pl->fast_smem = (size_t)p.v_entries * 16 * 8 + 2 * sizeof(BrwStepParams) + 32 * 8 + p.box_sites;
+          pl->threads = std::min(1024, ((p.M + 31) / 32) * 32);
+          BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)fe.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
+        }
     pl->use_box = true;
     pl->n_slots = p.boxes_per_replica * h->n_replicas;
   } else {
@@ -483,6 +502,10 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
 extern "C" int brawl_cuda_metropolis_tune(brawl_cuda_t *h, int bx, int by, int bz, int steps) {
   BRW_ENTER(h);
   BRW_CUDA(cudaStreamSynchronize(h->stream));
+  // steps < 0: additionally force the generic (runtime-geometry) kernel -- used by the tests to
+  // cross-check the specialised kernels
+  h->disable_fast = steps < 0;
+  if (steps < 0) steps = -steps - 1;
   h->tune_box[0] = bx; h->tune_box[1] = by; h->tune_box[2] = bz; h->tune_steps = steps;
   for (int i = 0; i < 2; i++) { brw_free_plan((BrwPlan *)h->mc_plan[i]); h->mc_plan[i] = nullptr; }
   return 0;
@@ -494,6 +517,7 @@ extern "C" int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *o)
   if (o) {
     o[0] = pl->use_box; o[1] = pl->p.P; o[2] = pl->p.m; o[3] = pl->p.B[0]; o[4] = pl->p.B[1]; o[5] = pl->p.B[2];
     o[6] = pl->p.M; o[7] = pl->p.boxes_per_replica; o[8] = pl->p.n_disp; o[9] = pl->p.steps;
+    if (pl->fast_fn) o[0] = 2;
   }
   return 0;
 }
@@ -518,7 +542,11 @@ extern "C" int brawl_cuda_metropolis_enqueue(brawl_cuda_t *h, const double *beta
     for (int64_t ph = 0; ph < phases; ph++) {
       uint64_t phase = offset + (uint64_t)ph;
       uint32_t kk1 = k1 ^ (uint32_t)(phase >> 32) * 0x9E3779B9u;
-      if (nbr_swap)
+      if (pl->fast_fn)
+        ((BrwFastKernel)pl->fast_fn)<<<pl->n_slots, pl->threads, pl->fast_smem, h->stream>>>(
+            h->g, p, h->d_lat, h->d_beta, pl->d_Vrep, pl->d_classes, pl->d_disp, k0, kk1, (uint32_t)phase, pl->d_att,
+            pl->d_acc, pl->d_dE);
+      else if (nbr_swap)
         brw_box_metropolis_kernel<1><<<pl->n_slots, pl->threads, pl->smem, h->stream>>>(
             h->g, p, h->d_lat, h->d_beta, pl->d_Vrep, pl->d_off, pl->d_classes, pl->d_disp, k0, kk1, (uint32_t)phase,
             pl->d_att, pl->d_acc, pl->d_dE);

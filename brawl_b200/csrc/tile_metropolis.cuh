@@ -43,6 +43,8 @@ struct BrwPlan {
   double *d_Vrep = nullptr;    // [v_entries][16] lane-replicated V (layout [shell][centre][nbr])
   size_t smem = 0;
   int threads = 0;
+  void *fast_fn = nullptr;     // specialised kernel for this (lattice, shells, pitch), if instantiated
+  size_t fast_smem = 0;
   // per-box counters
   unsigned long long *d_att = nullptr, *d_acc = nullptr;
   double *d_dE = nullptr;
@@ -291,6 +293,167 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_kernel(
   }
   __shared__ unsigned int s_att[32], s_acc[32];
   if ((tid & 31) == 0) { s_att[tid >> 5] = packed_att; s_acc[tid >> 5] = packed_acc; red[tid >> 5] = dE_sum; }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long A = 0, C = 0; double D = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) { A += s_att[w]; C += s_acc[w]; D += red[w]; }
+    att_out[blockIdx.x] += A; acc_out[blockIdx.x] += C; dE_out[blockIdx.x] += D;
+  }
+}
+
+// ---- specialised kernel: compile-time geometry ---------------------------------------------------
+// Same algorithm as brw_box_metropolis_kernel<0>, instantiated for a fixed (lattice, n_shells, box
+// pitch): every neighbour offset is an immediate of the LDS that gathers it, the shell loops are
+// fully unrolled in the reference's summation order, and the lane-replicated V table is addressed
+// with one shift-add per lookup.  ~2x fewer issued instructions than the generic kernel.
+#include <utility>
+template <int LAT> struct BrwTab;
+template <> struct BrwTab<1> {
+  static constexpr int start(int n) { return brw_bcc_start[n]; }
+  static constexpr int count(int n) { return brw_bcc_count[n]; }
+  static constexpr int off(int k, int c) { return brw_bcc_off[k][c]; }
+};
+template <> struct BrwTab<2> {
+  static constexpr int start(int n) { return brw_fcc_start[n]; }
+  static constexpr int count(int n) { return brw_fcc_count[n]; }
+  static constexpr int off(int k, int c) { return brw_fcc_off[k][c]; }
+};
+template <int LAT, int N> struct BrwShellRange {
+  static constexpr int start = BrwTab<LAT>::start(N), count = BrwTab<LAT>::count(N);
+};
+constexpr int brw_fdiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+// compact shared-memory offset of neighbour K for a centre site of x-parity PAR
+template <int LAT, int PX, int PY, int PAR, int K>
+struct BrwCOff {
+  static constexpr int dx = BrwTab<LAT>::off(K, 0), dy = BrwTab<LAT>::off(K, 1), dz = BrwTab<LAT>::off(K, 2);
+  static constexpr int dxc = brw_fdiv2(PAR + dx);
+  static constexpr int dyc = LAT == 1 ? brw_fdiv2(PAR + dy) : dy;
+  static constexpr int value = (dz * PY + dyc) * PX + dxc;
+};
+template <int LAT, int PX, int PY, int PAR, int K0, int... Is>
+__device__ __forceinline__ void brw_fast_shell(const uint8_t *bc, const char *Va, const char *Vb, double &ea,
+                                               double &eb, std::integer_sequence<int, Is...>) {
+  // comma fold keeps the reference's left-to-right neighbour order
+  ((ea = __dadd_rn(ea, *reinterpret_cast<const double *>(Va + ((int)bc[BrwCOff<LAT, PX, PY, PAR, K0 + Is>::value] << 7))),
+    eb = __dadd_rn(eb, *reinterpret_cast<const double *>(Vb + ((int)bc[BrwCOff<LAT, PX, PY, PAR, K0 + Is>::value] << 7)))),
+   ...);
+}
+template <int LAT, int NSH, int PX, int PY, int PAR, int N>
+__device__ __forceinline__ void brw_fast_shells(const uint8_t *bc, const char *Vl, int S, int ca, int cb, double &Ea,
+                                                double &Eb) {
+  if constexpr (N < NSH) {
+    const char *Va = Vl + ((N * S + ca) * S) * 128, *Vb = Vl + ((N * S + cb) * S) * 128;
+    double ea = 0.0, eb = 0.0;
+    brw_fast_shell<LAT, PX, PY, PAR, BrwShellRange<LAT, N>::start>(
+        bc, Va, Vb, ea, eb, std::make_integer_sequence<int, BrwShellRange<LAT, N>::count>{});
+    if constexpr (N == 0) { Ea = ea; Eb = eb; }
+    else { Ea = __dadd_rn(Ea, ea); Eb = __dadd_rn(Eb, eb); }
+    brw_fast_shells<LAT, NSH, PX, PY, PAR, N + 1>(bc, Vl, S, ca, cb, Ea, Eb);
+  }
+}
+
+template <int LAT, int NSH, int PX, int PY>
+__global__ void __launch_bounds__(1024) brw_box_metropolis_fast_kernel(
+    BrwGeom g, BrwBoxParams p, uint8_t *__restrict__ lat, const double *__restrict__ beta,
+    const double *__restrict__ Vrep, const int4 *__restrict__ classes, const int4 *__restrict__ disp, uint32_t k0,
+    uint32_t k1, uint32_t phase_lo, unsigned long long *__restrict__ att_out,
+    unsigned long long *__restrict__ acc_out, double *__restrict__ dE_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *Vs = reinterpret_cast<double *>(smem_raw);                       // [v_entries][16]
+  BrwStepParams *sp = reinterpret_cast<BrwStepParams *>(Vs + p.v_entries * 16);   // [2]
+  double *red = reinterpret_cast<double *>(sp + 2);                        // [32]
+  uint8_t *box = reinterpret_cast<uint8_t *>(red + 32);                    // [bzc][PY][PX]
+  __shared__ unsigned int s_att[32], s_acc[32];
+
+  const int tid = threadIdx.x;
+  const int replica = blockIdx.x / p.boxes_per_replica;
+  const int bid = blockIdx.x - replica * p.boxes_per_replica;
+  const int bi = bid % p.nb[0], bj = (bid / p.nb[0]) % p.nb[1], bk = bid / (p.nb[0] * p.nb[1]);
+  uint8_t *L = lat + (long)replica * g.n_sites;
+
+  BrwPhilox4 ro = brw_philox(0xFFFFFFFEu, 0u, (uint32_t)replica, phase_lo, k0, k1);
+  const int ox = 2 * (int)brw_below(ro.x, g.gx >> 1) + bi * p.B[0];
+  const int oy = 2 * (int)brw_below(ro.y, g.gy >> 1) + bj * p.B[1];
+  const int oz = 2 * (int)brw_below(ro.z, g.gz >> 1) + bk * p.B[2];
+
+  for (int i = tid; i < p.v_entries * 16; i += blockDim.x) Vs[i] = Vrep[i];
+  // ---- load box: one thread per 4 consecutive compact-x sites of a row (coalesced byte gathers)
+  for (int idx = tid; idx < p.box_sites; idx += blockDim.x) {
+    int lxc = idx % PX, t = idx / PX, lyc = t % PY, lz = t / PY;
+    int X, Y;
+    if (LAT == 1) { X = 2 * lxc + (lz & 1); Y = 2 * lyc + (lz & 1); }
+    else { Y = lyc; X = 2 * lxc + ((lyc + lz) & 1); }
+    int gxx = ox + X; if (gxx >= g.gx) gxx -= g.gx; if (gxx >= g.gx) gxx -= g.gx;
+    int gyy = oy + Y; if (gyy >= g.gy) gyy -= g.gy; if (gyy >= g.gy) gyy -= g.gy;
+    int gzz = oz + lz; if (gzz >= g.gz) gzz -= g.gz; if (gzz >= g.gz) gzz -= g.gz;
+    box[idx] = L[brw_grid_to_compact(g, gxx, gyy, gzz)];
+  }
+  const uint32_t box_id = (uint32_t)blockIdx.x;
+  if (tid == 0) brw_make_step<0>(g, p, classes, disp, k0, k1, 0u, box_id, phase_lo, &sp[0]);
+  __syncthreads();
+
+  const double my_beta = beta[replica];
+  const char *Vl = reinterpret_cast<const char *>(Vs + (tid & 15));
+  const int S = g.S;
+  constexpr int stx_unit = 1;  // compact x units per 2 grid units
+  const int stx = (p.P >> 1) * stx_unit, sty = (LAT == 1 ? (p.P >> 1) : p.P) * PX, stz = p.P * PY * PX;
+  // this thread's coarse cell (fixed for the whole phase; blockDim >= M is guaranteed by the host)
+  const bool active = tid < p.M;
+  const int ci = tid % p.A[0], cr = tid / p.A[0], cj = cr % p.A[1], ck = cr / p.A[1];
+  const int base1 = ci * stx + cj * sty + ck * stz;
+  unsigned int n_att = 0, n_acc = 0;
+  double dE_sum = 0.0;
+  BrwPhilox4 rnd = {0, 0, 0, 0};
+
+  for (int step = 0; step < p.steps; step++) {
+    const BrwStepParams q = sp[step & 1];
+    if (active) {
+      int i2 = ci + q.s[0]; if (i2 >= p.A[0]) i2 -= p.A[0];
+      int j2 = cj + q.s[1]; if (j2 >= p.A[1]) j2 -= p.A[1];
+      int k2 = ck + q.s[2]; if (k2 >= p.A[2]) k2 -= p.A[2];
+      const int c1 = q.c1_base + base1;
+      const int c2 = q.c2_base + i2 * stx + j2 * sty + k2 * stz;
+      const int a = box[c1], b = box[c2];
+      n_att++;
+      if ((step & 3) == 0) rnd = brw_philox((uint32_t)tid, (uint32_t)step, box_id, phase_lo, k0, k1);
+      if (a != b) {
+        double E1a, E1b, E2b, E2a;
+        if (q.par1) brw_fast_shells<LAT, NSH, PX, PY, 1, 0>(box + c1, Vl, S, a, b, E1a, E1b);
+        else brw_fast_shells<LAT, NSH, PX, PY, 0, 0>(box + c1, Vl, S, a, b, E1a, E1b);
+        if (q.par2) brw_fast_shells<LAT, NSH, PX, PY, 1, 0>(box + c2, Vl, S, b, a, E2b, E2a);
+        else brw_fast_shells<LAT, NSH, PX, PY, 0, 0>(box + c2, Vl, S, b, a, E2b, E2a);
+        const double before = __dadd_rn(E1a, E2b);             // pair_energy, sites unswapped
+        const double after = __dadd_rn(E1b, E2a);              // pair_energy, sites swapped
+        const double dE = __dsub_rn(after, before);            // src/metropolis.F90:792
+        bool accept = dE < 0.0;                                // :796
+        if (!accept) {
+          const uint32_t w = (step & 3) == 0 ? rnd.x : (step & 3) == 1 ? rnd.y : (step & 3) == 2 ? rnd.z : rnd.w;
+          accept = brw_u01(w) < exp(-my_beta * dE);            // :802
+        }
+        if (accept) { box[c1] = (uint8_t)b; box[c2] = (uint8_t)a; n_acc++; dE_sum += dE; }
+      } else n_acc++;                                          // :774-777
+    }
+    if (tid == 0 && step + 1 < p.steps)
+      brw_make_step<0>(g, p, classes, disp, k0, k1, (uint32_t)(step + 1), box_id, phase_lo, &sp[(step + 1) & 1]);
+    __syncthreads();
+  }
+
+  for (int idx = tid; idx < p.box_sites; idx += blockDim.x) {
+    int lxc = idx % PX, t = idx / PX, lyc = t % PY, lz = t / PY;
+    int X, Y;
+    if (LAT == 1) { X = 2 * lxc + (lz & 1); Y = 2 * lyc + (lz & 1); }
+    else { Y = lyc; X = 2 * lxc + ((lyc + lz) & 1); }
+    int gxx = ox + X; if (gxx >= g.gx) gxx -= g.gx; if (gxx >= g.gx) gxx -= g.gx;
+    int gyy = oy + Y; if (gyy >= g.gy) gyy -= g.gy; if (gyy >= g.gy) gyy -= g.gy;
+    int gzz = oz + lz; if (gzz >= g.gz) gzz -= g.gz; if (gzz >= g.gz) gzz -= g.gz;
+    L[brw_grid_to_compact(g, gxx, gyy, gzz)] = box[idx];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n_att += __shfl_down_sync(0xffffffffu, n_att, o);
+    n_acc += __shfl_down_sync(0xffffffffu, n_acc, o);
+    dE_sum += __shfl_down_sync(0xffffffffu, dE_sum, o);
+  }
+  if ((tid & 31) == 0) { s_att[tid >> 5] = n_att; s_acc[tid >> 5] = n_acc; red[tid >> 5] = dE_sum; }
   __syncthreads();
   if (tid == 0) {
     unsigned long long A = 0, C = 0; double D = 0.0;

@@ -118,11 +118,13 @@ int brawl_cuda_metropolis_enqueue(brawl_cuda_t *h, const double *beta, int64_t n
                                   int64_t *n_attempt_planned, int *n_kernel_launches);
 int brawl_cuda_metropolis_counters(brawl_cuda_t *h, int reset, int64_t *n_attempt, int64_t *n_accept,
                                    double *dE_sum);
-/* Tuning of the box decomposition (0 = automatic): box extents in doubled-grid units, trials
- * steps per phase. */
+/* Tuning of the box decomposition (0 = automatic): box extents in doubled-grid units, trial
+ * steps per phase.  steps_per_phase = -(s+1) selects s steps AND forces the generic
+ * runtime-geometry kernel instead of a specialised instantiation (test hook). */
 int brawl_cuda_metropolis_tune(brawl_cuda_t *h, int box_x, int box_y, int box_z, int steps_per_phase);
 /* Describe the decomposition chosen: period P, margin, box extents, active cells, boxes/replica,
- * |D| (number of allowed displacement classes), 1 if the box kernel is used */
+ * |D| (number of allowed displacement classes); out10[0] = 0 chain kernel, 1 generic box kernel,
+ * 2 specialised (compile-time geometry) box kernel */
 int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *out10);
 
 /* ---- short-range order ----------------------------------------------------------------------
