@@ -7,7 +7,7 @@
 Workload (BASELINE.json configs[1]): AlTiCrMo bcc Metropolis on a 128^3 lattice (4 194 304 atoms,
 reference grid 256^3 = 16 MiB int8), 4 species at 0.25, first 4 shells of AlTiCrMo.vij (Z = 50),
 whole-lattice swaps (nbr_swap = F), T = 1000 K, synthetic random start from initial_setup
-semantics.  One "step" = --sweeps lattice sweeps = sweeps * N_atoms attempted swaps.
+semantics.  One "step" = --sweeps lattice sweeps (default 128) = sweeps * N_atoms attempted swaps.
 
 Timing: CUDA events on the launching stream around each step, L2 flushed (512 MiB memset) before
 every timed step, W warm-up steps, max over ranks.  `value` has the lattice resident in HBM;
@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--sweeps", type=int, default=16, help="lattice sweeps (N_atoms attempted swaps each) per step")
+    ap.add_argument("--sweeps", type=int, default=128, help="lattice sweeps (N_atoms attempted swaps each) per step")
     ap.add_argument("--ref-trials", type=int, default=1500000, help="--impl reference: trials per thread per step")
     ap.add_argument("--cpu-trials", type=int, default=3000000, help="cpu_baseline leg: trials per thread")
     ap.add_argument("--box", default="", help="override box extents, e.g. 64,64,32")
@@ -308,7 +308,7 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "brw_box_metropolis_kernel<0>",
+                         "traffic": traffic, "kernel": {2: "brw_box_metropolis_fast_kernel<1,4,32,32>", 1: "brw_box_metropolis_kernel<0>", 0: "brw_chain_metropolis_kernel"}[plan["use_box"]],
                          "algorithmic_bytes_per_attempt": B_ALG, "attempts_per_launch": per_launch_trials,
                          "ms_per_launch": per_launch_ms, "peak_source": peak_src,
                          "note": "lattice is L2/shared-memory resident by design; see DESIGN.md"},

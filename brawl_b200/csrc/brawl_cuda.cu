@@ -445,8 +445,9 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
     p.n_classes = (int)classes.size(); p.n_disp = (int)disp.size();
     p.boxes_per_replica = p.nb[0] * p.nb[1] * p.nb[2];
     p.v_entries = g.S * g.S * g.n_shells;
-    int steps = h->tune_steps > 0 ? h->tune_steps : (p.box_sites + p.M - 1) / p.M;
-    p.steps = std::max(8, std::min(steps, 4096));
+    // default: about two sweeps of the box per phase (amortises the box load/store)
+    int steps = h->tune_steps > 0 ? h->tune_steps : (2 * p.box_sites + p.M - 1) / p.M;
+    p.steps = std::max(8, std::min(steps, 512));
     pl->threads = std::min(1024, ((p.M + 31) / 32) * 32);
     pl->smem = (size_t)p.v_entries * 16 * 8 + (size_t)2 * g.ztot * 4 + 2 * sizeof(BrwStepParams) + 32 * 8 + p.box_sites;
     // offset tables per x-parity of the centre site
@@ -477,7 +478,7 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       for (const BrwFastEntry &fe : brw_fast_table)
         if (fe.lat == g.lattice && fe.nsh == g.n_shells && fe.px == p.bxc && fe.py == p.byc) {
           pl->fast_fn = (void *)fe.fn;
-          pl->fast_smem = (size_t)p.v_entries * 16 * 8 + 2 * sizeof(BrwStepParams) + 32 * 8 + p.box_sites;
+          pl->fast_smem = (size_t)p.v_entries * 16 * 8 + 32 * 8 + (size_t)p.steps * sizeof(BrwStepParams) + p.box_sites;
           pl->threads = std::min(1024, ((p.M + 31) / 32) * 32);
           BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)fe.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
         }

@@ -352,6 +352,29 @@ __device__ __forceinline__ void brw_fast_shells(const uint8_t *bc, const char *V
   }
 }
 
+// box <-> global copy: one warp per compact-x row (PX consecutive bytes, wrapping inside the
+// global row), rows unrolled x8 so the independent loads overlap.  STORE=false: global -> shared.
+template <int LAT, int PX, int PY, bool STORE>
+__device__ __forceinline__ void brw_box_copy(const BrwGeom &g, uint8_t *L, uint8_t *box, int n_rows, int ox, int oy,
+                                             int oz) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  static_assert(PX <= 32, "one warp covers a row");
+  const int oxc = ox >> 1;                      // origin is even: compact x origin
+#pragma unroll 8
+  for (int r = warp; r < n_rows; r += nwarps) {
+    const int lyc = r % PY, lz = r / PY;
+    int gzz = oz + lz; if (gzz >= g.gz) gzz -= g.gz; if (gzz >= g.gz) gzz -= g.gz;
+    const int Y = LAT == 1 ? 2 * lyc + (lz & 1) : lyc;
+    int gyy = oy + Y; if (gyy >= g.gy) gyy -= g.gy; if (gyy >= g.gy) gyy -= g.gy;
+    if (lane < PX) {
+      int gxc = oxc + lane; if (gxc >= g.cx) gxc -= g.cx; if (gxc >= g.cx) gxc -= g.cx;
+      const long gi = ((long)gzz * g.cy + (gyy >> g.ys)) * g.cx + gxc;
+      if (STORE) L[gi] = box[r * PX + lane];
+      else box[r * PX + lane] = L[gi];
+    }
+  }
+}
+
 template <int LAT, int NSH, int PX, int PY>
 __global__ void __launch_bounds__(1024) brw_box_metropolis_fast_kernel(
     BrwGeom g, BrwBoxParams p, uint8_t *__restrict__ lat, const double *__restrict__ beta,
@@ -360,9 +383,9 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_fast_kernel(
     unsigned long long *__restrict__ acc_out, double *__restrict__ dE_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *Vs = reinterpret_cast<double *>(smem_raw);                       // [v_entries][16]
-  BrwStepParams *sp = reinterpret_cast<BrwStepParams *>(Vs + p.v_entries * 16);   // [2]
-  double *red = reinterpret_cast<double *>(sp + 2);                        // [32]
-  uint8_t *box = reinterpret_cast<uint8_t *>(red + 32);                    // [bzc][PY][PX]
+  double *red = Vs + p.v_entries * 16;                                     // [32]
+  BrwStepParams *sp = reinterpret_cast<BrwStepParams *>(red + 32);         // [steps]
+  uint8_t *box = reinterpret_cast<uint8_t *>(sp + p.steps);                // [bzc][PY][PX]
   __shared__ unsigned int s_att[32], s_acc[32];
 
   const int tid = threadIdx.x;
@@ -375,28 +398,19 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_fast_kernel(
   const int ox = 2 * (int)brw_below(ro.x, g.gx >> 1) + bi * p.B[0];
   const int oy = 2 * (int)brw_below(ro.y, g.gy >> 1) + bj * p.B[1];
   const int oz = 2 * (int)brw_below(ro.z, g.gz >> 1) + bk * p.B[2];
+  const uint32_t box_id = (uint32_t)blockIdx.x;
 
   for (int i = tid; i < p.v_entries * 16; i += blockDim.x) Vs[i] = Vrep[i];
-  // ---- load box: one thread per 4 consecutive compact-x sites of a row (coalesced byte gathers)
-  for (int idx = tid; idx < p.box_sites; idx += blockDim.x) {
-    int lxc = idx % PX, t = idx / PX, lyc = t % PY, lz = t / PY;
-    int X, Y;
-    if (LAT == 1) { X = 2 * lxc + (lz & 1); Y = 2 * lyc + (lz & 1); }
-    else { Y = lyc; X = 2 * lxc + ((lyc + lz) & 1); }
-    int gxx = ox + X; if (gxx >= g.gx) gxx -= g.gx; if (gxx >= g.gx) gxx -= g.gx;
-    int gyy = oy + Y; if (gyy >= g.gy) gyy -= g.gy; if (gyy >= g.gy) gyy -= g.gy;
-    int gzz = oz + lz; if (gzz >= g.gz) gzz -= g.gz; if (gzz >= g.gz) gzz -= g.gz;
-    box[idx] = L[brw_grid_to_compact(g, gxx, gyy, gzz)];
-  }
-  const uint32_t box_id = (uint32_t)blockIdx.x;
-  if (tid == 0) brw_make_step<0>(g, p, classes, disp, k0, k1, 0u, box_id, phase_lo, &sp[0]);
+  // every step's CTA-uniform parameters, computed in parallel up front (one thread per step)
+  for (int st = tid; st < p.steps; st += blockDim.x)
+    brw_make_step<0>(g, p, classes, disp, k0, k1, (uint32_t)st, box_id, phase_lo, &sp[st]);
+  brw_box_copy<LAT, PX, PY, false>(g, L, box, PY * p.bzc, ox, oy, oz);
   __syncthreads();
 
   const double my_beta = beta[replica];
   const char *Vl = reinterpret_cast<const char *>(Vs + (tid & 15));
   const int S = g.S;
-  constexpr int stx_unit = 1;  // compact x units per 2 grid units
-  const int stx = (p.P >> 1) * stx_unit, sty = (LAT == 1 ? (p.P >> 1) : p.P) * PX, stz = p.P * PY * PX;
+  const int stx = p.P >> 1, sty = (LAT == 1 ? (p.P >> 1) : p.P) * PX, stz = p.P * PY * PX;
   // this thread's coarse cell (fixed for the whole phase; blockDim >= M is guaranteed by the host)
   const bool active = tid < p.M;
   const int ci = tid % p.A[0], cr = tid / p.A[0], cj = cr % p.A[1], ck = cr / p.A[1];
@@ -406,7 +420,7 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_fast_kernel(
   BrwPhilox4 rnd = {0, 0, 0, 0};
 
   for (int step = 0; step < p.steps; step++) {
-    const BrwStepParams q = sp[step & 1];
+    const BrwStepParams q = sp[step];
     if (active) {
       int i2 = ci + q.s[0]; if (i2 >= p.A[0]) i2 -= p.A[0];
       int j2 = cj + q.s[1]; if (j2 >= p.A[1]) j2 -= p.A[1];
@@ -433,21 +447,10 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_fast_kernel(
         if (accept) { box[c1] = (uint8_t)b; box[c2] = (uint8_t)a; n_acc++; dE_sum += dE; }
       } else n_acc++;                                          // :774-777
     }
-    if (tid == 0 && step + 1 < p.steps)
-      brw_make_step<0>(g, p, classes, disp, k0, k1, (uint32_t)(step + 1), box_id, phase_lo, &sp[(step + 1) & 1]);
     __syncthreads();
   }
 
-  for (int idx = tid; idx < p.box_sites; idx += blockDim.x) {
-    int lxc = idx % PX, t = idx / PX, lyc = t % PY, lz = t / PY;
-    int X, Y;
-    if (LAT == 1) { X = 2 * lxc + (lz & 1); Y = 2 * lyc + (lz & 1); }
-    else { Y = lyc; X = 2 * lxc + ((lyc + lz) & 1); }
-    int gxx = ox + X; if (gxx >= g.gx) gxx -= g.gx; if (gxx >= g.gx) gxx -= g.gx;
-    int gyy = oy + Y; if (gyy >= g.gy) gyy -= g.gy; if (gyy >= g.gy) gyy -= g.gy;
-    int gzz = oz + lz; if (gzz >= g.gz) gzz -= g.gz; if (gzz >= g.gz) gzz -= g.gz;
-    L[brw_grid_to_compact(g, gxx, gyy, gzz)] = box[idx];
-  }
+  brw_box_copy<LAT, PX, PY, true>(g, L, box, PY * p.bzc, ox, oy, oz);
   for (int o = 16; o > 0; o >>= 1) {
     n_att += __shfl_down_sync(0xffffffffu, n_att, o);
     n_acc += __shfl_down_sync(0xffffffffu, n_acc, o);
