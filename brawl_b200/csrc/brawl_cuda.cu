@@ -371,6 +371,19 @@ static const BrwFastEntry brw_fast_table[] = {
     BRW_FAST(2, 4, 32, 64), BRW_FAST(2, 6, 32, 64), BRW_FAST(2, 4, 16, 32), BRW_FAST(2, 6, 16, 32),
 };
 
+// launch helper for the warp-per-walker kernels: layout + opt-in shared memory
+template <class K>
+static int brw_walker_prepare(const BrwGeom &g, int extra_doubles, K kernel, BrwWalkerLayout &lay) {
+  lay = brw_walker_layout(g, extra_doubles);
+  if (lay.total() + sizeof(BrwWarpScratch) * BRW_WALKER_WARPS > 220 * 1024) {
+    // too much per-walker state for shared memory: drop the table, then the staging
+    lay.use_tab = 0; lay.tab_bytes = 0;
+    if (lay.total() + sizeof(BrwWarpScratch) * BRW_WALKER_WARPS > 220 * 1024) return brw_fail("walker state does not fit in shared memory");
+  }
+  if (brw_cuda_check(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total()), "cudaFuncSetAttribute")) return 1;
+  return 0;
+}
+
 static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
   BrwPlan *&slot = *(BrwPlan **)&h->mc_plan[nbr_swap ? 1 : 0];
   if (slot && slot->valid) { *out = slot; return 0; }
@@ -562,8 +575,11 @@ extern "C" int brawl_cuda_metropolis_enqueue(brawl_cuda_t *h, const double *beta
     if (next_offset) *next_offset = offset + (uint64_t)phases;
   } else {
     if (n_trials > 0) {
-      brw_chain_metropolis_kernel<<<(h->n_replicas + 63) / 64, 64, 0, h->stream>>>(
-          h->g, h->d_V, h->d_lat, h->d_beta, h->n_replicas, (long)n_trials, nbr_swap, k0, k1, (uint32_t)offset,
+      BrwWalkerLayout lay;
+      if (brw_walker_prepare(h->g, 0, brw_chain_metropolis_kernel, lay)) return 1;
+      brw_chain_metropolis_kernel<<<(h->n_replicas + BRW_WALKER_WARPS - 1) / BRW_WALKER_WARPS, 32 * BRW_WALKER_WARPS,
+                                    lay.total(), h->stream>>>(
+          h->g, lay, h->d_V, h->d_lat, h->d_beta, h->n_replicas, (long)n_trials, nbr_swap, k0, k1, (uint32_t)offset,
           (uint32_t)(offset >> 32), pl->d_att, pl->d_acc, pl->d_dE);
       BRW_LAUNCH_CHECK("brw_chain_metropolis_kernel");
       launches++;
@@ -701,7 +717,7 @@ extern "C" int brawl_cuda_wl_sweeps_replay(brawl_cuda_t *h, int replica, double 
     // the reference indexes wl_logdos(ibin) unguarded; its walkers are inside their window by
     // construction (enter_energy_window, :643-741).  Refuse anything else instead of corrupting memory.
     int ib = (int)(((e_start - edges[0]) / range) * (double)bins) + 1;
-    if (!(e_start >= edges[0]) || ib < win_lo || ib > win_hi)
+    if (!(e_start == e_start) || ib < win_lo || ib > win_hi)   // (energies up to one bin below E_0 map to bin 1, like the reference)
       return brw_fail("walker energy %.10g (bin %d) is outside its window [%d,%d]", e_start, ib, win_lo, win_hi);
   }
   brw_wl_replay_kernel<<<1, 32, 0, h->stream>>>(g, h->d_V, h->d_lat + (size_t)replica * g.n_sites, d_lng, d_hist, edges[0], range, bins,
@@ -752,11 +768,13 @@ extern "C" int brawl_cuda_wl_sweeps(brawl_cuda_t *h, int n_walkers, double *lng,
     BRW_CUDA(cudaStreamSynchronize(h->stream));
     for (int w = 0; w < n_walkers; w++) {
       int ib = (int)(((e0[w] - edges[0]) / range) * (double)bins) + 1;
-      if (!(e0[w] >= edges[0]) || ib < win_lo[w] || ib > win_hi[w])
+      if (!(e0[w] == e0[w]) || ib < win_lo[w] || ib > win_hi[w])
         return brw_fail("walker %d energy %.10g (bin %d) is outside its window [%d,%d]", w, e0[w], ib, win_lo[w], win_hi[w]);
     }
   }
-  brw_wl_walker_kernel<<<(n_walkers + 31) / 32, 32, 0, h->stream>>>(g, h->d_V, h->d_lat, d_lng, d_hist, edges[0], range, bins, d_lo, d_hi,
+  BrwWalkerLayout lay;
+  if (brw_walker_prepare(g, bins + hist_stride, brw_wl_walker_kernel, lay)) return 1;
+  brw_wl_walker_kernel<<<(n_walkers + BRW_WALKER_WARPS - 1) / BRW_WALKER_WARPS, 32 * BRW_WALKER_WARPS, lay.total(), h->stream>>>(g, lay, h->d_V, h->d_lat, d_lng, d_hist, edges[0], range, bins, d_lo, d_hi,
                                                                     hist_stride, wl_f, (long)n_trials, hist_every, nbr_swap, (uint32_t)seed,
                                                                     (uint32_t)(seed >> 32), (uint32_t)offset, (uint32_t)(offset >> 32),
                                                                     n_walkers, d_e, d_acc);
@@ -770,6 +788,54 @@ extern "C" int brawl_cuda_wl_sweeps(brawl_cuda_t *h, int n_walkers, double *lng,
   if (e_final) BRW_CUDA(cudaMemcpyAsync(e_final, d_e, sizeof(double) * n_walkers, cudaMemcpyDeviceToHost, h->stream));
   BRW_CUDA(cudaStreamSynchronize(h->stream));
   if (n_accept) for (int w = 0; w < n_walkers; w++) n_accept[w] = (int64_t)acc[w];
+  return 0;
+}
+
+extern "C" int brawl_cuda_wl_enter_window(brawl_cuda_t *h, int n_walkers, const double *target, const double *lo_e,
+                                          const double *hi_e, double inv_two_sigma_sq, int64_t max_trials, uint64_t seed,
+                                          uint64_t offset, double *energies, int32_t *entered) {
+  BRW_ENTER(h);
+  if (n_walkers < 1 || n_walkers > h->n_replicas) return brw_fail("n_walkers %d out of 1..%d", n_walkers, h->n_replicas);
+  if (!target || !lo_e || !hi_e || !energies || !entered) return brw_fail("null array argument");
+  size_t nb = (size_t)n_walkers * (4 * sizeof(double) + sizeof(int)) + 64;
+  if (brw_small(h, nb)) return 1;
+  double *d_e = (double *)h->d_small, *d_t = d_e + n_walkers, *d_lo = d_t + n_walkers, *d_hi = d_lo + n_walkers;
+  int *d_ent = (int *)(d_hi + n_walkers);
+  BRW_CUDA(cudaMemcpyAsync(d_t, target, sizeof(double) * n_walkers, cudaMemcpyHostToDevice, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(d_lo, lo_e, sizeof(double) * n_walkers, cudaMemcpyHostToDevice, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(d_hi, hi_e, sizeof(double) * n_walkers, cudaMemcpyHostToDevice, h->stream));
+  if (brw_total_energy_dev(h, 0, n_walkers, 1, d_e)) return 1;                    // :658
+  BrwWalkerLayout lay;
+  if (brw_walker_prepare(h->g, 0, brw_wl_enter_window_kernel, lay)) return 1;
+  brw_wl_enter_window_kernel<<<(n_walkers + BRW_WALKER_WARPS - 1) / BRW_WALKER_WARPS, 32 * BRW_WALKER_WARPS, lay.total(), h->stream>>>(
+      h->g, lay, h->d_V, h->d_lat, d_t, d_lo, d_hi, inv_two_sigma_sq, (long)max_trials, (uint32_t)seed, (uint32_t)(seed >> 32),
+      (uint32_t)offset, (uint32_t)(offset >> 32), n_walkers, d_e, d_ent);
+  BRW_LAUNCH_CHECK("brw_wl_enter_window_kernel");
+  BRW_CUDA(cudaMemcpyAsync(energies, d_e, sizeof(double) * n_walkers, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(entered, d_ent, sizeof(int) * n_walkers, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int brawl_cuda_lattice_ptr(brawl_cuda_t *h, void **dev_ptr, int64_t *bytes_per_replica) {
+  if (!h) return brw_fail("null handle");
+  if (dev_ptr) *dev_ptr = h->d_lat;
+  if (bytes_per_replica) *bytes_per_replica = h->g.n_sites;
+  return 0;
+}
+
+__global__ void brw_swap_replicas_kernel(uint8_t *a, uint8_t *b, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint8_t t = a[i]; a[i] = b[i]; b[i] = t;
+  }
+}
+extern "C" int brawl_cuda_swap_replicas(brawl_cuda_t *h, int a, int b) {
+  BRW_ENTER(h);
+  BRW_REPLICA(h, a); BRW_REPLICA(h, b);
+  if (a == b) return 0;
+  brw_swap_replicas_kernel<<<grid_for(h->g.n_sites, 256, 148), 256, 0, h->stream>>>(
+      h->d_lat + (size_t)a * h->g.n_sites, h->d_lat + (size_t)b * h->g.n_sites, h->g.n_sites);
+  BRW_LAUNCH_CHECK("brw_swap_replicas_kernel");
   return 0;
 }
 
@@ -822,7 +888,9 @@ extern "C" int brawl_cuda_ns_walk(brawl_cuda_t *h, int n_walkers, const int32_t 
   BRW_CUDA(cudaMemcpyAsync(d_e, energies, sizeof(double) * n_walkers, cudaMemcpyHostToDevice, h->stream));
   BRW_CUDA(cudaMemcpyAsync(d_lim, e_limit, sizeof(double) * n_walkers, cudaMemcpyHostToDevice, h->stream));
   BRW_CUDA(cudaMemcpyAsync(d_ids, ids, sizeof(int) * n_walkers, cudaMemcpyHostToDevice, h->stream));
-  brw_ns_walker_kernel<<<(n_walkers + 31) / 32, 32, 0, h->stream>>>(h->g, h->d_V, h->d_lat, d_ids, d_e, d_lim, (long)n_steps, (uint32_t)seed,
+  BrwWalkerLayout lay;
+  if (brw_walker_prepare(h->g, 0, brw_ns_walker_kernel, lay)) return 1;
+  brw_ns_walker_kernel<<<(n_walkers + BRW_WALKER_WARPS - 1) / BRW_WALKER_WARPS, 32 * BRW_WALKER_WARPS, lay.total(), h->stream>>>(h->g, lay, h->d_V, h->d_lat, d_ids, d_e, d_lim, (long)n_steps, (uint32_t)seed,
                                                                     (uint32_t)(seed >> 32), (uint32_t)offset, (uint32_t)(offset >> 32),
                                                                     n_walkers, d_acc);
   BRW_LAUNCH_CHECK("brw_ns_walker_kernel");

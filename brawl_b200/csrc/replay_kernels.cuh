@@ -11,51 +11,87 @@
 #pragma once
 #include "brawl_common.cuh"
 
+struct BrwWarpScratch {
+  double val[4][BRW_MAX_Z];          // [0]=site1 before, [1]=site2 before, [2]=site1 after, [3]=site2 after
+  double ssum[4][BRW_MAX_SHELLS];    // per-shell partial sums of the four combinations
+};
 struct BrwReplaySmem {
   BrwMT mt;
-  double val[4][BRW_MAX_Z];   // [0]=site1 before, [1]=site2 before, [2]=site1 after, [3]=site2 after
+  BrwWarpScratch w;
 };
 
-// Full-warp evaluation of pair_energy before and after exchanging grid sites 1 and 2.
-// Returns (identical in all lanes) before/after.  `need_after` false skips the post-swap pair
-// (Wang-Landau: same-species proposals reuse pair_unswapped, src/wang-landau.F90:561-569).
-__device__ __forceinline__ void brw_warp_pair_energies(const BrwGeom &g, const double *__restrict__ V,
-                                                       const uint8_t *lat, int x1, int y1, int z1, int x2,
-                                                       int y2, int z2, int s1, int s2, bool need_after,
-                                                       double (*val)[BRW_MAX_Z], double &before, double &after) {
+// neighbour-index providers for brw_warp_pair_energies
+struct BrwNbrWrap {          // wrap arithmetic on the doubled grid (any lattice size)
+  const BrwGeom &g;
+  int x1, y1, z1, x2, y2, z2;
+  __device__ __forceinline__ int n1(int k) const { return brw_nbr(g, x1, y1, z1, k); }
+  __device__ __forceinline__ int n2(int k) const { return brw_nbr(g, x2, y2, z2, k); }
+};
+struct BrwNbrTable {         // precomputed table tab[site*ztot + k] (small lattices, shared memory)
+  const unsigned short *t1, *t2;
+  __device__ __forceinline__ int n1(int k) const { return t1[k]; }
+  __device__ __forceinline__ int n2(int k) const { return t2[k]; }
+};
+
+// Full-warp evaluation of pair_energy before and after exchanging compact sites c1 and c2.
+// Returns (identical in all lanes) before/after.
+// Arithmetic: each (combination, shell) chain is a sequential f64 sum from 0.0 in the reference's
+// neighbour order, done by one lane; lanes 0..3 then combine the shells left to right -- exactly the
+// association of <lattice>_shellK_energy / <lattice>_energy_Nshells.  V may live in global or
+// shared memory.
+template <class Nbr>
+__device__ __forceinline__ void brw_warp_pair_energies_t(const BrwGeom &g, const double *V, const uint8_t *lat,
+                                                         const Nbr &nb, int c1, int c2, int s1, int s2,
+                                                         BrwWarpScratch *w, double &before, double &after) {
   const int lane = threadIdx.x & 31;
-  const int c1 = brw_grid_to_compact(g, x1, y1, z1), c2 = brw_grid_to_compact(g, x2, y2, z2);
   const int SS = g.S * g.S;
   for (int k = lane; k < g.ztot; k += 32) {
     const double *Vn = V + g.off[k][3] * SS;
-    int n1 = brw_nbr(g, x1, y1, z1, k), n2 = brw_nbr(g, x2, y2, z2, k);
+    int n1 = nb.n1(k), n2 = nb.n2(k);
     int t1 = lat[n1], t2 = lat[n2];
-    val[0][k] = __ldg(Vn + t1 * g.S + s1);
-    val[1][k] = __ldg(Vn + t2 * g.S + s2);
+    w->val[0][k] = Vn[t1 * g.S + s1];
+    w->val[1][k] = Vn[t2 * g.S + s2];
     // after the exchange: site 1 holds s2, site 2 holds s1, and a neighbour that *is* one of the
     // two sites shows the exchanged occupant
     int u1 = n1 == c1 ? s2 : (n1 == c2 ? s1 : t1);
     int u2 = n2 == c1 ? s2 : (n2 == c2 ? s1 : t2);
-    val[2][k] = __ldg(Vn + u1 * g.S + s2);
-    val[3][k] = __ldg(Vn + u2 * g.S + s1);
+    w->val[2][k] = Vn[u1 * g.S + s2];
+    w->val[3][k] = Vn[u2 * g.S + s1];
+  }
+  __syncwarp();
+  {
+    const int c = lane & 3;
+    const double *v = w->val[c];
+    for (int n = lane >> 2; n < g.n_shells; n += 8) {
+      double e = 0.0;
+      const int end = g.shell_end[n];
+#pragma unroll 4
+      for (int k = n ? g.shell_end[n - 1] : 0; k < end; k++) e = __dadd_rn(e, v[k]);
+      w->ssum[c][n] = e;
+    }
   }
   __syncwarp();
   double tot = 0.0;
   if (lane < 4) {
-    const double *v = val[lane];
-    int k = 0;
-    for (int n = 0; n < g.n_shells; n++) {
-      double e = 0.0;
-      const int end = g.shell_end[n];
-      for (; k < end; k++) e = __dadd_rn(e, v[k]);
-      tot = (n == 0) ? e : __dadd_rn(tot, e);
-    }
+    tot = w->ssum[lane][0];
+    for (int n = 1; n < g.n_shells; n++) tot = __dadd_rn(tot, w->ssum[lane][n]);
   }
   double e0 = __shfl_sync(0xffffffffu, tot, 0), e1 = __shfl_sync(0xffffffffu, tot, 1);
   double e2 = __shfl_sync(0xffffffffu, tot, 2), e3 = __shfl_sync(0xffffffffu, tot, 3);
   before = __dadd_rn(e0, e1);
-  after = need_after ? __dadd_rn(e2, e3) : before;
+  after = __dadd_rn(e2, e3);
   __syncwarp();
+}
+// grid-coordinate form used by the replay kernels (`need_after` false: Wang-Landau same-species
+// proposals reuse pair_unswapped, src/wang-landau.F90:561-569)
+__device__ __forceinline__ void brw_warp_pair_energies(const BrwGeom &g, const double *__restrict__ V,
+                                                       const uint8_t *lat, int x1, int y1, int z1, int x2,
+                                                       int y2, int z2, int s1, int s2, bool need_after,
+                                                       BrwWarpScratch *w, double &before, double &after) {
+  BrwNbrWrap nb{g, x1, y1, z1, x2, y2, z2};
+  brw_warp_pair_energies_t(g, V, lat, nb, brw_grid_to_compact(g, x1, y1, z1), brw_grid_to_compact(g, x2, y2, z2), s1, s2,
+                           w, before, after);
+  if (!need_after) after = before;
 }
 
 __device__ __forceinline__ void brw_mt_load(BrwMT *mt, const uint32_t *state625) {
@@ -94,7 +130,7 @@ __device__ __forceinline__ int brw_warp_mc_step(const BrwGeom &g, const double *
   const int s1 = lat[c1], s2 = lat[c2];
   if (s1 == s2) return 1;                                   // :774-777 (no energy, no RNG)
   double before, after;
-  brw_warp_pair_energies(g, V, lat, x1, y1, z1, x2, y2, z2, s1, s2, true, sm->val, before, after);
+  brw_warp_pair_energies(g, V, lat, x1, y1, z1, x2, y2, z2, s1, s2, true, &sm->w, before, after);
   const double delta_e = __dsub_rn(after, before);          // :792
   int accept = 0;
   if ((threadIdx.x & 31) == 0) {
@@ -167,7 +203,7 @@ __global__ void __launch_bounds__(32) brw_wl_replay_kernel(BrwGeom g, const doub
     const int c1 = brw_grid_to_compact(g, x1, y1, z1), c2 = brw_grid_to_compact(g, x2, y2, z2);
     const int s1 = lat[c1], s2 = lat[c2];
     double pair_unswapped, pair_swapped;
-    brw_warp_pair_energies(g, V, lat, x1, y1, z1, x2, y2, z2, s1, s2, s1 != s2, sm.val, pair_unswapped, pair_swapped);
+    brw_warp_pair_energies(g, V, lat, x1, y1, z1, x2, y2, z2, s1, s2, s1 != s2, &sm.w, pair_unswapped, pair_swapped);
     e_swapped = e_unswapped;
     if (s1 != s2) e_swapped = __dadd_rn(__dsub_rn(e_unswapped, pair_unswapped), pair_swapped);   // :568
     int ibin = brw_bin_index(e_unswapped, edge0, range, bins), jbin = brw_bin_index(e_swapped, edge0, range, bins);
@@ -215,7 +251,7 @@ __global__ void __launch_bounds__(32) brw_ns_replay_kernel(BrwGeom g, const doub
     c1 = __shfl_sync(0xffffffffu, c1, 0); c2 = __shfl_sync(0xffffffffu, c2, 0);
     s1 = __shfl_sync(0xffffffffu, s1, 0); s2 = __shfl_sync(0xffffffffu, s2, 0);
     double before, after;
-    brw_warp_pair_energies(g, V, lat, x1, y1, z1, x2, y2, z2, s1, s2, true, sm.val, before, after);
+    brw_warp_pair_energies(g, V, lat, x1, y1, z1, x2, y2, z2, s1, s2, true, &sm.w, before, after);
     const double delta_e = __dsub_rn(after, before);
     if (__dadd_rn(E, delta_e) < e_limit) {                        // :183-186
       E = __dadd_rn(E, delta_e);

@@ -464,36 +464,3 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_fast_kernel(
     att_out[blockIdx.x] += A; acc_out[blockIdx.x] += C; dE_out[blockIdx.x] += D;
   }
 }
-
-// ---- sequential chain per replica (lattices too small for boxes) ---------------------------------
-// One thread per replica, uniform random site pairs exactly as the reference proposes them
-// (src/random_site.f90), Philox stream per replica.  Lattice stays in global memory (L1/L2).
-__global__ void brw_chain_metropolis_kernel(BrwGeom g, const double *__restrict__ V, uint8_t *lat,
-                                            const double *__restrict__ beta, int n_rep, long n_trials, int nbr_swap,
-                                            uint32_t k0, uint32_t k1, uint32_t off_lo, uint32_t off_hi,
-                                            unsigned long long *att_out, unsigned long long *acc_out, double *dE_out) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_rep) return;
-  uint8_t *L = lat + (long)r * g.n_sites;
-  const double b = beta[r];
-  unsigned long long acc = 0;
-  double dsum = 0.0;
-  for (long t = 0; t < n_trials; t++) {
-    BrwPhilox4 r1 = brw_philox((uint32_t)t, (uint32_t)(t >> 32) ^ 0x10000000u, (uint32_t)r, off_lo, k0, k1 ^ off_hi);
-    BrwPhilox4 r2 = brw_philox((uint32_t)t, (uint32_t)(t >> 32) ^ 0x20000000u, (uint32_t)r, off_lo, k0, k1 ^ off_hi);
-    int x1, y1, z1, x2, y2, z2;
-    brw_random_site(g, brw_u01(r1.x), brw_u01(r1.y), brw_u01(r1.z), x1, y1, z1);
-    if (nbr_swap) brw_random_nbr(g, brw_u01(r1.w), x1, y1, z1, x2, y2, z2);
-    else brw_random_site(g, brw_u01(r2.x), brw_u01(r2.y), brw_u01(r2.z), x2, y2, z2);
-    int c1 = brw_grid_to_compact(g, x1, y1, z1), c2 = brw_grid_to_compact(g, x2, y2, z2);
-    int s1 = L[c1], s2 = L[c2];
-    if (s1 == s2) { acc++; continue; }
-    double before, after;
-    brw_pair_energies(g, V, L, c1, c2, before, after);
-    double dE = __dsub_rn(after, before);
-    bool accept = dE < 0.0;
-    if (!accept) accept = brw_u01(r2.w) < exp(-b * dE);
-    if (accept) { L[c1] = (uint8_t)s2; L[c2] = (uint8_t)s1; acc++; dsum += dE; }
-  }
-  att_out[r] += (unsigned long long)n_trials; acc_out[r] += acc; dE_out[r] += dsum;
-}

@@ -1,53 +1,242 @@
-// walker_kernels.cuh -- production (Philox) Wang-Landau sweeps and nested-sampling walks for
-// batches of independent walkers on small lattices: one thread per walker, each an exact
-// sequential chain with the reference's proposal distribution and f64 energy association.
-//   WL : src/wang-landau.F90:539-626 (sweeps), :515-523 (bin_index)
-//   NS : src/nested_sampling.f90:157-192
+// walker_kernels.cuh -- production (Philox) kernels for batches of independent walkers/replicas on
+// small lattices: ONE WARP PER WALKER, each an exact sequential chain with the reference's proposal
+// distribution and f64 energy association (brw_warp_pair_energies); the walker's lattice is staged
+// in shared memory for the whole call.
+//   Metropolis : src/metropolis.F90:751-891 (k-loop :348-354), lattices too small for boxes
+//   WL         : src/wang-landau.F90:539-626 (sweeps), :515-523 (bin_index), :643-741 (enter_energy_window)
+//   NS         : src/nested_sampling.f90:157-192
+// RNG: Philox4x32-10, counter = (trial, stream tag, walker, offset), key = seed.  Lane 0 draws.
 #pragma once
 #include "brawl_common.cuh"
-#include "replay_kernels.cuh"   // brw_bin_index
+#include "replay_kernels.cuh"   // brw_warp_pair_energies, brw_bin_index
 
-__global__ void brw_wl_walker_kernel(BrwGeom g, const double *__restrict__ V, uint8_t *lat, double *lng, double *hist,
-                                     double edge0, double range, int bins, const int *__restrict__ win_lo,
-                                     const int *__restrict__ win_hi, int hist_stride, double wl_f, long n_trials,
-                                     int hist_every, int nbr_swap, uint32_t k0, uint32_t k1, uint32_t off_lo,
-                                     uint32_t off_hi, int n_walkers, double *e_io, unsigned long long *n_accept) {
-  int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= n_walkers) return;
-  uint8_t *L = lat + (long)w * g.n_sites;
-  double *my_lng = lng + (long)w * bins, *my_hist = hist + (long)w * hist_stride;
-  const int lo = win_lo[w], hi = win_hi[w];
-  double e_unswapped = e_io[w], e_swapped;
-  unsigned long long accepted = 0;
-  for (long i = 1; i <= n_trials; i++) {
-    BrwPhilox4 r1 = brw_philox((uint32_t)i, (uint32_t)(i >> 32) ^ 0x30000000u, (uint32_t)w, off_lo, k0, k1 ^ off_hi);
-    BrwPhilox4 r2 = brw_philox((uint32_t)i, (uint32_t)(i >> 32) ^ 0x40000000u, (uint32_t)w, off_lo, k0, k1 ^ off_hi);
-    int x1, y1, z1, x2, y2, z2;
+#define BRW_WALKER_WARPS 4          // warps (= walkers) per CTA
+#define BRW_WALKER_SMEM_SITES 4096  // lattices up to this many sites are staged in shared memory
+#define BRW_WALKER_TAB_BYTES 65536  // neighbour-index table is used when n_sites*ztot*2 fits in this
+
+// Dynamic shared-memory layout of the walker kernels (host mirror: brw_walker_layout):
+//   [ V : S*S*n_shells f64 ][ nbr table : n_sites*ztot u16 (optional) ]
+//   then per warp: [ lattice : n_sites bytes, padded to 8 (optional) ][ extra f64 words ]
+struct BrwWalkerLayout {
+  int use_tab, staged;
+  int v_bytes, tab_bytes, lat_bytes, extra_bytes;   // extra = per-warp f64 scratch (WL: ln g + hist)
+  __host__ __device__ size_t total() const { return (size_t)v_bytes + tab_bytes + (size_t)BRW_WALKER_WARPS * (lat_bytes + extra_bytes); }
+};
+static inline BrwWalkerLayout brw_walker_layout(const BrwGeom &g, int extra_doubles) {
+  BrwWalkerLayout L;
+  L.v_bytes = g.S * g.S * g.n_shells * 8;
+  L.staged = g.n_sites <= BRW_WALKER_SMEM_SITES;
+  L.use_tab = L.staged && (size_t)g.n_sites * g.ztot * 2 <= BRW_WALKER_TAB_BYTES && g.n_sites <= 65535;
+  L.tab_bytes = L.use_tab ? ((g.n_sites * g.ztot * 2 + 7) & ~7) : 0;
+  L.lat_bytes = L.staged ? ((g.n_sites + 7) & ~7) : 0;
+  L.extra_bytes = extra_doubles * 8;
+  return L;
+}
+
+struct BrwWalkerCtx {
+  uint8_t *L;                  // the walker's lattice (shared-memory copy, or global if too large)
+  uint8_t *G;                  // its home in global memory
+  const double *V;             // V_ex in shared memory
+  const unsigned short *tab;   // neighbour table or nullptr
+  double *extra;               // per-warp f64 scratch
+  bool staged;
+};
+
+// CTA-wide set-up: V and the neighbour table are built cooperatively, each warp stages its lattice.
+__device__ __forceinline__ BrwWalkerCtx brw_walker_begin(const BrwGeom &g, const BrwWalkerLayout &lay,
+                                                         const double *__restrict__ Vg, uint8_t *lat_global,
+                                                         unsigned char *smem, bool valid) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *Vs = reinterpret_cast<double *>(smem);
+  unsigned short *tab = reinterpret_cast<unsigned short *>(smem + lay.v_bytes);
+  for (int i = threadIdx.x; i < g.S * g.S * g.n_shells; i += blockDim.x) Vs[i] = Vg[i];
+  if (lay.use_tab)
+    for (int i = threadIdx.x; i < g.n_sites * g.ztot; i += blockDim.x) {
+      int c = i / g.ztot, k = i - c * g.ztot, x, y, z;
+      brw_compact_to_grid(g, c, x, y, z);
+      tab[i] = (unsigned short)brw_nbr(g, x, y, z, k);
+    }
+  BrwWalkerCtx c;
+  unsigned char *mine = smem + lay.v_bytes + lay.tab_bytes + (size_t)warp * (lay.lat_bytes + lay.extra_bytes);
+  c.G = lat_global;
+  c.V = Vs;
+  c.tab = lay.use_tab ? tab : nullptr;
+  c.staged = lay.staged;
+  c.L = lay.staged ? mine : lat_global;
+  c.extra = reinterpret_cast<double *>(mine + lay.lat_bytes);
+  if (lay.staged && valid)
+    for (int i = lane; i < g.n_sites; i += 32) c.L[i] = lat_global[i];
+  __syncthreads();
+  return c;
+}
+__device__ __forceinline__ void brw_walker_end(const BrwGeom &g, const BrwWalkerCtx &c) {
+  if (c.staged) {
+    __syncwarp();
+    for (int i = (threadIdx.x & 31); i < g.n_sites; i += 32) c.G[i] = c.L[i];
+  }
+}
+__device__ __forceinline__ void brw_walker_pair(const BrwGeom &g, const BrwWalkerCtx &c, int x1, int y1, int z1, int x2,
+                                                int y2, int z2, int c1, int c2, int s1, int s2, BrwWarpScratch *w,
+                                                double &before, double &after) {
+  if (c.tab) {
+    BrwNbrTable nb{c.tab + c1 * g.ztot, c.tab + c2 * g.ztot};
+    brw_warp_pair_energies_t(g, c.V, c.L, nb, c1, c2, s1, s2, w, before, after);
+  } else {
+    BrwNbrWrap nb{g, x1, y1, z1, x2, y2, z2};
+    brw_warp_pair_energies_t(g, c.V, c.L, nb, c1, c2, s1, s2, w, before, after);
+  }
+}
+// lane 0 draws two sites (or site + first-shell neighbour) from one/two Philox blocks; broadcast.
+// Returns the spare uniform (4th word of the second block) in all lanes for the accept test.
+__device__ __forceinline__ uint32_t brw_warp_propose_philox(const BrwGeom &g, int nbr_swap, uint32_t t_lo, uint32_t t_hi,
+                                                            uint32_t walker, uint32_t off_lo, uint32_t k0, uint32_t k1,
+                                                            int &x1, int &y1, int &z1, int &x2, int &y2, int &z2) {
+  uint32_t spare = 0;
+  if ((threadIdx.x & 31) == 0) {
+    BrwPhilox4 r1 = brw_philox(t_lo, t_hi ^ 0x10000000u, walker, off_lo, k0, k1);
+    BrwPhilox4 r2 = brw_philox(t_lo, t_hi ^ 0x20000000u, walker, off_lo, k0, k1);
     brw_random_site(g, brw_u01(r1.x), brw_u01(r1.y), brw_u01(r1.z), x1, y1, z1);
     if (nbr_swap) brw_random_nbr(g, brw_u01(r1.w), x1, y1, z1, x2, y2, z2);
     else brw_random_site(g, brw_u01(r2.x), brw_u01(r2.y), brw_u01(r2.z), x2, y2, z2);
+    spare = r2.w;
+  }
+  x1 = __shfl_sync(0xffffffffu, x1, 0); y1 = __shfl_sync(0xffffffffu, y1, 0); z1 = __shfl_sync(0xffffffffu, z1, 0);
+  x2 = __shfl_sync(0xffffffffu, x2, 0); y2 = __shfl_sync(0xffffffffu, y2, 0); z2 = __shfl_sync(0xffffffffu, z2, 0);
+  return __shfl_sync(0xffffffffu, spare, 0);
+}
+
+// ---- Metropolis chains -------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_chain_metropolis_kernel(
+    BrwGeom g, BrwWalkerLayout lay, const double *__restrict__ V, uint8_t *lat, const double *__restrict__ beta,
+    int n_rep, long n_trials, int nbr_swap, uint32_t k0, uint32_t k1, uint32_t off_lo, uint32_t off_hi,
+    unsigned long long *att_out, unsigned long long *acc_out, double *dE_out) {
+  __shared__ BrwWarpScratch scratch[BRW_WALKER_WARPS];
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * BRW_WALKER_WARPS + warp;
+  const bool valid = r < n_rep;
+  BrwWalkerCtx c = brw_walker_begin(g, lay, V, lat + (long)(valid ? r : 0) * g.n_sites, dsm, valid);
+  if (!valid) return;
+  const double b = beta[r];
+  unsigned long long acc = 0;
+  double dsum = 0.0;
+  for (long t = 0; t < n_trials; t++) {
+    int x1 = 0, y1 = 0, z1 = 0, x2 = 0, y2 = 0, z2 = 0;
+    uint32_t w = brw_warp_propose_philox(g, nbr_swap, (uint32_t)t, (uint32_t)(t >> 32), (uint32_t)r, off_lo, k0,
+                                         k1 ^ off_hi, x1, y1, z1, x2, y2, z2);
     const int c1 = brw_grid_to_compact(g, x1, y1, z1), c2 = brw_grid_to_compact(g, x2, y2, z2);
-    const int s1 = L[c1], s2 = L[c2];
+    const int s1 = c.L[c1], s2 = c.L[c2];
+    if (s1 == s2) { acc++; continue; }                        // src/metropolis.F90:774-777
+    double before, after;
+    brw_walker_pair(g, c, x1, y1, z1, x2, y2, z2, c1, c2, s1, s2, &scratch[warp], before, after);
+    const double dE = __dsub_rn(after, before);
+    bool accept = dE < 0.0;
+    if (!accept) accept = brw_u01(w) < exp(-b * dE);
+    if (accept) {
+      if (lane == 0) { c.L[c1] = (uint8_t)s2; c.L[c2] = (uint8_t)s1; }
+      acc++; dsum += dE;
+    }
+    __syncwarp();
+  }
+  brw_walker_end(g, c);
+  if (lane == 0) { att_out[r] += (unsigned long long)n_trials; acc_out[r] += acc; dE_out[r] += dsum; }
+}
+
+// ---- Wang-Landau sweeps ---------------------------------------------------------------------------
+// ln g (all bins) and the window's hist slice of each walker are staged in shared memory for the call.
+__global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_wl_walker_kernel(
+    BrwGeom g, BrwWalkerLayout lay, const double *__restrict__ V, uint8_t *lat, double *lng, double *hist, double edge0,
+    double range, int bins, const int *__restrict__ win_lo, const int *__restrict__ win_hi, int hist_stride, double wl_f,
+    long n_trials, int hist_every, int nbr_swap, uint32_t k0, uint32_t k1, uint32_t off_lo, uint32_t off_hi,
+    int n_walkers, double *e_io, unsigned long long *n_accept) {
+  __shared__ BrwWarpScratch scratch[BRW_WALKER_WARPS];
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * BRW_WALKER_WARPS + warp;
+  const bool valid = w < n_walkers;
+  BrwWalkerCtx c = brw_walker_begin(g, lay, V, lat + (long)(valid ? w : 0) * g.n_sites, dsm, valid);
+  if (!valid) return;
+  double *g_lng = lng + (long)w * bins, *g_hist = hist + (long)w * hist_stride;
+  const int lo = win_lo[w], hi = win_hi[w], nh = hi - lo + 1;
+  double *my_lng = c.extra, *my_hist = c.extra + bins;
+  for (int i = lane; i < bins; i += 32) my_lng[i] = g_lng[i];
+  for (int i = lane; i < nh; i += 32) my_hist[i] = g_hist[i];
+  __syncwarp();
+  double e_unswapped = e_io[w], e_swapped;
+  unsigned long long accepted = 0;
+  for (long i = 1; i <= n_trials; i++) {
+    int x1 = 0, y1 = 0, z1 = 0, x2 = 0, y2 = 0, z2 = 0;
+    uint32_t u = brw_warp_propose_philox(g, nbr_swap, (uint32_t)i, (uint32_t)(i >> 32) ^ 0x01000000u, (uint32_t)w, off_lo,
+                                         k0, k1 ^ off_hi, x1, y1, z1, x2, y2, z2);
+    const int c1 = brw_grid_to_compact(g, x1, y1, z1), c2 = brw_grid_to_compact(g, x2, y2, z2);
+    const int s1 = c.L[c1], s2 = c.L[c2];
     e_swapped = e_unswapped;
     if (s1 != s2) {
       double pair_unswapped, pair_swapped;
-      brw_pair_energies(g, V, L, c1, c2, pair_unswapped, pair_swapped);
-      e_swapped = __dadd_rn(__dsub_rn(e_unswapped, pair_unswapped), pair_swapped);    // :568
+      brw_walker_pair(g, c, x1, y1, z1, x2, y2, z2, c1, c2, s1, s2, &scratch[warp], pair_unswapped, pair_swapped);
+      e_swapped = __dadd_rn(__dsub_rn(e_unswapped, pair_unswapped), pair_swapped);      // :568
     }
     int ibin = brw_bin_index(e_unswapped, edge0, range, bins), jbin = brw_bin_index(e_swapped, edge0, range, bins);
-    if (jbin > lo - 1 && jbin < hi + 1) {
-      // u == 0 gives log = -inf: accepted, as in the reference
-      if (log(brw_u01(r2.w)) < (my_lng[ibin - 1] - my_lng[jbin - 1])) {               // :598
-        accepted++;
-        e_unswapped = e_swapped;
-        L[c1] = (uint8_t)s2; L[c2] = (uint8_t)s1;
+    // decision on lane 0 (it owns ln g / hist); u == 0 gives log = -inf: accepted, as in the reference
+    int acc = 0;
+    if (lane == 0) {
+      if (jbin > lo - 1 && jbin < hi + 1) {
+        if (log(brw_u01(u)) < (my_lng[ibin - 1] - my_lng[jbin - 1])) {                   // :598
+          acc = 1;
+          c.L[c1] = (uint8_t)s2; c.L[c2] = (uint8_t)s1;
+        } else jbin = ibin;
       } else jbin = ibin;
-    } else jbin = ibin;
-    if (hist_every > 0 && i % hist_every == 0) my_hist[jbin - lo] += 1.0;             // :605-606
-    my_lng[jbin - 1] += wl_f;                                                         // :612 / :624
+      if (hist_every > 0 && i % hist_every == 0) my_hist[jbin - lo] += 1.0;              // :605-606
+      my_lng[jbin - 1] += wl_f;                                                          // :612 / :624
+    }
+    acc = __shfl_sync(0xffffffffu, acc, 0);
+    if (acc) { accepted++; e_unswapped = e_swapped; }
+    __syncwarp();
   }
-  e_io[w] = e_unswapped;
-  n_accept[w] = accepted;
+  for (int i = lane; i < bins; i += 32) g_lng[i] = my_lng[i];
+  for (int i = lane; i < nh; i += 32) g_hist[i] = my_hist[i];
+  brw_walker_end(g, c);
+  if (lane == 0) { e_io[w] = e_unswapped; n_accept[w] = accepted; }
+}
+
+// enter_energy_window (src/wang-landau.F90:643-741): biased walk towards the window centre,
+// accept iff log(u) < -((E'-E*)^2 - (E-E*)^2) * inv_two_sigma_sq, until lo_e < E < hi_e (the
+// reference's min_e+condition / max_e-condition) or max_trials.  entered[w] = 1 on success.
+__global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_wl_enter_window_kernel(
+    BrwGeom g, BrwWalkerLayout lay, const double *__restrict__ V, uint8_t *lat, const double *__restrict__ target,
+    const double *__restrict__ lo_e, const double *__restrict__ hi_e, double inv_two_sigma_sq, long max_trials,
+    uint32_t k0, uint32_t k1, uint32_t off_lo, uint32_t off_hi, int n_walkers, double *e_io, int *entered) {
+  __shared__ BrwWarpScratch scratch[BRW_WALKER_WARPS];
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * BRW_WALKER_WARPS + warp;
+  const bool valid = w < n_walkers;
+  BrwWalkerCtx c = brw_walker_begin(g, lay, V, lat + (long)(valid ? w : 0) * g.n_sites, dsm, valid);
+  if (!valid) return;
+  const double tgt = target[w], lo = lo_e[w], hi = hi_e[w];
+  double e = e_io[w];
+  int ok = (e < hi && e > lo) ? 1 : 0;
+  for (long i = 0; i < max_trials && !ok; i++) {
+    int x1 = 0, y1 = 0, z1 = 0, x2 = 0, y2 = 0, z2 = 0;
+    uint32_t u = brw_warp_propose_philox(g, 0, (uint32_t)i, (uint32_t)(i >> 32) ^ 0x02000000u, (uint32_t)w, off_lo, k0,
+                                         k1 ^ off_hi, x1, y1, z1, x2, y2, z2);
+    const int c1 = brw_grid_to_compact(g, x1, y1, z1), c2 = brw_grid_to_compact(g, x2, y2, z2);
+    const int s1 = c.L[c1], s2 = c.L[c2];
+    if (s1 != s2) {                                                                       // :710
+      double pu, ps;
+      brw_walker_pair(g, c, x1, y1, z1, x2, y2, z2, c1, c2, s1, s2, &scratch[warp], pu, ps);
+      const double e_new = __dadd_rn(__dsub_rn(e, pu), ps);                                // :721
+      const double delta = ((e_new - tgt) * (e_new - tgt) - (e - tgt) * (e - tgt)) * inv_two_sigma_sq;   // :725-727
+      if (log(brw_u01(u)) < -delta) {                                                      // :729
+        e = e_new;
+        if (lane == 0) { c.L[c1] = (uint8_t)s2; c.L[c2] = (uint8_t)s1; }
+      }
+      __syncwarp();
+    }
+    ok = (e < hi && e > lo) ? 1 : 0;
+  }
+  brw_walker_end(g, c);
+  if (lane == 0) { e_io[w] = e; entered[w] = ok; }
 }
 
 // intra-window average of ln g and hist over the walkers of each window held on this GPU
@@ -63,42 +252,54 @@ __global__ void brw_wl_window_average_kernel(double *a, int len, int wpw, int n_
   for (int k = 0; k < wpw; k++) a[((long)(q * wpw + k)) * len + b] = s;
 }
 
-__global__ void brw_ns_walker_kernel(BrwGeom g, const double *__restrict__ V, uint8_t *lat,
-                                     const int *__restrict__ walker_ids, double *energies,
-                                     const double *__restrict__ e_limit, long n_steps, uint32_t k0, uint32_t k1,
-                                     uint32_t off_lo, uint32_t off_hi, int n_walkers, unsigned long long *n_accept) {
-  int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= n_walkers) return;
-  uint8_t *L = lat + (long)walker_ids[w] * g.n_sites;
+// ---- nested-sampling walks ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_ns_walker_kernel(
+    BrwGeom g, BrwWalkerLayout lay, const double *__restrict__ V, uint8_t *lat, const int *__restrict__ walker_ids,
+    double *energies,
+    const double *__restrict__ e_limit, long n_steps, uint32_t k0, uint32_t k1, uint32_t off_lo, uint32_t off_hi,
+    int n_walkers, unsigned long long *n_accept) {
+  __shared__ BrwWarpScratch scratch[BRW_WALKER_WARPS];
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * BRW_WALKER_WARPS + warp;
+  const bool valid = w < n_walkers;
+  BrwWalkerCtx c = brw_walker_begin(g, lay, V, lat + (long)(valid ? walker_ids[w] : 0) * g.n_sites, dsm, valid);
+  if (!valid) return;
   double E = energies[w];
   const double lim = e_limit[w];
   unsigned long long n_acc = 0;
   for (long st = 0; st < n_steps; st++) {
-    BrwPhilox4 r1 = brw_philox((uint32_t)st, (uint32_t)(st >> 32) ^ 0x50000000u, (uint32_t)w, off_lo, k0, k1 ^ off_hi);
-    int x1, y1, z1, x2, y2, z2;
-    brw_random_site(g, brw_u01(r1.x), brw_u01(r1.y), brw_u01(r1.z), x1, y1, z1);
-    const int c1 = brw_grid_to_compact(g, x1, y1, z1);
-    const int s1 = L[c1];
-    int c2, s2;
-    uint32_t tries = 0;
-    do {                                                     // :162-173 redraw until species differ
-      BrwPhilox4 r2 = brw_philox((uint32_t)st, ((uint32_t)(st >> 32) & 0xFFFFu) ^ 0x60000000u ^ (tries << 16),
-                                 (uint32_t)w, off_lo, k0, k1 ^ off_hi);
-      brw_random_site(g, brw_u01(r2.x), brw_u01(r2.y), brw_u01(r2.z), x2, y2, z2);
-      c2 = brw_grid_to_compact(g, x2, y2, z2);
-      s2 = L[c2];
-      tries++;
-    } while (s1 == s2 && tries < 4096u);
-    if (s1 == s2) continue;                                  // single-species lattice: nothing to do
+    int x1 = 0, y1 = 0, z1 = 0, x2 = 0, y2 = 0, z2 = 0, c1 = 0, c2 = 0, s1 = 0, s2 = 0;
+    if (lane == 0) {
+      BrwPhilox4 r1 = brw_philox((uint32_t)st, (uint32_t)(st >> 32) ^ 0x50000000u, (uint32_t)w, off_lo, k0, k1 ^ off_hi);
+      brw_random_site(g, brw_u01(r1.x), brw_u01(r1.y), brw_u01(r1.z), x1, y1, z1);
+      c1 = brw_grid_to_compact(g, x1, y1, z1);
+      s1 = c.L[c1];
+      uint32_t tries = 0;
+      do {                                                     // :162-173 redraw until species differ
+        BrwPhilox4 r2 = brw_philox((uint32_t)st, ((uint32_t)(st >> 32) & 0xFFFFu) ^ 0x60000000u ^ (tries << 16),
+                                   (uint32_t)w, off_lo, k0, k1 ^ off_hi);
+        brw_random_site(g, brw_u01(r2.x), brw_u01(r2.y), brw_u01(r2.z), x2, y2, z2);
+        c2 = brw_grid_to_compact(g, x2, y2, z2);
+        s2 = c.L[c2];
+        tries++;
+      } while (s1 == s2 && tries < 4096u);
+    }
+    x1 = __shfl_sync(0xffffffffu, x1, 0); y1 = __shfl_sync(0xffffffffu, y1, 0); z1 = __shfl_sync(0xffffffffu, z1, 0);
+    x2 = __shfl_sync(0xffffffffu, x2, 0); y2 = __shfl_sync(0xffffffffu, y2, 0); z2 = __shfl_sync(0xffffffffu, z2, 0);
+    c1 = __shfl_sync(0xffffffffu, c1, 0); c2 = __shfl_sync(0xffffffffu, c2, 0);
+    s1 = __shfl_sync(0xffffffffu, s1, 0); s2 = __shfl_sync(0xffffffffu, s2, 0);
+    if (s1 == s2) continue;                                    // single-species lattice: nothing to do
     double before, after;
-    brw_pair_energies(g, V, L, c1, c2, before, after);
+    brw_walker_pair(g, c, x1, y1, z1, x2, y2, z2, c1, c2, s1, s2, &scratch[warp], before, after);
     const double dE = __dsub_rn(after, before);
-    if (__dadd_rn(E, dE) < lim) {                            // :183-186
+    if (__dadd_rn(E, dE) < lim) {                              // :183-186
       E = __dadd_rn(E, dE);
       n_acc++;
-      L[c1] = (uint8_t)s2; L[c2] = (uint8_t)s1;
+      if (lane == 0) { c.L[c1] = (uint8_t)s2; c.L[c2] = (uint8_t)s1; }
     }
+    __syncwarp();
   }
-  energies[w] = E;
-  n_accept[w] = n_acc;
+  brw_walker_end(g, c);
+  if (lane == 0) { energies[w] = E; n_accept[w] = n_acc; }
 }

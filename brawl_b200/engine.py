@@ -200,6 +200,30 @@ class Device:
                                           wl_f, n_trials, int(nbr_swap), seed, offset, _p(acc), _p(ef)))
         return acc, ef
 
+    def wl_enter_window(self, target, lo_e, hi_e, inv_two_sigma_sq, max_trials, seed=0x42726157, offset=0):
+        n = len(target)
+        t = np.ascontiguousarray(target, dtype=np.float64)
+        lo = np.ascontiguousarray(lo_e, dtype=np.float64)
+        hi = np.ascontiguousarray(hi_e, dtype=np.float64)
+        e = np.zeros(n, dtype=np.float64)
+        ent = np.zeros(n, dtype=np.int32)
+        check(self.L.brawl_cuda_wl_enter_window(self.h, n, _p(t), _p(lo), _p(hi), inv_two_sigma_sq, int(max_trials), seed,
+                                                offset, _p(e), _p(ent)))
+        return e, ent
+
+    def swap_replicas(self, a, b):
+        check(self.L.brawl_cuda_swap_replicas(self.h, a, b))
+
+    def lattice_tensor(self, torch):
+        """The device-resident compact lattices as a torch uint8 tensor [n_replicas][n_atoms] (no copy)."""
+        ptr, nb = C.c_void_p(), C.c_int64()
+        check(self.L.brawl_cuda_lattice_ptr(self.h, C.byref(ptr), C.byref(nb)))
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (self.n_replicas, nb.value), "typestr": "|u1",
+                                        "data": (ptr.value, False), "version": 2}
+        return torch.as_tensor(_Arr(), device="cuda")
+
     # --- nested sampling ------------------------------------------------------------------------------
     def ns_walk_replay(self, energy, e_limit, n_steps, mt_state625, replica=0):
         e, acc = C.c_double(energy), C.c_int64()

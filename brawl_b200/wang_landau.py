@@ -1,0 +1,353 @@
+"""Wang-Landau driver on top of the C ABI -- host-side mirror of the reference's wl_main
+(src/wang-landau.F90:101-314) with the trial loop (`sweeps`, :539-626), the window entry
+(`enter_energy_window`, :643-741) and the configuration exchange on the GPU.
+
+Units of work are (window, walker) pairs.  Placement: every window lives entirely on one GPU
+(rank r owns windows r*W/P .. (r+1)*W/P-1, `walkers` walkers each), so the per-`sweeps` average of
+ln g / hist over a window's walkers (the MPI_Allreduce + "/num_walkers" at :628-631) never crosses
+GPUs.  Cross-GPU traffic is only what the reference also has once per outer iteration / f-stage:
+an all-gather of walker energies (replica_exchange, :1392-1501), point-to-point configuration
+swaps between adjacent windows on different GPUs, the converged flags (:230) and the all-gather of
+the W x bins ln g table for dos_combine (:1147-1194) -- all through torch.distributed (NCCL on
+GPUs; gloo in the CPU tests of the host logic).
+
+Not mirrored (documented in DESIGN.md): dynamic window resizing (mpi_window_optimise -- i.e. this
+driver behaves like `performance = 2`), rho(E) sampling, merge_configs/load_window_config.
+The pure functions below restate the reference's integer/f64 host arithmetic exactly.
+"""
+import math
+
+import numpy as np
+
+from .engine import Device, RY_TO_EV, BrawlCudaError
+
+
+def _f32(v):
+    return float(np.float32(v))
+
+
+class WLParams:
+    """wl_params (src/derived_types.f90:322-350); reals are single precision in the reference, so
+    e.g. wl_f = 0.05 is really 0.05000000074505806."""
+
+    def __init__(self, mc_sweeps=100, bins=512, num_windows=4, bin_overlap=0.25, tolerance=5e-5, flatness=0.9,
+                 wl_f=0.05, energy_min=-96.0, energy_max=0.0, radial_samples=8, performance=2, nbr_swap=False):
+        self.mc_sweeps, self.bins, self.num_windows = int(mc_sweeps), int(bins), int(num_windows)
+        self.bin_overlap, self.tolerance, self.flatness = _f32(bin_overlap), _f32(tolerance), _f32(flatness)
+        self.wl_f, self.energy_min, self.energy_max = _f32(wl_f), _f32(energy_min), _f32(energy_max)
+        self.radial_samples, self.performance, self.nbr_swap = int(radial_samples), int(performance), bool(nbr_swap)
+
+    @classmethod
+    def from_file(cls, path):
+        """read_wl_file (src/io.f90:951-1086): key=value lines, '#' comments, unknown keys ignored."""
+        kw = {}
+        conv = dict(mc_sweeps=int, bins=int, num_windows=int, bin_overlap=float, tolerance=float, flatness=float,
+                    wl_f=float, energy_min=float, energy_max=float, radial_samples=int, performance=int)
+        for line in open(path):
+            if "=" not in line or line.lstrip().startswith("#"):
+                continue
+            k, v = line.split("=", 1)
+            k, v = k.rstrip(), v.split("#")[0].strip()     # a leading blank breaks a key in the reference too
+            if k in conv:
+                kw[k] = conv[k](v)
+            elif k == "nbr_swap":
+                kw[k] = v.strip(".").upper().startswith("T")
+        return cls(**kw)
+
+
+# --- pure host arithmetic (1-based inclusive bin indices, as in the reference) ---------------------
+def divide_range(bins, num_windows):
+    """divide_range (:855-891) with power = 1."""
+    W = num_windows
+    iv = np.zeros((W, 2), dtype=np.int64)
+    iv[0, 0] = 1
+    iv[W - 1, 1] = bins
+    factor = (float(bins) - 1.0) / ((W + 1.0) ** 1 - 1.0)
+    for i in range(2, W + 1):
+        iv[i - 2, 1] = int(math.floor(factor * ((i - 1) ** 1) + 1))
+        iv[i - 1, 0] = iv[i - 2, 1] + 1
+    return iv
+
+
+def create_overlap(intervals, bin_overlap):
+    """create_overlap (:934-955): every window but the first is extended downwards; note the last
+    window's width is computed without the +1 (reference quirk)."""
+    idx = intervals.copy()
+    W = idx.shape[0]
+    if W > 1:
+        for i in range(2, W):
+            b = idx[i - 2, 1] - idx[i - 2, 0] + 1
+            idx[i - 1, 0] = int(intervals[i - 1, 0] - max(math.ceil(np.float32(bin_overlap) * np.float32(b)), 2))
+            idx[i - 1, 1] = intervals[i - 1, 1]
+        b = idx[W - 2, 1] - idx[W - 2, 0]
+        idx[W - 1, 0] = int(intervals[W - 1, 0] - max(math.ceil(np.float32(bin_overlap) * np.float32(b)), 2))
+        idx[W - 1, 1] = intervals[W - 1, 1]
+    return idx
+
+
+def create_energy_bins(n_atoms, energy_min, energy_max, bins):
+    """create_energy_bins (:969-986): meV/atom -> Ry/cell."""
+    energy_to_ry = n_atoms / (RY_TO_EV * 1000)
+    width = (energy_max - energy_min) / float(np.float32(bins)) * energy_to_ry
+    return np.array([energy_min * energy_to_ry + i * width for i in range(bins + 1)], dtype=np.float64)
+
+
+def bin_index(e, edges, bins):
+    """bin_index (:515-523); int() truncates toward zero like Fortran INT."""
+    return int(((e - edges[0]) / (edges[bins] - edges[0])) * float(bins)) + 1
+
+
+def dos_combine(lng_windows, window_indices):
+    """dos_combine (:1147-1194): stitch window i onto the combined curve at the overlap bin where
+    the slopes agree best, then subtract the minimum.  lng_windows[W][bins] (already window-averaged)."""
+    W, bins = lng_windows.shape
+    comb = lng_windows[0].copy()
+    beta_index = 0
+    for i in range(2, W + 1):
+        buf = lng_windows[i - 1]
+        start, end = int(window_indices[i - 1, 0]), int(window_indices[i - 1, 1])
+        beta_diff = np.finfo(np.float64).max
+        for j in range(0, int(window_indices[i - 2, 1] - window_indices[i - 1, 0] - 1) + 1):
+            b_orig = comb[start + j] - comb[start + j - 1]            # (start+j+1) - (start+j), 1-based
+            b_merge = buf[start + j] - buf[start + j - 1]
+            if abs(b_orig - b_merge) < beta_diff:
+                beta_diff = abs(b_orig - b_merge)
+                beta_index = start + j + 1
+        for j in range(beta_index, end + 1):         # same association as the reference: (buf + comb(bi)) - buf(bi)
+            comb[j - 1] = buf[j - 1] + comb[beta_index - 1] - buf[beta_index - 1]
+    return comb - comb.min()
+
+
+def overlap_location(ibin, q, window_indices):
+    """Which overlap region (1-based index of its lower window, 0 = none) a walker of window q
+    (1-based) with energy bin ibin sits in (replica_exchange, :1409-1427)."""
+    W = window_indices.shape[0]
+    lower = q > 1 and (ibin < window_indices[q - 2, 1] + 1) and (ibin > window_indices[q - 1, 0] - 1)
+    upper = q < W and (ibin > window_indices[q, 0] - 1) and (ibin < window_indices[q - 1, 1] + 1)
+    return q if upper else (q - 1 if lower else 0)
+
+
+def plan_replica_exchange(energies, lng_windows, window_indices, walkers, edges, rng):
+    """Pair walkers of adjacent windows that sit in the same overlap region (random order, :1441-1468)
+    and decide each exchange with the lower walker's ln g: u < exp(lng(ibin) - lng(jbin)) (:1482).
+    energies[W*walkers] in global walker order (window-major).  Deterministic given `rng`, so every
+    rank computes the same plan.  Returns [(walker_a, walker_b), ...] of accepted exchanges."""
+    W = window_indices.shape[0]
+    bins = edges.size - 1
+    ib = [bin_index(e, edges, bins) for e in energies]
+    loc = [overlap_location(ib[g], g // walkers + 1, window_indices) for g in range(W * walkers)]
+    swaps = []
+    for i in range(1, W):
+        lower = [g for g in range((i - 1) * walkers, i * walkers)]
+        upper = [g for g in range(i * walkers, (i + 1) * walkers)]
+        rng.shuffle(lower)
+        rng.shuffle(upper)
+        used = set()
+        for a in lower:
+            if loc[a] != i:
+                continue
+            for b in upper:
+                if b in used or loc[b] != i:
+                    continue
+                used.add(b)
+                lng = lng_windows[i - 1]
+                # bins / regions are NOT refreshed after an exchange -- the reference evaluates them once
+                # per call (:1405-1431); a walker sits in at most one region, so it is paired at most once
+                if rng.random() < math.exp(min(0.0, lng[ib[a] - 1] - lng[ib[b] - 1])):
+                    swaps.append((a, b))
+                break
+    return swaps
+
+
+def random_configuration(lattice, n_1, n_2, n_3, counts, rng):
+    """A uniformly random arrangement of the species multiset on the lattice sites (the distribution
+    initial_setup samples, src/initialise.F90:434-617), reference grid layout."""
+    z, y, x = np.meshgrid(np.arange(2 * n_3), np.arange(2 * n_2), np.arange(2 * n_1), indexing="ij")
+    if lattice == "bcc":
+        mask = ((x & 1) == (z & 1)) & ((y & 1) == (z & 1))
+    elif lattice == "fcc":
+        mask = ((x + y + z) & 1) == 0
+    else:
+        mask = np.ones_like(x, dtype=bool)
+    spec = np.concatenate([np.full(int(c), s + 1, dtype=np.int8) for s, c in enumerate(counts)])
+    if spec.size != int(mask.sum()):
+        raise BrawlCudaError("species counts do not sum to the number of lattice sites")
+    rng.shuffle(spec)
+    g = np.zeros(mask.shape, dtype=np.int8)
+    g[mask] = spec
+    return g
+
+
+class _Comm:
+    """torch.distributed plumbing (world size 1 needs no torch at all)."""
+
+    def __init__(self, rank=0, world=1, device=None):
+        self.rank, self.world, self.device = rank, world, device
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+
+    def all_gather(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if self.world == 1:
+            return a[None]
+        t = self.torch.from_numpy(a.copy())
+        if self.device is not None:
+            t = t.to(self.device)
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return np.stack([o.cpu().numpy() for o in out])
+
+    def all_sum(self, v):
+        return float(self.all_gather(np.array([float(v)])).sum())
+
+
+class WangLandau:
+    """wl_main for the windows owned by this rank.  `dev` is created here: one handle with
+    (windows_per_rank * walkers) replicas."""
+
+    def __init__(self, lattice, n_1, n_2, n_3, n_species, n_shells, V_ex, counts, params, walkers=8, device=0,
+                 rank=0, world=1, seed=0x42726157, torch_device=None):
+        self.p, self.walkers, self.rank, self.world, self.seed = params, walkers, rank, world, seed
+        W = params.num_windows
+        if W % world:
+            raise BrawlCudaError("num_windows must be divisible by the number of GPUs")
+        self.w_local = W // world
+        self.first_window = rank * self.w_local                 # 0-based
+        self.n_local = self.w_local * walkers
+        self.dev = Device(lattice, n_1, n_2, n_3, n_species, n_shells, V_ex, device=device, n_replicas=self.n_local)
+        self.lattice, self.n, self.counts = lattice, (n_1, n_2, n_3), counts
+        self.n_atoms = self.dev.n_atoms
+        self.intervals = divide_range(params.bins, W)
+        self.window_indices = create_overlap(self.intervals, params.bin_overlap)
+        self.edges = create_energy_bins(self.n_atoms, params.energy_min, params.energy_max, params.bins)
+        self.comm = _Comm(rank, world, torch_device)
+        self.rng_local = np.random.default_rng([seed, rank])
+        self.rng_shared = np.random.default_rng([seed, 0xEC])   # identical on all ranks
+        self.offset = 0
+        self.lng = np.zeros((self.n_local, params.bins))
+        self.hist = np.zeros((self.n_local, params.bins))
+        q = np.repeat(np.arange(self.first_window, self.first_window + self.w_local), walkers)
+        self.win_lo = self.window_indices[q, 0].astype(np.int32)
+        self.win_hi = self.window_indices[q, 1].astype(np.int32)
+        self.energies = np.zeros(self.n_local)
+        self.total_trials = 0
+        self.stage_sweeps = []
+
+    # --- window entry (enter_energy_window, :643-741) ------------------------------------------------
+    def enter_energy_windows(self, max_rounds=200):
+        p = self.p
+        lo = self.edges[self.win_lo - 1]
+        hi = self.edges[self.win_hi]
+        target = (lo + hi) / 2.0
+        cond = np.abs(hi - lo) * 0.1
+        sigma = _f32(0.0025) * abs(p.energy_max - p.energy_min) * self.n_atoms / (RY_TO_EV * 1000)
+        inv = 1.0 / (2.0 * sigma ** 2)
+        pending = np.ones(self.n_local, dtype=bool)
+        for w in range(self.n_local):
+            self.dev.set_config(random_configuration(self.lattice, *self.n, self.counts, self.rng_local), w, 1)
+        for _ in range(max_rounds):
+            e, ent = self.dev.wl_enter_window(target, lo + cond, hi - cond, inv, self.n_atoms * 250, self.seed, self.offset)
+            self.offset += 1
+            pending = ent == 0
+            if not pending.any():
+                self.energies = e
+                return
+            for w in np.flatnonzero(pending):                 # re-randomise (:671-674)
+                self.dev.set_config(random_configuration(self.lattice, *self.n, self.counts, self.rng_local), int(w), 1)
+        raise BrawlCudaError("walkers failed to enter their energy windows")
+
+    # --- one outer iteration: sweeps + window average + replica exchange -------------------------------
+    def _sweeps(self, wl_f):
+        p = self.p
+        n_trials = p.mc_sweeps * self.n_atoms
+        acc, ef = self.dev.wl_sweeps(self.lng, self.hist, self.edges, self.win_lo, self.win_hi, wl_f, n_trials,
+                                     seed=self.seed, offset=self.offset, nbr_swap=p.nbr_swap)
+        self.offset += 1
+        self.total_trials += n_trials * self.n_local
+        self.energies = ef
+        # intra-window average (:628-631): all walkers of a window are on this GPU
+        w = self.walkers
+        for q in range(self.w_local):
+            self.lng[q * w:(q + 1) * w] = self.lng[q * w:(q + 1) * w].sum(axis=0) / float(np.float32(w))
+            self.hist[q * w:(q + 1) * w] = self.hist[q * w:(q + 1) * w].sum(axis=0) / float(np.float32(w))
+
+    def _window_lng_all(self):
+        """lng per window for all windows (all-gather over ranks): [W][bins]."""
+        loc = self.lng[::self.walkers]
+        return self.comm.all_gather(loc).reshape(self.p.num_windows, self.p.bins)
+
+    def _replica_exchange(self):
+        if self.p.num_windows < 2 or self.p.performance not in (0, 2, 4):
+            return 0
+        e_all = self.comm.all_gather(self.energies).reshape(-1)
+        lng_all = self._window_lng_all()
+        swaps = plan_replica_exchange(list(e_all), lng_all, self.window_indices, self.walkers, self.edges, self.rng_shared)
+        for a, b in swaps:
+            ra, rb = a // self.n_local, b // self.n_local
+            la, lb = a % self.n_local, b % self.n_local
+            if ra == rb == self.rank:
+                self.dev.swap_replicas(la, lb)
+                self.energies[la], self.energies[lb] = self.energies[lb], self.energies[la]
+            elif self.rank in (ra, rb):
+                mine, peer = (la, rb) if self.rank == ra else (lb, ra)
+                self._exchange_remote(mine, peer)
+                self.energies[mine] = e_all[b if self.rank == ra else a]
+        return len(swaps)
+
+    def _exchange_remote(self, local_replica, peer_rank):
+        """Swap one configuration with a walker on another GPU: device-to-device over NCCL."""
+        torch, dist = self.comm.torch, self.comm.dist
+        send = self.dev.lattice_tensor(torch)[local_replica].clone()
+        recv = torch.empty_like(send)
+        ops = [dist.P2POp(dist.isend, send, peer_rank), dist.P2POp(dist.irecv, recv, peer_rank)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        self.dev.lattice_tensor(torch)[local_replica].copy_(recv)
+
+    def _flat_windows(self, min_hist=None):
+        """flatness = minval(hist)/(sum(hist)/mpi_bins) > flatness per local window (:222-226)."""
+        ok = []
+        for q in range(self.w_local):
+            w0 = q * self.walkers
+            nb = self.win_hi[w0] - self.win_lo[w0] + 1
+            h = self.hist[w0, :nb]
+            flat = h.min() / (h.sum() / nb) if h.sum() > 0 else 0.0
+            good = flat > self.p.flatness
+            if min_hist is not None:
+                good = good and h.min() > min_hist
+            ok.append(bool(good))
+        return ok
+
+    def _stage(self, wl_f, min_hist=None, max_sweeps=100000, exchange_every=1):
+        converged = [False] * self.w_local
+        n = 0
+        while True:
+            n += 1
+            self._sweeps(wl_f)
+            if n % exchange_every == 0:
+                self._replica_exchange()
+            flat = self._flat_windows(min_hist)
+            converged = [c or f for c, f in zip(converged, flat)]
+            if self.comm.all_sum(sum(converged)) == self.p.num_windows or n >= max_sweeps:
+                break
+        self.stage_sweeps.append(n)
+        self.hist[...] = 0.0
+        combined = dos_combine(self._window_lng_all(), self.window_indices)      # dos_average + dos_combine
+        self.lng[...] = combined[None, :]
+        return combined
+
+    def run(self, max_sweeps_per_stage=100000, callback=None):
+        """pre_sampling (:757-838) then the f-halving loop (:198-292).  Returns ln g(E) [bins]."""
+        p = self.p
+        self.enter_energy_windows()
+        wl_f = p.wl_f
+        combined = self._stage(wl_f, min_hist=1000.0 / float(np.float32(self.walkers)), max_sweeps=max_sweeps_per_stage,
+                               exchange_every=10)
+        while wl_f > p.tolerance:
+            combined = self._stage(wl_f, max_sweeps=max_sweeps_per_stage)
+            wl_f = wl_f * 0.5
+            if callback:
+                callback(wl_f, combined)
+        return combined

@@ -148,6 +148,19 @@ int brawl_cuda_wl_sweeps(brawl_cuda_t *h, int n_walkers, double *lng_dev_or_host
                          const int32_t *win_hi, int hist_stride, double wl_f, int64_t n_trials, int nbr_swap,
                          uint64_t seed, uint64_t offset, int64_t *n_accept, double *e_final);
 
+/* enter_energy_window (src/wang-landau.F90:643-741) for the first n_walkers replicas: a biased
+ * walk, accept iff log(u) < -((E'-target)^2 - (E-target)^2) * inv_two_sigma_sq, until
+ * lo_e[w] < E < hi_e[w] (the reference's min_e+condition / max_e-condition) or max_trials trials.
+ * energies[w] returns the running energy, entered[w] = 1 on success. */
+int brawl_cuda_wl_enter_window(brawl_cuda_t *h, int n_walkers, const double *target, const double *lo_e,
+                               const double *hi_e, double inv_two_sigma_sq, int64_t max_trials, uint64_t seed,
+                               uint64_t offset, double *energies, int32_t *entered);
+/* Device storage of the compact lattices ([n_replicas][bytes_per_replica] uint8, species 0..S-1),
+ * for device-side exchange between GPUs (replica_exchange, src/wang-landau.F90:1475-1495) */
+int brawl_cuda_lattice_ptr(brawl_cuda_t *h, void **dev_ptr, int64_t *bytes_per_replica);
+/* exchange the configurations of two replicas on the device (same-GPU replica exchange) */
+int brawl_cuda_swap_replicas(brawl_cuda_t *h, int a, int b);
+
 /* Average a device array a[walker][len] over the walkers of each window held by this handle
  * (walkers q*wpw .. q*wpw+wpw-1 form window q) and write the mean/`divisor`-scaled sum back to
  * every walker: the on-GPU part of the allreduce + "/num_walkers" at src/wang-landau.F90:628-631. */

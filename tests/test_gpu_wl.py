@@ -1,0 +1,46 @@
+"""Wang-Landau on the GPU: the reference's regression case tests/04_parallel_wang-landau
+(bcc n=4, 4 species, 6 shells, 512 bins, 4 windows, overlap 0.25, f 0.05 -> 5e-5, flatness 0.9)
+against its golden ln g(E) with the reference's own acceptance criterion (NRMSE < 1 %,
+tests/ci_test.py:42-50)."""
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def nrmse(ref, test):
+    return float(np.sqrt(np.mean((ref - test) ** 2)) / np.mean(np.abs(ref)))
+
+
+def test_enter_energy_window(orc, golden):
+    import brawl_b200
+    from brawl_b200 import wang_landau as wl
+    p = wl.WLParams()
+    drv = wl.WangLandau("bcc", 4, 4, 4, 4, 6, golden["t04_V"], [32, 32, 32, 32], p, walkers=4)
+    drv.enter_energy_windows()
+    e = drv.dev.total_energy(0, drv.n_local)
+    assert np.allclose(e, drv.energies, rtol=0, atol=1e-11)          # running energy == exact energy
+    lo = drv.edges[drv.win_lo - 1]; hi = drv.edges[drv.win_hi]
+    cond = 0.1 * np.abs(hi - lo)
+    assert np.all((e > lo + cond) & (e < hi - cond))
+    g = drv.dev.get_config(0, drv.n_local)
+    for gi in g:
+        assert np.array_equal(np.bincount(gi.ravel(), minlength=5), [384, 32, 32, 32, 32])
+
+
+def test_wang_landau_golden_04(orc, golden):
+    import brawl_b200
+    from brawl_b200 import wang_landau as wl
+    p = wl.WLParams(mc_sweeps=100, bins=512, num_windows=4, bin_overlap=0.25, tolerance=5e-5, flatness=0.90,
+                    wl_f=0.05, energy_min=-96, energy_max=0.0, radial_samples=8)
+    drv = wl.WangLandau("bcc", 4, 4, 4, 4, 6, golden["t04_V"], [32, 32, 32, 32], p, walkers=8, seed=2024)
+    t0 = time.time()
+    lng = drv.run()
+    dt = time.time() - t0
+    ref = np.asarray(golden["t04_wl_dos"], dtype=np.float64)
+    err = nrmse(ref, lng)
+    print("WL: %.1f s, %d sweeps calls per stage %s, %.3g trials, NRMSE %.4f" % (dt, sum(drv.stage_sweeps), drv.stage_sweeps, drv.total_trials, err))
+    assert lng.min() == 0.0 and np.all(np.isfinite(lng))
+    assert err < 0.01, err
