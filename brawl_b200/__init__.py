@@ -6,3 +6,4 @@ binding and the host-side mirror of the reference's operator table.  No CPU fall
 from ._lib import BrawlCudaError, EXPORTS, LIB_PATH, load  # noqa: F401
 from .engine import Device, RunParams, K_B_IN_RY, RY_TO_EV, LATTICES  # noqa: F401
 from . import wang_landau  # noqa: F401,E402
+from . import nested_sampling  # noqa: F401,E402
