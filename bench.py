@@ -46,11 +46,11 @@ def synthetic_config(n, S, rank):
     initial_setup: a uniformly random arrangement of the species multiset)."""
     rng = np.random.default_rng(110179 + 11 * rank)
     N = 2 * n ** 3
-    spec = np.repeat(np.arange(1, S + 1, dtype=np.int8), N // S)
+    spec = np.repeat(np.arange(1, S + 1, dtype=np.int8), -(-N // S))[:N]
     rng.shuffle(spec)
+    par = (np.arange(2 * n) & 1).astype(np.int8)
+    mask = (par[None, None, :] == par[:, None, None]) & (par[None, :, None] == par[:, None, None])
     g = np.zeros((2 * n, 2 * n, 2 * n), dtype=np.int8)
-    z, y, x = np.meshgrid(np.arange(2 * n), np.arange(2 * n), np.arange(2 * n), indexing="ij")
-    mask = ((x & 1) == (z & 1)) & ((y & 1) == (z & 1))
     g[mask] = spec
     return g
 
@@ -95,15 +95,15 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_rate(n_threads, trials_per_thread, n=N_CELLS, seed0=0):
+def cpu_reference_rate(n_threads, trials_per_thread, n=N_CELLS, seed0=0, S=4, V=None, temp=T_KELVIN):
     """The reference algorithm (oracle C restatement, validated bit-exactly against the reference's
     goldens) on host cores: one independent replica per thread, the reference's own Metropolis
     parallel model (src/comms.F90:122-160).  Returns (attempted swaps/s over all threads, seconds)."""
     from oracle import oracle          # CPU baseline legs only: the oracle is the thing being timed here
-    V = load_V()
-    osys = oracle.System("bcc", n, n, n, 4, 4, V)
-    beta = 1.0 / (T_KELVIN * oracle.K_B_IN_RY)
-    grids = [synthetic_config(n, 4, seed0 + t) for t in range(n_threads)]
+    V = load_V() if V is None else V
+    osys = oracle.System("bcc", n, n, n, S, 4, V)
+    beta = 1.0 / (temp * oracle.K_B_IN_RY)
+    grids = [synthetic_config(n, S, seed0 + t) for t in range(n_threads)]
     mts = [oracle.MT(rank=seed0 + t) for t in range(n_threads)]
     for t in range(n_threads):                         # warm the caches / page in
         osys.metropolis_trials(grids[t], mts[t], beta, 20000)
@@ -166,6 +166,9 @@ def main():
     ap.add_argument("--steps-per-phase", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--n-cells", type=int, default=N_CELLS)
+    ap.add_argument("--workload", default="chain", choices=["chain", "replicas"],
+                    help="chain: BASELINE configs[1] (headline); replicas: configs[4], R x 32^3 bcc AlCrFeCoNi per GPU")
+    ap.add_argument("--replicas", type=int, default=1024)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = max(args.warmup, 3) if os.environ.get("BENCH_ALLOW_SHORT_WARMUP") is None else args.warmup
@@ -189,11 +192,25 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n = args.n_cells
-    V = load_V()
-    g0 = synthetic_config(n, 4, rank)
+    R = 1
+    if args.workload == "replicas":
+        # BASELINE configs[4]: R independent AlCrFeCoNi replicas (32^3 bcc, 65 536 atoms each) per GPU, first 4 shell
+        # blocks of fcc_al_1.00_crfeconi.vij as a synthetic bcc table, annealing ladder 3000 -> 100 K over the replicas
+        n, R, S = 32, args.replicas, 5
+        gold = np.load(os.path.join(ROOT, "tests", "golden", "brawl_golden.npz"))
+        V = np.ascontiguousarray(gold["ex_AlCrFeCoNi_V"][: 5 * 5 * 4])
+        base = synthetic_config(n, 5, rank)
+        g0 = np.ascontiguousarray(np.broadcast_to(base, (R,) + base.shape))
+        temps = np.linspace(3000.0, 100.0, R)
+        beta = 1.0 / (temps * brawl_b200.K_B_IN_RY)
+        B_alg = 104
+    else:
+        S = 4
+        V = load_V()
+        g0 = synthetic_config(n, 4, rank)
+        beta = 1.0 / (T_KELVIN * brawl_b200.K_B_IN_RY)
     N = 2 * n ** 3
-    beta = 1.0 / (T_KELVIN * brawl_b200.K_B_IN_RY)
-    dev = brawl_b200.Device("bcc", n, n, n, 4, 4, V, device=local_rank, n_replicas=1)
+    dev = brawl_b200.Device("bcc", n, n, n, S, 4, V, device=local_rank, n_replicas=R)
     stream = torch.cuda.Stream()            # non-default stream shared by torch events and the library
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
@@ -204,7 +221,7 @@ def main():
         dev.metropolis_tune((0, 0, 0), args.steps_per_phase)
     plan = dev.metropolis_plan()
     dev.set_config(g0)
-    e_start = dev.total_energy(exact_order=False)[0]
+    e_start = dev.total_energy(0, R, exact_order=False).mean()
     trials_per_step = args.sweeps * N
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 
@@ -239,13 +256,14 @@ def main():
     clocks = sampler.stop()
     att, acc, dE = dev.metropolis_counters(reset=True)
     assert att[0] == attempts, (att, attempts)
+    attempts *= R                                   # planned attempts are per replica
     total_ms = float(np.sum(times))
-    e_end = dev.total_energy(exact_order=False)[0]
+    e_end = dev.total_energy(0, R, exact_order=False).mean()
 
     # ---- end-to-end arm ("e2e"): host buffers through the public C-ABI calls ----------------------
-    host_cfg = torch.empty((2 * n, 2 * n, 2 * n), dtype=torch.int8).pin_memory()
+    host_cfg = torch.empty((R, 2 * n, 2 * n, 2 * n), dtype=torch.int8).pin_memory()
     host_np = host_cfg.numpy()
-    host_np[...] = dev.get_config()
+    dev.get_config(0, R, out=host_np)
     e2e_times, e2e_attempts, e2e_launches = [], 0, 0
     n_e2e = max(3, min(args.steps, 5))
     for it in range(2 + n_e2e):
@@ -255,13 +273,13 @@ def main():
         ev0.record(stream)
         dev.set_config(host_np)                                     # H2D 8n^3 bytes (+ pack kernel)
         a, c, d = dev.metropolis_run(beta, trials_per_step)         # trials
-        dev.get_config(out=host_np.reshape((1,) + host_np.shape))   # D2H 8n^3 bytes (+ unpack kernel)
-        e_host = dev.total_energy(exact_order=False)[0]            # D2H 8 bytes (2 kernels)
+        dev.get_config(0, R, out=host_np)                           # D2H 8n^3 bytes (+ unpack kernel)
+        e_host = dev.total_energy(0, R, exact_order=False)          # D2H 8 bytes per replica (2 kernels)
         ev1.record(stream)
         ev1.synchronize()
         if it >= 2:
             e2e_times.append(ev0.elapsed_time(ev1))
-            e2e_attempts += int(a[0])
+            e2e_attempts += int(a.sum())
             per_phase = plan["trials_per_step"] * plan["steps_per_phase"] * plan["boxes_per_replica"]
             e2e_launches += (int(a[0]) // per_phase if plan["use_box"] else 1) + 4   # + pack, unpack, 2 energy kernels
     e2e_ms = float(np.sum(e2e_times))
@@ -284,6 +302,10 @@ def main():
         # dominant kernel = brw_box_metropolis_kernel: the step is `launches` back-to-back launches of it
         per_launch_ms = total_ms / max(1, launches)
         per_launch_trials = attempts / max(1, launches)
+        wl_name = ("AlTiCrMo bcc %d^3 (%d atoms), 4 species @0.25, 4 shells (Z=50), Metropolis whole-lattice swaps, T=%g K; "
+                   "replicas only for N>1 (one chain per GPU)" % (n, N, T_KELVIN)) if args.workload == "chain" else (
+                   "%d independent AlCrFeCoNi replicas per GPU, bcc 32^3 (65536 atoms each), 5 species @0.2, 4 shells (Z=50), "
+                   "Metropolis whole-lattice swaps, T ladder 3000->100 K" % R)
         achieved = per_launch_trials * B_ALG / (per_launch_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -296,14 +318,13 @@ def main():
             "metric": METRIC, "value": value, "unit": "swaps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "AlTiCrMo bcc %d^3 (%d atoms), 4 species @0.25, 4 shells (Z=50), Metropolis "
-                                   "whole-lattice swaps, T=%g K; replicas only for N>1 (one chain per GPU)" % (n, N, T_KELVIN),
-                       "attempted_swaps_per_step": trials_per_step, "sweeps_per_step": args.sweeps,
+            "config": {"workload": wl_name,
+                       "attempted_swaps_per_step": trials_per_step * R, "sweeps_per_step": args.sweeps,
                        "l2": "flushed with a 512 MiB memset before every timed step",
-                       "decomposition": plan, "acceptance": float(acc[0]) / max(1, float(att[0])),
+                       "decomposition": plan, "acceptance": float(acc.sum()) / max(1, float(att.sum())),
                        "energy_per_atom_start_end_Ry": [e_start / N, e_end / N]},
-            "e2e": {"value": e2e_value, "unit": "swaps/s", "h2d_bytes_per_step": int(8 * n ** 3 + 8),
-                    "d2h_bytes_per_step": int(8 * n ** 3 + 8 + 24),
+            "e2e": {"value": e2e_value, "unit": "swaps/s", "h2d_bytes_per_step": int(R * (8 * n ** 3 + 8)),
+                    "d2h_bytes_per_step": int(R * (8 * n ** 3 + 8 + 24)),
                     "calls": "set_config + metropolis_run + get_config + total_energy, pinned host buffers"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
@@ -315,10 +336,13 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            v, dt = cpu_reference_rate(cores, args.cpu_trials)
+            if args.workload == "replicas":
+                v, dt = cpu_reference_rate(cores, args.cpu_trials, n=n, S=S, V=V, temp=1000.0)
+            else:
+                v, dt = cpu_reference_rate(cores, args.cpu_trials)
             out["cpu_baseline"] = {"value": v, "unit": "swaps/s", "cores": cores, "kind": "port",
-                                   "sample": "%d threads x %d trials on private 128^3 bcc replicas, %.1f s; C restatement "
-                                             "of the reference hot path (bit-exact vs reference goldens)" % (cores, args.cpu_trials, dt)}
+                                   "sample": "%d threads x %d trials on private %d^3 bcc replicas, %.1f s; C restatement "
+                                             "of the reference hot path (bit-exact vs reference goldens)" % (cores, args.cpu_trials, n, dt)}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

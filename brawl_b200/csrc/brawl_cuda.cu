@@ -271,11 +271,14 @@ static int brw_total_energy_dev(brawl_cuda_ctx *h, int first, int n, int exact, 
       BRW_LAUNCH_CHECK("brw_ordered_sum_kernel");
     }
   } else {
-    int nblk = std::max(1, std::min(592, (g.n_sites + 255) / 256));
-    if (n >= 148) nblk = std::min(nblk, 8);
+    // one CTA per compact row, grid-strided; many replicas: fewer CTAs each
+    int n_rows = g.cy * g.cz;
+    int nblk = std::max(1, std::min(n_rows, n >= 148 ? 8 : (n >= 8 ? 148 : 1184)));
     if (brw_ensure_scratch(h, (size_t)nblk * n * sizeof(double))) return 1;
     dim3 grid(nblk, n);
-    brw_energy_partial_kernel<<<grid, 256, 0, h->stream>>>(g, h->d_V, h->d_lat + (size_t)first * g.n_sites, h->d_scratch, nblk);
+    int threads = g.cx >= 128 ? 128 : (g.cx > 32 ? 64 : 32);
+    brw_energy_partial_kernel<<<grid, threads, sizeof(double) * g.S * g.S * g.n_shells, h->stream>>>(
+        g, h->d_V, h->d_lat + (size_t)first * g.n_sites, h->d_scratch, nblk);
     BRW_LAUNCH_CHECK("brw_energy_partial_kernel");
     brw_tree_final_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_scratch, nblk, d_out, n);
     BRW_LAUNCH_CHECK("brw_tree_final_kernel");

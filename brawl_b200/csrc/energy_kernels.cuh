@@ -87,24 +87,56 @@ __global__ void __launch_bounds__(256) brw_ordered_sum_kernel(const double *__re
 
 // ---- tree sum: fast total energy (deterministic, not reference order) -------------------------
 // Fused site-energy + block reduction; partial[r*nblk + b]; finished by brw_tree_final_kernel.
-__global__ void __launch_bounds__(256) brw_energy_partial_kernel(BrwGeom g, const double *__restrict__ V,
+// One CTA per compact row (fixed y,z): the row's neighbour rows are CTA-uniform, V sits in shared
+// memory, and wraps are single conditional adds (loop fallback only for boxes smaller than the reach).
+__device__ __forceinline__ int brw_wrap1(int t, int w) {
+  t += (t < 0) ? w : 0;
+  t -= (t >= w) ? w : 0;
+  if (t < 0 || t >= w) t = brw_wrap(t, w);
+  return t;
+}
+__global__ void __launch_bounds__(128) brw_energy_partial_kernel(BrwGeom g, const double *__restrict__ V,
                                                                  const uint8_t *__restrict__ lat,
                                                                  double *__restrict__ partial, int nblk) {
-  __shared__ double red[8];
+  __shared__ double red[4];
+  extern __shared__ double Vs[];
   const int r = blockIdx.y;
   const uint8_t *L = lat + (long)r * g.n_sites;
+  for (int i = threadIdx.x; i < g.S * g.S * g.n_shells; i += blockDim.x) Vs[i] = V[i];
+  __syncthreads();
+  const int SS = g.S * g.S;
   double acc = 0.0;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.n_sites; c += nblk * blockDim.x) {
-    int x, y, z;
-    brw_compact_to_grid(g, c, x, y, z);
-    acc += brw_site_energy(g, V, x, y, z, L[c], BrwPlainSpec{L});
+  const int n_rows = g.cy * g.cz;
+  for (int row = blockIdx.x; row < n_rows; row += nblk) {
+    const int yc = row % g.cy, z = row / g.cy;
+    const int y = g.lattice == 1 ? 2 * yc + (z & 1) : yc;
+    const int xpar = g.lattice == 1 ? (z & 1) : (g.lattice == 2 ? ((y + z) & 1) : 0);
+    for (int xc = threadIdx.x; xc < g.cx; xc += blockDim.x) {
+      const int x = g.lattice == 0 ? xc : 2 * xc + xpar;
+      const int centre = L[row * g.cx + xc];
+      double tot = 0.0;
+      int k = 0;
+      for (int n = 0; n < g.n_shells; n++) {
+        double e = 0.0;
+        const double *Vn = Vs + n * SS + centre;
+        const int end = g.shell_end[n];
+        for (; k < end; k++) {
+          const int nx = brw_wrap1(x + g.off[k][0], g.wx), ny = brw_wrap1(y + g.off[k][1], g.wy),
+                    nz = brw_wrap1(z + g.off[k][2], g.wz);
+          const int s = L[(nz * g.cy + (ny >> g.ys)) * g.cx + (nx >> g.xs)];
+          e = __dadd_rn(e, Vn[s * g.S]);
+        }
+        tot = (n == 0) ? e : __dadd_rn(tot, e);
+      }
+      acc += tot;
+    }
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int w = 0; w < (blockDim.x >> 5); w++) s += red[w];
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w];
     partial[(long)r * nblk + blockIdx.x] = s;
   }
 }
