@@ -169,6 +169,9 @@ def main():
     ap.add_argument("--workload", default="chain", choices=["chain", "replicas"],
                     help="chain: BASELINE configs[1] (headline); replicas: configs[4], R x 32^3 bcc AlCrFeCoNi per GPU")
     ap.add_argument("--replicas", type=int, default=1024)
+    ap.add_argument("--dE-mode", type=int, default=1, choices=[0, 1],
+                    help="1 (library default): integer-count screening, reference association recomputed inside the guard "
+                         "band (decision-identical); 0: reference association for every trial")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = max(args.warmup, 3) if os.environ.get("BENCH_ALLOW_SHORT_WARMUP") is None else args.warmup
@@ -211,6 +214,7 @@ def main():
         beta = 1.0 / (T_KELVIN * brawl_b200.K_B_IN_RY)
     N = 2 * n ** 3
     dev = brawl_b200.Device("bcc", n, n, n, S, 4, V, device=local_rank, n_replicas=R)
+    dev.metropolis_set_mode(args.dE_mode)
     stream = torch.cuda.Stream()            # non-default stream shared by torch events and the library
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
@@ -321,7 +325,10 @@ def main():
             "config": {"workload": wl_name,
                        "attempted_swaps_per_step": trials_per_step * R, "sweeps_per_step": args.sweeps,
                        "l2": "flushed with a 512 MiB memset before every timed step",
-                       "decomposition": plan, "acceptance": float(acc.sum()) / max(1, float(att.sum())),
+                       "decomposition": plan,
+                       "dE_mode": {0: "reference f64 association for every trial",
+                                   1: "integer-count screening + reference association inside the guard band "
+                                      "(accept/reject decisions identical to mode 0)"}[args.dE_mode], "acceptance": float(acc.sum()) / max(1, float(att.sum())),
                        "energy_per_atom_start_end_Ry": [e_start / N, e_end / N]},
             "e2e": {"value": e2e_value, "unit": "swaps/s", "h2d_bytes_per_step": int(R * (8 * n ** 3 + 8)),
                     "d2h_bytes_per_step": int(R * (8 * n ** 3 + 8 + 24)),
@@ -329,7 +336,7 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": {2: "brw_box_metropolis_fast_kernel<1,4,32,32>", 1: "brw_box_metropolis_kernel<0>", 0: "brw_chain_metropolis_kernel"}[plan["use_box"]],
+                         "traffic": traffic, "kernel": {3: "brw_box_metropolis_fast_kernel<1,4,32,32,true>", 2: "brw_box_metropolis_fast_kernel<1,4,32,32,false>", 1: "brw_box_metropolis_kernel<0>", 0: "brw_chain_metropolis_kernel"}[plan["use_box"]],
                          "algorithmic_bytes_per_attempt": B_ALG, "attempts_per_launch": per_launch_trials,
                          "ms_per_launch": per_launch_ms, "peak_source": peak_src,
                          "note": "lattice is L2/shared-memory resident by design; see DESIGN.md"},

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "brawl_cuda_metropolis_enqueue": [_vp, _vp, _i64, _i, _u64, _u64, _vp, _vp, _vp],
     "brawl_cuda_metropolis_counters": [_vp, _i, _vp, _vp, _vp],
     "brawl_cuda_metropolis_tune": [_vp, _i, _i, _i, _i],
+    "brawl_cuda_metropolis_set_mode": [_vp, _i],
     "brawl_cuda_metropolis_plan": [_vp, _i, _vp],
     "brawl_cuda_radial_counts": [_vp, _i, _i, _vp, _vp],
     "brawl_cuda_wl_sweeps_replay": [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _d, _i64, _i, _vp, _vp, _vp],

@@ -211,6 +211,7 @@ struct brawl_cuda_ctx {
   void *mc_plan[2];
   int last_plan;
   int tune_box[3], tune_steps, disable_fast;
+  int dE_mode;                 // 0: reference association for every trial; 1: integer-count screening (default)
 };
 
 int brw_fail(const char *fmt, ...);              // sets last error, returns 1

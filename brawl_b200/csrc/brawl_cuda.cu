@@ -134,6 +134,7 @@ extern "C" int brawl_cuda_create(int lattice, int n1, int n2, int n3, int S, int
   h->n_replicas = n_replicas;
   h->grid_cells = (int64_t)g.gx * g.gy * g.gz;
   h->tune_box[0] = h->tune_box[1] = h->tune_box[2] = 0; h->tune_steps = 0;
+  h->dE_mode = 1;
 #define BRW_CREATE_CUDA(x) do { if (brw_cuda_check((x), #x)) { brawl_cuda_destroy(h); return 1; } } while (0)
   BRW_CREATE_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
@@ -367,8 +368,9 @@ extern "C" int brawl_cuda_metropolis_replay(brawl_cuda_t *h, int replica, double
 typedef void (*BrwFastKernel)(BrwGeom, BrwBoxParams, uint8_t *, const double *, const double *, const int4 *,
                               const int4 *, uint32_t, uint32_t, uint32_t, unsigned long long *, unsigned long long *,
                               double *);
-struct BrwFastEntry { int lat, nsh, px, py; BrwFastKernel fn; };
-#define BRW_FAST(LAT, NSH, PX, PY) {LAT, NSH, PX, PY, brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY>}
+struct BrwFastEntry { int lat, nsh, px, py; BrwFastKernel fn, fn_screen; };
+#define BRW_FAST(LAT, NSH, PX, PY) {LAT, NSH, PX, PY, brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, false>, \
+                                    brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, true>}
 static const BrwFastEntry brw_fast_table[] = {
     BRW_FAST(1, 4, 32, 32), BRW_FAST(1, 6, 32, 32), BRW_FAST(1, 4, 16, 16), BRW_FAST(1, 6, 16, 16),
     BRW_FAST(2, 4, 32, 64), BRW_FAST(2, 6, 32, 64), BRW_FAST(2, 4, 16, 32), BRW_FAST(2, 6, 16, 32),
@@ -451,6 +453,11 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
   }
   if (feasible) {
     p.P = P; p.m = m;
+    {
+      double vmax = 0.0;
+      for (int i = 0; i < g.S * g.S * g.n_shells; i++) vmax = std::max(vmax, std::fabs(h->hV[i]));
+      p.guard = 1e-9 * g.ztot * vmax;
+    }
     p.M = 1;
     for (int d = 0; d < 3; d++) {
       int G = d == 0 ? g.gx : d == 1 ? g.gy : g.gz;
@@ -490,13 +497,16 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
     BRW_PLAN_CUDA(cudaMemcpy(pl->d_Vrep, vrep.data(), vrep.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (nbr_swap) BRW_PLAN_CUDA(cudaFuncSetAttribute(brw_box_metropolis_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     else BRW_PLAN_CUDA(cudaFuncSetAttribute(brw_box_metropolis_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
-    if (!nbr_swap && !h->disable_fast && p.M <= 1024)
+    if (!nbr_swap && !h->disable_fast && p.M <= 768)
       for (const BrwFastEntry &fe : brw_fast_table)
         if (fe.lat == g.lattice && fe.nsh == g.n_shells && fe.px == p.bxc && fe.py == p.byc) {
-          pl->fast_fn = (void *)fe.fn;
+          // screening needs <= 5 species (four 8-bit count fields + one inferred) and is a per-handle option
+          const bool screen = h->dE_mode == 1 && g.S <= 5;
+          pl->fast_fn = (void *)(screen ? fe.fn_screen : fe.fn);
+          pl->screened = screen;
           pl->fast_smem = (size_t)p.v_entries * 16 * 8 + 32 * 8 + (size_t)p.steps * sizeof(BrwStepParams) + p.box_sites;
-          pl->threads = std::min(1024, ((p.M + 31) / 32) * 32);
-          BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)fe.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
+          pl->threads = std::min(768, ((p.M + 31) / 32) * 32);
+          BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)pl->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
         }
     pl->use_box = true;
     pl->n_slots = p.boxes_per_replica * h->n_replicas;
@@ -527,6 +537,14 @@ extern "C" int brawl_cuda_metropolis_tune(brawl_cuda_t *h, int bx, int by, int b
   for (int i = 0; i < 2; i++) { brw_free_plan((BrwPlan *)h->mc_plan[i]); h->mc_plan[i] = nullptr; }
   return 0;
 }
+extern "C" int brawl_cuda_metropolis_set_mode(brawl_cuda_t *h, int dE_mode) {
+  BRW_ENTER(h);
+  if (dE_mode != 0 && dE_mode != 1) return brw_fail("dE_mode must be 0 (reference association for every trial) or 1 (screened)");
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  h->dE_mode = dE_mode;
+  for (int i = 0; i < 2; i++) { brw_free_plan((BrwPlan *)h->mc_plan[i]); h->mc_plan[i] = nullptr; }
+  return 0;
+}
 extern "C" int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *o) {
   BRW_ENTER(h);
   BrwPlan *pl;
@@ -534,7 +552,7 @@ extern "C" int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *o)
   if (o) {
     o[0] = pl->use_box; o[1] = pl->p.P; o[2] = pl->p.m; o[3] = pl->p.B[0]; o[4] = pl->p.B[1]; o[5] = pl->p.B[2];
     o[6] = pl->p.M; o[7] = pl->p.boxes_per_replica; o[8] = pl->p.n_disp; o[9] = pl->p.steps;
-    if (pl->fast_fn) o[0] = 2;
+    if (pl->fast_fn) o[0] = pl->screened ? 3 : 2;
   }
   return 0;
 }

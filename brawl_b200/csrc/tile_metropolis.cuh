@@ -24,6 +24,7 @@
 #include "brawl_common.cuh"
 
 struct BrwBoxParams {          // POD kernel parameter
+  double guard;                // screening guard band on dE (Ry); see brw_box_metropolis_fast_kernel
   int P, m;
   int B[3], nb[3], A[3], M;
   int bxc, byc, bzc, box_sites;
@@ -44,6 +45,7 @@ struct BrwPlan {
   size_t smem = 0;
   int threads = 0;
   void *fast_fn = nullptr;     // specialised kernel for this (lattice, shells, pitch), if instantiated
+  bool screened = false;
   size_t fast_smem = 0;
   // per-box counters
   unsigned long long *d_att = nullptr, *d_acc = nullptr;
@@ -334,9 +336,31 @@ template <int LAT, int PX, int PY, int PAR, int K0, int... Is>
 __device__ __forceinline__ void brw_fast_shell(const uint8_t *bc, const char *Va, const char *Vb, double &ea,
                                                double &eb, std::integer_sequence<int, Is...>) {
   // comma fold keeps the reference's left-to-right neighbour order
-  ((ea = __dadd_rn(ea, *reinterpret_cast<const double *>(Va + ((int)bc[BrwCOff<LAT, PX, PY, PAR, K0 + Is>::value] << 7))),
-    eb = __dadd_rn(eb, *reinterpret_cast<const double *>(Vb + ((int)bc[BrwCOff<LAT, PX, PY, PAR, K0 + Is>::value] << 7)))),
+  // box bytes hold 8*species, so (byte << 4) is the 128-byte stride of the lane-replicated V table
+  ((ea = __dadd_rn(ea, *reinterpret_cast<const double *>(Va + ((int)bc[BrwCOff<LAT, PX, PY, PAR, K0 + Is>::value] << 4))),
+    eb = __dadd_rn(eb, *reinterpret_cast<const double *>(Vb + ((int)bc[BrwCOff<LAT, PX, PY, PAR, K0 + Is>::value] << 4)))),
    ...);
+}
+// ---- integer neighbour counts (screening path) ----------------------------------------------------
+// acc gets one 8-bit field per species 0..3: field s counts neighbours of species s in this shell.
+// PTX shl.b32 clamps shift amounts > 31 to "all bits out", so species 4 (byte 32) adds 0 and is
+// recovered as Z_n - sum(others).  Counts are <= 32 per shell, so fields never overflow.
+__device__ __forceinline__ uint32_t brw_shl1(uint32_t sh) {
+  uint32_t r;
+  asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(sh));
+  return r;
+}
+template <int LAT, int PX, int PY, int PAR, int K0, int... Is>
+__device__ __forceinline__ uint32_t brw_count_shell(const uint8_t *bc, std::integer_sequence<int, Is...>) {
+  return (brw_shl1(bc[BrwCOff<LAT, PX, PY, PAR, K0 + Is>::value]) + ...);
+}
+template <int LAT, int NSH, int PX, int PY, int PAR, int N>
+__device__ __forceinline__ void brw_count_shells(const uint8_t *bc, uint32_t (&acc)[NSH]) {
+  if constexpr (N < NSH) {
+    acc[N] = brw_count_shell<LAT, PX, PY, PAR, BrwShellRange<LAT, N>::start>(
+        bc, std::make_integer_sequence<int, BrwShellRange<LAT, N>::count>{});
+    brw_count_shells<LAT, NSH, PX, PY, PAR, N + 1>(bc, acc);
+  }
 }
 template <int LAT, int NSH, int PX, int PY, int PAR, int N>
 __device__ __forceinline__ void brw_fast_shells(const uint8_t *bc, const char *Vl, int S, int ca, int cb, double &Ea,
@@ -369,14 +393,22 @@ __device__ __forceinline__ void brw_box_copy(const BrwGeom &g, uint8_t *L, uint8
     if (lane < PX) {
       int gxc = oxc + lane; if (gxc >= g.cx) gxc -= g.cx; if (gxc >= g.cx) gxc -= g.cx;
       const long gi = ((long)gzz * g.cy + (gyy >> g.ys)) * g.cx + gxc;
-      if (STORE) L[gi] = box[r * PX + lane];
-      else box[r * PX + lane] = L[gi];
+      if (STORE) L[gi] = (uint8_t)(box[r * PX + lane] >> 3);     // shared-memory bytes hold 8*species
+      else box[r * PX + lane] = (uint8_t)(L[gi] << 3);
     }
   }
 }
 
-template <int LAT, int NSH, int PX, int PY>
-__global__ void __launch_bounds__(1024) brw_box_metropolis_fast_kernel(
+// SCREEN = true: the decision is first attempted with dE formed from integer neighbour counts
+// (dE = sum_n sum_s (c1-c2)[n][s] * (V_n[b][s] - V_n[a][s]); exact counts, different f64 rounding).
+// Whenever that value is within a guard band of a decision boundary (|dE| < guard, or |u - exp(-beta dE)|
+// within the propagated band) the trial is recomputed with the reference's association and decided
+// by it.  The guard (host: 1e-9 * ztot * max|V|) exceeds the worst-case rounding difference between
+// the two formulas by > 4 orders of magnitude, so every accept/reject equals the one the reference
+// arithmetic yields: trajectories are identical to SCREEN = false
+// (test_screened_kernel_trajectory_identical).
+template <int LAT, int NSH, int PX, int PY, bool SCREEN>
+__global__ void __launch_bounds__(768) brw_box_metropolis_fast_kernel(
     BrwGeom g, BrwBoxParams p, uint8_t *__restrict__ lat, const double *__restrict__ beta,
     const double *__restrict__ Vrep, const int4 *__restrict__ classes, const int4 *__restrict__ disp, uint32_t k0,
     uint32_t k1, uint32_t phase_lo, unsigned long long *__restrict__ att_out,
@@ -431,18 +463,49 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_fast_kernel(
       n_att++;
       if ((step & 3) == 0) rnd = brw_philox((uint32_t)tid, (uint32_t)step, box_id, phase_lo, k0, k1);
       if (a != b) {
-        double E1a, E1b, E2b, E2a;
-        if (q.par1) brw_fast_shells<LAT, NSH, PX, PY, 1, 0>(box + c1, Vl, S, a, b, E1a, E1b);
-        else brw_fast_shells<LAT, NSH, PX, PY, 0, 0>(box + c1, Vl, S, a, b, E1a, E1b);
-        if (q.par2) brw_fast_shells<LAT, NSH, PX, PY, 1, 0>(box + c2, Vl, S, b, a, E2b, E2a);
-        else brw_fast_shells<LAT, NSH, PX, PY, 0, 0>(box + c2, Vl, S, b, a, E2b, E2a);
-        const double before = __dadd_rn(E1a, E2b);             // pair_energy, sites unswapped
-        const double after = __dadd_rn(E1b, E2a);              // pair_energy, sites swapped
-        const double dE = __dsub_rn(after, before);            // src/metropolis.F90:792
-        bool accept = dE < 0.0;                                // :796
-        if (!accept) {
-          const uint32_t w = (step & 3) == 0 ? rnd.x : (step & 3) == 1 ? rnd.y : (step & 3) == 2 ? rnd.z : rnd.w;
-          accept = brw_u01(w) < exp(-my_beta * dE);            // :802
+        const int sa = a >> 3, sb = b >> 3;                    // species (box bytes hold 8*species)
+        const uint32_t w = (step & 3) == 0 ? rnd.x : (step & 3) == 1 ? rnd.y : (step & 3) == 2 ? rnd.z : rnd.w;
+        const double u = brw_u01(w);
+        bool decided = false, accept = false;
+        double dE = 0.0;
+        if (SCREEN) {
+          uint32_t A1[NSH], A2[NSH];
+          if (q.par1) brw_count_shells<LAT, NSH, PX, PY, 1, 0>(box + c1, A1);
+          else brw_count_shells<LAT, NSH, PX, PY, 0, 0>(box + c1, A1);
+          if (q.par2) brw_count_shells<LAT, NSH, PX, PY, 1, 0>(box + c2, A2);
+          else brw_count_shells<LAT, NSH, PX, PY, 0, 0>(box + c2, A2);
+          const int s4 = S < 4 ? S : 4;
+#pragma unroll
+          for (int n = 0; n < NSH; n++) {
+            const double *Va = reinterpret_cast<const double *>(Vl + ((n * S + sa) * S) * 128);
+            const double *Vb = reinterpret_cast<const double *>(Vl + ((n * S + sb) * S) * 128);
+            int rest = 0;
+            for (int sp = 0; sp < s4; sp++) {
+              const int d = (int)((A1[n] >> (8 * sp)) & 255u) - (int)((A2[n] >> (8 * sp)) & 255u);
+              rest -= d;
+              dE = fma((double)d, Vb[sp * 16] - Va[sp * 16], dE);
+            }
+            if (S == 5) dE = fma((double)rest, Vb[4 * 16] - Va[4 * 16], dE);
+          }
+          if (fabs(dE) > p.guard) {
+            if (dE < 0.0) { accept = true; decided = true; }
+            else {
+              const double t = exp(-my_beta * dE);
+              if (fabs(u - t) > t * (my_beta * p.guard + 1e-12)) { accept = u < t; decided = true; }
+            }
+          }
+        }
+        if (!decided) {
+          double E1a, E1b, E2b, E2a;
+          if (q.par1) brw_fast_shells<LAT, NSH, PX, PY, 1, 0>(box + c1, Vl, S, sa, sb, E1a, E1b);
+          else brw_fast_shells<LAT, NSH, PX, PY, 0, 0>(box + c1, Vl, S, sa, sb, E1a, E1b);
+          if (q.par2) brw_fast_shells<LAT, NSH, PX, PY, 1, 0>(box + c2, Vl, S, sb, sa, E2b, E2a);
+          else brw_fast_shells<LAT, NSH, PX, PY, 0, 0>(box + c2, Vl, S, sb, sa, E2b, E2a);
+          const double before = __dadd_rn(E1a, E2b);           // pair_energy, sites unswapped
+          const double after = __dadd_rn(E1b, E2a);            // pair_energy, sites swapped
+          dE = __dsub_rn(after, before);                       // src/metropolis.F90:792
+          accept = dE < 0.0;                                   // :796
+          if (!accept) accept = u < exp(-my_beta * dE);        // :802
         }
         if (accept) { box[c1] = (uint8_t)b; box[c2] = (uint8_t)a; n_acc++; dE_sum += dE; }
       } else n_acc++;                                          // :774-777

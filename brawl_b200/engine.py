@@ -159,6 +159,11 @@ class Device:
     def metropolis_tune(self, box=(0, 0, 0), steps_per_phase=0):
         check(self.L.brawl_cuda_metropolis_tune(self.h, box[0], box[1], box[2], steps_per_phase))
 
+    def metropolis_set_mode(self, dE_mode):
+        """0: reference f64 association for every trial; 1 (default): integer-count screening with
+        exact recomputation inside the guard band (decision-identical)."""
+        check(self.L.brawl_cuda_metropolis_set_mode(self.h, int(dE_mode)))
+
     def metropolis_plan(self, nbr_swap=False):
         o = np.zeros(10, dtype=np.int32)
         check(self.L.brawl_cuda_metropolis_plan(self.h, int(nbr_swap), _p(o)))

@@ -122,9 +122,15 @@ int brawl_cuda_metropolis_counters(brawl_cuda_t *h, int reset, int64_t *n_attemp
  * steps per phase.  steps_per_phase = -(s+1) selects s steps AND forces the generic
  * runtime-geometry kernel instead of a specialised instantiation (test hook). */
 int brawl_cuda_metropolis_tune(brawl_cuda_t *h, int box_x, int box_y, int box_z, int steps_per_phase);
+/* How the specialised box kernels form dE.  0: the reference's f64 association for every trial.
+ * 1 (default): integer neighbour counts give dE first; any trial whose dE or acceptance test lies
+ * within a guard band of a decision boundary is recomputed with the reference's association and
+ * decided by it, so accept/reject decisions -- and therefore trajectories -- are identical to mode 0
+ * (needs <= 5 species; otherwise mode 0 is used). */
+int brawl_cuda_metropolis_set_mode(brawl_cuda_t *h, int dE_mode);
 /* Describe the decomposition chosen: period P, margin, box extents, active cells, boxes/replica,
  * |D| (number of allowed displacement classes); out10[0] = 0 chain kernel, 1 generic box kernel,
- * 2 specialised (compile-time geometry) box kernel */
+ * 2 specialised (compile-time geometry) box kernel, 3 specialised + screened dE */
 int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *out10);
 
 /* ---- short-range order ----------------------------------------------------------------------

@@ -365,13 +365,41 @@ def test_specialised_kernel_equals_generic_kernel(bw, orc, golden, lattice, n, S
         if generic:
             dev.metropolis_tune((0, 0, 0), -1)          # automatic steps, generic kernel forced
         plan = dev.metropolis_plan()
-        assert plan["use_box"] == (1 if generic else 2), plan
+        assert plan["use_box"] == (1 if generic else 3), plan
         dev.set_config(g)
         out = dev.metropolis_run(1.0 / (700.0 * bw.K_B_IN_RY), 3 * int(mask.sum()), seed=77)
         res.append((dev.get_config().copy(), out))
     assert np.array_equal(res[0][0], res[1][0])
     for a, b in zip(res[0][1], res[1][1]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("lattice,n,S,shells,key,T", [("bcc", 32, 4, 4, "ex_AlTiCrMo_V", 300.0), ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", 2000.0),
+                                                      ("bcc", 32, 5, 4, "ex_AlCrFeCoNi_V", 800.0), ("fcc", 16, 5, 4, "ex_AlCrFeCoNi_V", 600.0),
+                                                      ("fcc", 32, 2, 6, "t01_V", 500.0)])
+def test_screened_kernel_trajectory_identical(bw, orc, golden, lattice, n, S, shells, key, T):
+    """dE_mode 1 (integer-count screening, reference association recomputed inside the guard band)
+    takes exactly the accept/reject decisions of dE_mode 0 (reference association for every trial):
+    same seed => identical configuration and identical accept counts after millions of trials."""
+    V = golden[key][: 5 * 5 * shells].reshape(shells, 5, 5)[:, :S, :S].copy().ravel() if key != "ex_AlTiCrMo_V" else golden[key][: S * S * shells]
+    g = np.zeros((2 * n, 2 * n, 2 * n), dtype=np.int8)
+    rng = np.random.default_rng(4)
+    par = np.arange(2 * n) & 1
+    mask = ((par[None, None, :] == par[:, None, None]) & (par[None, :, None] == par[:, None, None])) if lattice == "bcc" else \
+        (((par[None, None, :] + par[None, :, None] + par[:, None, None]) & 1) == 0)
+    g[mask] = rng.integers(1, S + 1, size=int(mask.sum()))
+    res = []
+    for mode in (0, 1):
+        dev = bw.Device(lattice, n, n, n, S, shells, V)
+        dev.metropolis_set_mode(mode)
+        assert dev.metropolis_plan()["use_box"] == (3 if mode else 2)
+        dev.set_config(g)
+        out = dev.metropolis_run(1.0 / (T * bw.K_B_IN_RY), 12 * int(mask.sum()), seed=99)
+        res.append((dev.get_config().copy(), out, dev.total_energy()[0]))
+    assert np.array_equal(res[0][0], res[1][0])
+    assert np.array_equal(res[0][1][0], res[1][1][0]) and np.array_equal(res[0][1][1], res[1][1][1])
+    assert res[0][2] == res[1][2]
+    assert abs(res[0][1][2][0] - res[1][1][2][0]) < 1e-9          # sum of accepted dE: same to rounding
 
 
 def test_production_limits(bw, orc, golden):
