@@ -368,12 +368,14 @@ extern "C" int brawl_cuda_metropolis_replay(brawl_cuda_t *h, int replica, double
 typedef void (*BrwFastKernel)(BrwGeom, BrwBoxParams, uint8_t *, const double *, const double *, const int4 *,
                               const int4 *, uint32_t, uint32_t, uint32_t, unsigned long long *, unsigned long long *,
                               double *);
-struct BrwFastEntry { int lat, nsh, px, py; BrwFastKernel fn, fn_screen; };
-#define BRW_FAST(LAT, NSH, PX, PY) {LAT, NSH, PX, PY, brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, false>, \
-                                    brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, true>}
+struct BrwFastEntry { int lat, nsh, px, py, maxt; BrwFastKernel fn, fn_screen; };
+// MAXT = launch bound: CTAs of <= 384 threads (e.g. the 128^3 single chain, 352 threads) may use up to
+// 168 registers/thread, CTAs of <= 768 threads (e.g. one 32^3-cell replica per CTA, 736 threads) 80.
+#define BRW_FAST(LAT, NSH, PX, PY, MAXT) {LAT, NSH, PX, PY, MAXT, brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, false, MAXT>, \
+                                          brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, true, MAXT>}
 static const BrwFastEntry brw_fast_table[] = {
-    BRW_FAST(1, 4, 32, 32), BRW_FAST(1, 6, 32, 32), BRW_FAST(1, 4, 16, 16), BRW_FAST(1, 6, 16, 16),
-    BRW_FAST(2, 4, 32, 64), BRW_FAST(2, 6, 32, 64), BRW_FAST(2, 4, 16, 32), BRW_FAST(2, 6, 16, 32),
+    BRW_FAST(1, 4, 32, 32, 384), BRW_FAST(1, 4, 32, 32, 768), BRW_FAST(1, 6, 32, 32, 384), BRW_FAST(1, 6, 32, 32, 768),
+    BRW_FAST(2, 4, 32, 64, 384), BRW_FAST(2, 4, 32, 64, 768), BRW_FAST(2, 6, 32, 64, 384), BRW_FAST(2, 6, 32, 64, 768),
 };
 
 // launch helper for the warp-per-walker kernels: layout + opt-in shared memory
@@ -499,7 +501,8 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
     else BRW_PLAN_CUDA(cudaFuncSetAttribute(brw_box_metropolis_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     if (!nbr_swap && !h->disable_fast && p.M <= 768)
       for (const BrwFastEntry &fe : brw_fast_table)
-        if (fe.lat == g.lattice && fe.nsh == g.n_shells && fe.px == p.bxc && fe.py == p.byc) {
+        if (!pl->fast_fn && fe.lat == g.lattice && fe.nsh == g.n_shells && fe.px == p.bxc && fe.py == p.byc &&
+            ((p.M + 31) / 32) * 32 <= fe.maxt) {
           // screening needs <= 5 species (four 8-bit count fields + one inferred) and is a per-handle option
           const bool screen = h->dE_mode == 1 && g.S <= 5;
           pl->fast_fn = (void *)(screen ? fe.fn_screen : fe.fn);

@@ -407,8 +407,8 @@ __device__ __forceinline__ void brw_box_copy(const BrwGeom &g, uint8_t *L, uint8
 // the two formulas by > 4 orders of magnitude, so every accept/reject equals the one the reference
 // arithmetic yields: trajectories are identical to SCREEN = false
 // (test_screened_kernel_trajectory_identical).
-template <int LAT, int NSH, int PX, int PY, bool SCREEN>
-__global__ void __launch_bounds__(768) brw_box_metropolis_fast_kernel(
+template <int LAT, int NSH, int PX, int PY, bool SCREEN, int MAXT>
+__global__ void __launch_bounds__(MAXT) brw_box_metropolis_fast_kernel(
     BrwGeom g, BrwBoxParams p, uint8_t *__restrict__ lat, const double *__restrict__ beta,
     const double *__restrict__ Vrep, const int4 *__restrict__ classes, const int4 *__restrict__ disp, uint32_t k0,
     uint32_t k1, uint32_t phase_lo, unsigned long long *__restrict__ att_out,
@@ -474,16 +474,20 @@ __global__ void __launch_bounds__(768) brw_box_metropolis_fast_kernel(
           else brw_count_shells<LAT, NSH, PX, PY, 0, 0>(box + c1, A1);
           if (q.par2) brw_count_shells<LAT, NSH, PX, PY, 1, 0>(box + c2, A2);
           else brw_count_shells<LAT, NSH, PX, PY, 0, 0>(box + c2, A2);
-          const int s4 = S < 4 ? S : 4;
+          // fully unrolled over (shell, species): counts stay in registers
 #pragma unroll
           for (int n = 0; n < NSH; n++) {
             const double *Va = reinterpret_cast<const double *>(Vl + ((n * S + sa) * S) * 128);
             const double *Vb = reinterpret_cast<const double *>(Vl + ((n * S + sb) * S) * 128);
+            const uint32_t x1 = A1[n], x2 = A2[n];
             int rest = 0;
-            for (int sp = 0; sp < s4; sp++) {
-              const int d = (int)((A1[n] >> (8 * sp)) & 255u) - (int)((A2[n] >> (8 * sp)) & 255u);
-              rest -= d;
-              dE = fma((double)d, Vb[sp * 16] - Va[sp * 16], dE);
+#pragma unroll
+            for (int sp = 0; sp < 4; sp++) {
+              if (sp < S) {
+                const int d = (int)__byte_perm(x1, 0, 0x4440 | sp) - (int)__byte_perm(x2, 0, 0x4440 | sp);
+                rest -= d;
+                dE = fma((double)d, Vb[sp * 16] - Va[sp * 16], dE);
+              }
             }
             if (S == 5) dE = fma((double)rest, Vb[4 * 16] - Va[4 * 16], dE);
           }
