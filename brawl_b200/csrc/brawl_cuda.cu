@@ -470,8 +470,8 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
     p.n_classes = (int)classes.size(); p.n_disp = (int)disp.size();
     p.boxes_per_replica = p.nb[0] * p.nb[1] * p.nb[2];
     p.v_entries = g.S * g.S * g.n_shells;
-    // default: about two sweeps of the box per phase (amortises the box load/store)
-    int steps = h->tune_steps > 0 ? h->tune_steps : (2 * p.box_sites + p.M - 1) / p.M;
+    // default: about four sweeps of the box per phase (amortises the box load/store)
+    int steps = h->tune_steps > 0 ? h->tune_steps : (4 * p.box_sites + p.M - 1) / p.M;
     p.steps = std::max(8, std::min(steps, 512));
     pl->threads = std::min(1024, ((p.M + 31) / 32) * 32);
     pl->smem = (size_t)p.v_entries * 16 * 8 + (size_t)2 * g.ztot * 4 + 2 * sizeof(BrwStepParams) + 32 * 8 + p.box_sites;

@@ -350,16 +350,25 @@ __device__ __forceinline__ uint32_t brw_shl1(uint32_t sh) {
   asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(sh));
   return r;
 }
+// ld.shared.u8 straight into a 32-bit register with the neighbour offset as an immediate (avoids the
+// byte->word PRMT the C++ uint8_t load would add).  Neighbours are never the two sites of the
+// trial, so ordering against this thread's own box stores is irrelevant.
+template <int OFF>
+__device__ __forceinline__ uint32_t brw_lds_u8(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(saddr), "n"(OFF));
+  return v;
+}
 template <int LAT, int PX, int PY, int PAR, int K0, int... Is>
-__device__ __forceinline__ uint32_t brw_count_shell(const uint8_t *bc, std::integer_sequence<int, Is...>) {
-  return (brw_shl1(bc[BrwCOff<LAT, PX, PY, PAR, K0 + Is>::value]) + ...);
+__device__ __forceinline__ uint32_t brw_count_shell(uint32_t saddr, std::integer_sequence<int, Is...>) {
+  return (brw_shl1(brw_lds_u8<BrwCOff<LAT, PX, PY, PAR, K0 + Is>::value>(saddr)) + ...);
 }
 template <int LAT, int NSH, int PX, int PY, int PAR, int N>
-__device__ __forceinline__ void brw_count_shells(const uint8_t *bc, uint32_t (&acc)[NSH]) {
+__device__ __forceinline__ void brw_count_shells(uint32_t saddr, uint32_t (&acc)[NSH]) {
   if constexpr (N < NSH) {
     acc[N] = brw_count_shell<LAT, PX, PY, PAR, BrwShellRange<LAT, N>::start>(
-        bc, std::make_integer_sequence<int, BrwShellRange<LAT, N>::count>{});
-    brw_count_shells<LAT, NSH, PX, PY, PAR, N + 1>(bc, acc);
+        saddr, std::make_integer_sequence<int, BrwShellRange<LAT, N>::count>{});
+    brw_count_shells<LAT, NSH, PX, PY, PAR, N + 1>(saddr, acc);
   }
 }
 template <int LAT, int NSH, int PX, int PY, int PAR, int N>
@@ -441,6 +450,7 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_fast_kernel(
 
   const double my_beta = beta[replica];
   const char *Vl = reinterpret_cast<const char *>(Vs + (tid & 15));
+  const uint32_t box_s = (uint32_t)__cvta_generic_to_shared(box);
   const int S = g.S;
   const int stx = p.P >> 1, sty = (LAT == 1 ? (p.P >> 1) : p.P) * PX, stz = p.P * PY * PX;
   // this thread's coarse cell (fixed for the whole phase; blockDim >= M is guaranteed by the host)
@@ -470,10 +480,11 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_fast_kernel(
         double dE = 0.0;
         if (SCREEN) {
           uint32_t A1[NSH], A2[NSH];
-          if (q.par1) brw_count_shells<LAT, NSH, PX, PY, 1, 0>(box + c1, A1);
-          else brw_count_shells<LAT, NSH, PX, PY, 0, 0>(box + c1, A1);
-          if (q.par2) brw_count_shells<LAT, NSH, PX, PY, 1, 0>(box + c2, A2);
-          else brw_count_shells<LAT, NSH, PX, PY, 0, 0>(box + c2, A2);
+          const uint32_t sa1 = box_s + c1, sa2 = box_s + c2;
+          if (q.par1) brw_count_shells<LAT, NSH, PX, PY, 1, 0>(sa1, A1);
+          else brw_count_shells<LAT, NSH, PX, PY, 0, 0>(sa1, A1);
+          if (q.par2) brw_count_shells<LAT, NSH, PX, PY, 1, 0>(sa2, A2);
+          else brw_count_shells<LAT, NSH, PX, PY, 0, 0>(sa2, A2);
           // fully unrolled over (shell, species): counts stay in registers
 #pragma unroll
           for (int n = 0; n < NSH; n++) {
