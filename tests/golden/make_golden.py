@@ -80,6 +80,15 @@ def main():
     out["ex_AlTiCrMo_V"] = vij(REF + "/examples/02_wang-landau_AlTiCrMo/AlTiCrMo.vij")
     out["ex_FeNi_V"] = vij(glob.glob(REF + "/examples/01_metropolis_FeNi/**/FeNi.vij", recursive=True)[0])
     out["ex_AlCrFeCoNi_V"] = vij(glob.glob(REF + "/examples/03_nested_sampling_AlCrFeCoNi/**/*.vij", recursive=True)[0])
+    # --- the reference's own input files for its regression cases (text) + two raw NetCDF goldens
+    for case, files in (("01_serial_metropolis", ("brawl.inp", "metropolis.inp", "fcc_epi.vij")),
+                        ("02_parallel_metropolis", ("brawl.inp", "metropolis.inp", "bcc_epi.vij")),
+                        ("03_serial_nested_sampling", ("brawl.inp", "ns_input.inp", "fcc_al_1.00_crfeconi.vij"))):
+        for fn in files:
+            out["in_%s_%s" % (case[:2], fn)] = text(t + case + "/" + fn)
+    out["raw_t02_r0_initial_nc"] = np.frombuffer(open(r + "02_parallel_metropolis/proc_0000_initial_config_at_0300.0.nc", "rb").read(), dtype=np.uint8)
+    out["raw_t02_r0_rho_nc"] = np.frombuffer(open(r + "02_parallel_metropolis/proc_0000_rho_of_T.nc", "rb").read(), dtype=np.uint8)
+    out["raw_t02_av_rho_nc"] = np.frombuffer(open(r + "02_parallel_metropolis/av_radial_density.nc", "rb").read(), dtype=np.uint8)
     path = os.path.join(HERE, "brawl_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", len(out), "entries")
