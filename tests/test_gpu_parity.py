@@ -525,3 +525,72 @@ def test_wl_and_ns_production_kernels(bw, orc, golden):
     e2, nacc = dev.ns_walk(np.arange(W), e_exact, lim, 500, seed=6)
     assert np.all(e2 < lim) and np.all(nacc > 0)
     assert np.allclose(e2, dev.total_energy(0, W), rtol=0, atol=1e-11)
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases and full-size properties
+def test_edge_cases_empty_and_degenerate_inputs(bw, orc, golden):
+    V = golden["t02_V"]
+    sysm = orc.System("bcc", 4, 4, 4, 4, 6, V)
+    g = random_config(orc, sysm, 2)
+    dev = bw.Device("bcc", 4, 4, 4, 4, 6, V)
+    dev.set_config(g)
+    assert dev.pair_dE([], []).size == 0                                   # empty batch
+    st = orc.MT(seed=1).state625(); st0 = st.copy()
+    assert dev.metropolis_replay(1.0, 0, st) == 0 and np.array_equal(st, st0)     # zero trials: RNG untouched
+    att, acc, dE = dev.metropolis_run(1.0, 0)
+    assert att[0] == 0 and acc[0] == 0 and dE[0] == 0.0
+    assert np.array_equal(dev.get_config(), g)
+    bad = st.copy(); bad[624] = 700
+    with pytest.raises(bw.BrawlCudaError, match="MT19937"):
+        dev.metropolis_replay(1.0, 10, bad)
+    with pytest.raises(bw.BrawlCudaError):
+        dev.total_energy(0, 2)                                              # more replicas than the handle owns
+    # single-species lattice: every proposal is a same-species "accept", energy is a constant
+    V1 = np.array([1e-3, -2e-3, 5e-4, 1e-4])
+    one = np.where(g > 0, 1, 0).astype(np.int8)
+    d1 = bw.Device("bcc", 4, 4, 4, 1, 4, V1)
+    d1.set_config(one)
+    assert d1.total_energy()[0] == orc.System("bcc", 4, 4, 4, 1, 4, V1).total_energy(one)
+    att, acc, dE = d1.metropolis_run(5.0, 1000)
+    assert att[0] == acc[0] == 1000 and dE[0] == 0.0
+    # maximum species count of the library (16)
+    S = 16
+    V16 = rand_V(S, 2, 3)
+    s16 = orc.System("fcc", 3, 3, 3, S, 2, V16)
+    g16 = random_config(orc, s16, 9)
+    d16 = bw.Device("fcc", 3, 3, 3, S, 2, V16)
+    d16.set_config(g16)
+    assert d16.total_energy()[0] == s16.total_energy(g16)
+    with pytest.raises(bw.BrawlCudaError, match="n_species"):
+        bw.Device("fcc", 3, 3, 3, 17, 2, np.zeros(17 * 17 * 2))
+
+
+def test_full_size_128_cubed_properties(bw, golden):
+    """BASELINE configs[1] at full size (128^3 bcc, 4 194 304 atoms): size-independent properties --
+    species counts conserved, occupancy pattern intact, sum of accepted dE == change of the exact
+    (reference-order) total energy, exact and tree energies agree, trajectory reproducible."""
+    n, S = 128, 4
+    V = golden["ex_AlTiCrMo_V"][:64]
+    rng = np.random.default_rng(1)
+    par = (np.arange(2 * n) & 1).astype(np.int8)
+    mask = (par[None, None, :] == par[:, None, None]) & (par[None, :, None] == par[:, None, None])
+    g = np.zeros((2 * n,) * 3, dtype=np.int8)
+    spec = np.repeat(np.arange(1, S + 1, dtype=np.int8), 2 * n ** 3 // S); rng.shuffle(spec)
+    g[mask] = spec
+    N = 2 * n ** 3
+    finals = []
+    for rep in range(2):
+        dev = bw.Device("bcc", n, n, n, S, 4, V)
+        dev.set_config(g)
+        e0 = dev.total_energy(exact_order=True)[0]
+        assert abs(dev.total_energy(exact_order=False)[0] - e0) < 1e-9 * abs(e0) + 1e-9
+        att, acc, dE = dev.metropolis_run(1.0 / (1000.0 * bw.K_B_IN_RY), 4 * N, seed=5)
+        g1 = dev.get_config()
+        e1 = dev.total_energy(exact_order=True)[0]
+        assert att[0] >= 4 * N and 0 < acc[0] < att[0]
+        assert np.array_equal(np.bincount(g1.ravel(), minlength=S + 1), np.bincount(g.ravel(), minlength=S + 1))
+        assert np.array_equal(g1 == 0, g == 0)
+        assert abs((e1 - e0) - dE[0]) < 1e-9 * abs(e1 - e0) + 1e-9, (e0, e1, dE[0])
+        finals.append((g1, att[0], acc[0], e1))
+    assert np.array_equal(finals[0][0], finals[1][0]) and finals[0][1:] == finals[1][1:]
