@@ -184,9 +184,10 @@ def main():
     ap.add_argument("--workload", default="chain", choices=["chain", "replicas"],
                     help="chain: BASELINE configs[1] (headline); replicas: configs[4], R x 32^3 bcc AlCrFeCoNi per GPU")
     ap.add_argument("--replicas", type=int, default=1024)
-    ap.add_argument("--dE-mode", type=int, default=1, choices=[0, 1],
-                    help="1 (library default): integer-count screening, reference association recomputed inside the guard "
-                         "band (decision-identical); 0: reference association for every trial")
+    ap.add_argument("--dE-mode", type=int, default=2, choices=[0, 1, 2],
+                    help="2 (library default): word-lattice kernel, integer-count screening with fixed-point dp4a dE, "
+                         "reference association recomputed inside the guard band (decision-identical); 1: the same "
+                         "screening on the byte lattice; 0: reference association for every trial")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = max(args.warmup, 3) if os.environ.get("BENCH_ALLOW_SHORT_WARMUP") is None else args.warmup
@@ -276,7 +277,7 @@ def main():
     sampler.mark_end()
     clocks = sampler.stop()
     att, acc, dE = dev.metropolis_counters(reset=True)
-    assert att[0] == attempts, (att, attempts)
+    assert att[0] == attempts, (att, attempts)      # planned == counted on the device
     attempts *= R                                   # planned attempts are per replica
     total_ms = float(np.sum(times))
     e_end = dev.total_energy(0, R, exact_order=False).mean()
@@ -301,8 +302,7 @@ def main():
         if it >= 2:
             e2e_times.append(ev0.elapsed_time(ev1))
             e2e_attempts += int(a.sum())
-            per_phase = plan["trials_per_step"] * plan["steps_per_phase"] * plan["boxes_per_replica"]
-            e2e_launches += (int(a[0]) // per_phase if plan["use_box"] else 1) + 4   # + pack, unpack, 2 energy kernels
+            e2e_launches += dev.metropolis_last_launches() + 4   # + pack, unpack, 2 energy kernels
     e2e_ms = float(np.sum(e2e_times))
 
     # ---- reduce over ranks (max time, sum attempts) -----------------------------------------------
@@ -345,7 +345,9 @@ def main():
                        "decomposition": plan,
                        "dE_mode": {0: "reference f64 association for every trial",
                                    1: "integer-count screening + reference association inside the guard band "
-                                      "(accept/reject decisions identical to mode 0)"}[args.dE_mode], "acceptance": float(acc.sum()) / max(1, float(att.sum())),
+                                      "(accept/reject decisions identical to mode 0)",
+                                   2: "word lattice: integer-count screening with fixed-point dp4a dE + reference "
+                                      "association inside the guard band (accept/reject decisions identical to mode 0)"}[args.dE_mode], "acceptance": float(acc.sum()) / max(1, float(att.sum())),
                        "energy_per_atom_start_end_Ry": [e_start / N, e_end / N]},
             "e2e": {"value": e2e_value, "unit": "swaps/s", "h2d_bytes_per_step": int(R * (8 * n ** 3 + 8)),
                     "d2h_bytes_per_step": int(R * (8 * n ** 3 + 8 + 24)),
@@ -353,7 +355,7 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": {3: "brw_box_metropolis_fast_kernel<1,4,32,32,true>", 2: "brw_box_metropolis_fast_kernel<1,4,32,32,false>", 1: "brw_box_metropolis_kernel<0>", 0: "brw_chain_metropolis_kernel"}[plan["use_box"]],
+                         "traffic": traffic, "kernel": {4: "brw_box_metropolis_word_kernel<1,4,32,32,41,1317,4,512,6,6,4,9,9,6>", 3: "brw_box_metropolis_fast_kernel<1,4,32,32,true>", 2: "brw_box_metropolis_fast_kernel<1,4,32,32,false>", 1: "brw_box_metropolis_kernel<0>", 0: "brw_chain_metropolis_kernel"}[plan["use_box"]],
                          "algorithmic_bytes_per_attempt": B_ALG, "attempts_per_launch": per_launch_trials,
                          "ms_per_launch": per_launch_ms, "peak_source": peak_src,
                          "note": "lattice is L2/shared-memory resident by design; see DESIGN.md"},

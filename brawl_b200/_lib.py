@@ -34,6 +34,7 @@ _SIGNATURES = {
     "brawl_cuda_metropolis_run": [_vp, _vp, _i64, _i, _u64, _u64, _vp, _vp, _vp, _vp],
     "brawl_cuda_metropolis_enqueue": [_vp, _vp, _i64, _i, _u64, _u64, _vp, _vp, _vp],
     "brawl_cuda_metropolis_counters": [_vp, _i, _vp, _vp, _vp],
+    "brawl_cuda_metropolis_last_launches": [_vp, _vp],
     "brawl_cuda_metropolis_tune": [_vp, _i, _i, _i, _i],
     "brawl_cuda_metropolis_set_mode": [_vp, _i],
     "brawl_cuda_metropolis_plan": [_vp, _i, _vp],

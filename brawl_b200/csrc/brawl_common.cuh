@@ -210,7 +210,7 @@ struct brawl_cuda_ctx {
   // production Metropolis plans: [0] whole-lattice swaps, [1] neighbour swaps (BrwPlan*)
   void *mc_plan[2];
   int last_plan;
-  int tune_box[3], tune_steps, disable_fast;
+  int tune_box[3], tune_steps, disable_fast, cubic_period_only, last_launches;
   int dE_mode;                 // 0: reference association for every trial; 1: integer-count screening (default)
 };
 

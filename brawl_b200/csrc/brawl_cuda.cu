@@ -16,6 +16,7 @@
 #include "energy_kernels.cuh"
 #include "replay_kernels.cuh"
 #include "tile_metropolis.cuh"
+#include "word_metropolis.cuh"
 #include "walker_kernels.cuh"
 
 // ---- error state ---------------------------------------------------------------------------------
@@ -134,7 +135,7 @@ extern "C" int brawl_cuda_create(int lattice, int n1, int n2, int n3, int S, int
   h->n_replicas = n_replicas;
   h->grid_cells = (int64_t)g.gx * g.gy * g.gz;
   h->tune_box[0] = h->tune_box[1] = h->tune_box[2] = 0; h->tune_steps = 0;
-  h->dE_mode = 1;
+  h->dE_mode = 2;
 #define BRW_CREATE_CUDA(x) do { if (brw_cuda_check((x), #x)) { brawl_cuda_destroy(h); return 1; } } while (0)
   BRW_CREATE_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
@@ -366,7 +367,7 @@ extern "C" int brawl_cuda_metropolis_replay(brawl_cuda_t *h, int replica, double
 
 // ---- production Metropolis ---------------------------------------------------------------------------------
 typedef void (*BrwFastKernel)(BrwGeom, BrwBoxParams, uint8_t *, const double *, const double *, const int4 *,
-                              const int4 *, uint32_t, uint32_t, uint32_t, unsigned long long *, unsigned long long *,
+                              const int4 *, uint32_t, uint32_t, uint32_t, int, unsigned long long *, unsigned long long *,
                               double *);
 struct BrwFastEntry { int lat, nsh, px, py, maxt; BrwFastKernel fn, fn_screen; };
 // MAXT = launch bound: CTAs of <= 384 threads (e.g. the 128^3 single chain, 352 threads) may use up to
@@ -374,8 +375,17 @@ struct BrwFastEntry { int lat, nsh, px, py, maxt; BrwFastKernel fn, fn_screen; }
 #define BRW_FAST(LAT, NSH, PX, PY, MAXT) {LAT, NSH, PX, PY, MAXT, brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, false, MAXT>, \
                                           brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, true, MAXT>}
 static const BrwFastEntry brw_fast_table[] = {
-    BRW_FAST(1, 4, 32, 32, 384), BRW_FAST(1, 4, 32, 32, 768), BRW_FAST(1, 6, 32, 32, 384), BRW_FAST(1, 6, 32, 32, 768),
-    BRW_FAST(2, 4, 32, 64, 384), BRW_FAST(2, 4, 32, 64, 768), BRW_FAST(2, 6, 32, 64, 384), BRW_FAST(2, 6, 32, 64, 768),
+    BRW_FAST(1, 4, 32, 32, 512), BRW_FAST(1, 4, 32, 32, 768), BRW_FAST(1, 6, 32, 32, 512), BRW_FAST(1, 6, 32, 32, 768),
+    BRW_FAST(2, 4, 32, 64, 512), BRW_FAST(2, 4, 32, 64, 768), BRW_FAST(2, 6, 32, 64, 512), BRW_FAST(2, 6, 32, 64, 768),
+};
+
+// Word-lattice kernels (word_metropolis.cuh): fixed box and period orientation per entry; the row pitch
+// PXP = 32 + A0 and plane pitch PLP make the 32 lanes of a warp hit 32 different banks.
+struct BrwWordEntry { int lat, nsh, bxc, byc, bzc, P[3], A[3], pxp, plp, nlimb, maxt; BrwFastKernel fn; };
+static const BrwWordEntry brw_word_table[] = {
+    // bcc, 4 shells, box 64x64x32 (doubled-grid units), P = (6,6,4): A = (9,9,6), 486 trials per step
+    {1, 4, 32, 32, 32, {6, 6, 4}, {9, 9, 6}, 41, 1317, 4, 512,
+     brw_box_metropolis_word_kernel<1, 4, 32, 32, 41, 1317, 4, 512, 6, 6, 4, 9, 9, 6>},
 };
 
 // launch helper for the warp-per-walker kernels: layout + opt-in shared memory
@@ -415,65 +425,155 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       first.push_back({e[0], e[1], e[2]});
     }
   }
-  std::vector<int4> classes, disp;
-  int P = 0;
-  bool feasible = g.lattice != 0 &&   // simple cubic wraps neighbours with modulus n (reference quirk): chain kernel only
-                  brw_choose_period(g, nbr_swap, first, 16, P, classes, disp);
+  // candidate period sets (smallest volume first); the box is sized with the first one, then every
+  // candidate is scored for that box
+  std::vector<std::vector<BrwModeChoice>> cands;
+  if (g.lattice != 0)   // simple cubic wraps neighbours with modulus n (reference quirk): chain kernel only
+    brw_candidate_modes(g, nbr_swap, first, 16, h->cubic_period_only != 0, 6, cands);
+  bool feasible = !cands.empty();
+  std::vector<BrwModeChoice> modes;
+  if (feasible) modes = cands[0];
+  int Pmax = 0;                       // largest period entry over the candidates: minimum box extent
+  for (auto &cs : cands) for (auto &mc : cs) for (int d = 0; d < 3; d++) Pmax = std::max(Pmax, mc.P[d]);
+  const int P = Pmax;
   int B[3] = {g.gx, g.gy, g.gz};
   if (feasible) {
     for (int d = 0; d < 3; d++) if (B[d] < 2 * m + P) feasible = false;
   }
-  if (feasible) {
-    // box extents: user override or automatic halving of the longest edge
-    const size_t budget = 200 * 1024;
-    size_t fixed = (size_t)g.S * g.S * g.n_shells * 16 * 8 + 2 * g.ztot * 4 + 2 * sizeof(BrwStepParams) + 32 * 8 + 64;
-    auto sites = [&](const int *b) { return (size_t)b[0] * b[1] * b[2] / (g.lattice == 1 ? 4 : 2); };
-    auto trials = [&](const int *b) { long M = 1; for (int d = 0; d < 3; d++) M *= (b[d] - 2 * m) / P; return M; };
+  // box extents: user override or automatic halving of the longest edge, for a given shared-memory
+  // footprint per site.  Returns 0 ok, 1 infeasible, 2 error (message set).
+  const size_t budget = 200 * 1024;
+  auto size_box = [&](double bytes_per_site, size_t fixed, int minP, const int *P0, int *Bo) -> int {
+    for (int d = 0; d < 3; d++) Bo[d] = d == 0 ? g.gx : d == 1 ? g.gy : g.gz;
+    auto bytes = [&](const int *b) { return (size_t)((double)b[0] * b[1] * b[2] / (g.lattice == 1 ? 4 : 2) * bytes_per_site); };
+    auto trials = [&](const int *b) { long M = 1; for (int d = 0; d < 3; d++) M *= (b[d] - 2 * m) / P0[d]; return M; };
     if (h->tune_box[0] > 0) {
       for (int d = 0; d < 3; d++) {
         int G = d == 0 ? g.gx : d == 1 ? g.gy : g.gz;
-        B[d] = h->tune_box[d];
-        if (B[d] < 2 * m + P || (B[d] & 1) || G % B[d]) { delete pl; return brw_fail("box extent %d invalid for axis %d (grid %d, need even divisor >= %d)", B[d], d, G, 2 * m + P); }
-      }
-      if (sites(B) + fixed > budget) { delete pl; return brw_fail("box does not fit in shared memory"); }
-    } else {
-      for (;;) {
-        long nbox = (long)(g.gx / B[0]) * (g.gy / B[1]) * (g.gz / B[2]) * h->n_replicas;
-        bool too_big = sites(B) + fixed > budget;
-        bool want_more = nbox < 120 && trials(B) >= 512;
-        if (!too_big && !want_more) break;
-        // halve the longest edge that can still be halved
-        int best = -1;
-        for (int d = 0; d < 3; d++) {
-          int nbd = B[d] / 2;
-          if ((B[d] % 4) == 0 && nbd >= 2 * m + P && (best < 0 || B[d] >= B[best])) best = d;   // ties: z, then y, then x
+        Bo[d] = h->tune_box[d];
+        if (Bo[d] < 2 * m + minP || (Bo[d] & 1) || G % Bo[d]) {
+          brw_fail("box extent %d invalid for axis %d (grid %d, need even divisor >= %d)", Bo[d], d, G, 2 * m + minP);
+          return 2;
         }
-        if (best < 0) { if (too_big) feasible = false; break; }
-        B[best] /= 2;
       }
+      if (bytes(Bo) + fixed > budget) { brw_fail("box does not fit in shared memory"); return 2; }
+      return 0;
+    }
+    for (;;) {
+      long nbox = (long)(g.gx / Bo[0]) * (g.gy / Bo[1]) * (g.gz / Bo[2]) * h->n_replicas;
+      bool too_big = bytes(Bo) + fixed > budget;
+      bool want_more = nbox < 120 && trials(Bo) >= 512;
+      if (!too_big && !want_more) return 0;
+      // halve the longest edge that can still be halved
+      // (a box that has a specialised kernel is not halved out of it just to get more CTAs)
+      auto has_fast = [&](const int *b) {
+        for (const BrwFastEntry &fe : brw_fast_table)
+          if (fe.lat == g.lattice && fe.nsh == g.n_shells && fe.px == (b[0] >> g.xs) && fe.py == (b[1] >> g.ys)) return true;
+        return false;
+      };
+      int best = -1;
+      for (int d = 0; d < 3; d++) {
+        int nbd = Bo[d] / 2;
+        if ((Bo[d] % 4) != 0 || nbd < 2 * m + minP) continue;
+        if (!too_big && has_fast(Bo)) {
+          int Bh[3] = {Bo[0], Bo[1], Bo[2]};
+          Bh[d] = nbd;
+          if (!has_fast(Bh)) continue;
+        }
+        if (best < 0 || Bo[d] >= Bo[best]) best = d;   // ties: z, then y, then x
+      }
+      if (best < 0) return too_big ? 1 : 0;
+      Bo[best] /= 2;
+    }
+  };
+  // word-lattice decomposition: if the box sized for 4-byte sites is one a word kernel is instantiated for,
+  // its (single) period orientation is the plan -- for every dE_mode, so that modes 0/1/2 share one
+  // decomposition and produce identical trajectories
+  const BrwWordEntry *we = nullptr;
+  if (feasible && !nbr_swap && !h->cubic_period_only && g.S <= 5) {
+    for (const BrwWordEntry &e : brw_word_table) {
+      if (we || e.lat != g.lattice || e.nsh != g.n_shells) continue;
+      int Bw[3];
+      const size_t fixed_w = 32 * 1024;
+      const int st = size_box(4.0 * e.plp / (double)(e.bxc * e.byc), fixed_w, std::max(e.P[0], std::max(e.P[1], e.P[2])), e.P, Bw);
+      if (st != 0) continue;       // (an invalid user box is reported by the byte-lattice sizing below)
+      if ((Bw[0] >> g.xs) != e.bxc || (Bw[1] >> g.ys) != e.byc || Bw[2] != e.bzc) continue;
+      BrwModeChoice mc;
+      mc.P[0] = e.P[0]; mc.P[1] = e.P[1]; mc.P[2] = e.P[2];
+      if (!brw_period_admissible(g, nbr_swap, first, mc.P, mc.classes, mc.disp)) continue;
+      bool same_cells = true;
+      for (int d = 0; d < 3; d++) if ((Bw[d] - 2 * m) / e.P[d] != e.A[d]) same_cells = false;
+      if (!same_cells) continue;
+      we = &e;
+      for (int d = 0; d < 3; d++) B[d] = Bw[d];
+      cands.clear();
+      cands.push_back(std::vector<BrwModeChoice>{mc});
+      modes = cands[0];
     }
   }
+  if (feasible && !we) {
+    size_t fixed = (size_t)g.S * g.S * g.n_shells * 16 * 8 + 2 * g.ztot * 4 + 2 * sizeof(BrwStepParams) + 32 * 8 + 64;
+    const int st = size_box(1.0, fixed, P, modes[0].P, B);
+    if (st == 2) { delete pl; return 1; }
+    if (st == 1) feasible = false;
+  }
   if (feasible) {
-    p.P = P; p.m = m;
+    p.m = m;
     {
       double vmax = 0.0;
       for (int i = 0; i < g.S * g.S * g.n_shells; i++) vmax = std::max(vmax, std::fabs(h->hV[i]));
       p.guard = 1e-9 * g.ztot * vmax;
     }
-    p.M = 1;
     for (int d = 0; d < 3; d++) {
       int G = d == 0 ? g.gx : d == 1 ? g.gy : g.gz;
-      p.B[d] = B[d]; p.nb[d] = G / B[d]; p.A[d] = (B[d] - 2 * m) / P; p.M *= p.A[d];
+      p.B[d] = B[d]; p.nb[d] = G / B[d];
     }
     p.bxc = B[0] >> g.xs; p.byc = B[1] >> g.ys; p.bzc = B[2];
     p.box_sites = p.bxc * p.byc * p.bzc;
-    p.n_classes = (int)classes.size(); p.n_disp = (int)disp.size();
+    // is a specialised kernel instantiated for this lattice / shell count / box pitch?  Its CTAs hold at
+    // most 768 threads, one trial each.
+    bool has_fast = false;
+    if (!nbr_swap && !h->disable_fast)
+      for (const BrwFastEntry &fe : brw_fast_table)
+        if (fe.lat == g.lattice && fe.nsh == g.n_shells && fe.px == p.bxc && fe.py == p.byc) has_fast = true;
+    const int cap = has_fast ? 768 : 1 << 30;
+    // score every candidate for this box: simultaneous trials per step, limited by the CTA size
+    long best_score = -1;
+    for (auto &cs : cands) {
+      long worst = 1L << 40;
+      for (auto &mc : cs) {
+        long M = 1;
+        for (int d = 0; d < 3; d++) M *= (B[d] - 2 * m) / mc.P[d];
+        worst = std::min(worst, std::min<long>(M, cap));
+      }
+      if (worst > best_score) { best_score = worst; modes = cs; }
+    }
+    p.n_modes = (int)modes.size();
+    std::vector<int4> classes, disp;
+    int Mmax = 0, Mmin = 1 << 30;
+    for (int q = 0; q < p.n_modes; q++) {
+      BrwBoxMode &md = p.mode[q];
+      for (int d = 0; d < 3; d++) { md.P[d] = modes[q].P[d]; md.A[d] = (B[d] - 2 * m) / md.P[d]; }
+      // shrink the active region along its longest axis until the trials of one step fit the CTA
+      while ((long)md.A[0] * md.A[1] * md.A[2] > cap) {
+        int big = 0;
+        for (int d = 1; d < 3; d++) if (md.A[d] > md.A[big]) big = d;
+        md.A[big]--;
+      }
+      md.M = md.A[0] * md.A[1] * md.A[2];
+      md.cls0 = (int)classes.size(); md.n_classes = (int)modes[q].classes.size();
+      md.d0 = (int)disp.size(); md.n_disp = (int)modes[q].disp.size();
+      classes.insert(classes.end(), modes[q].classes.begin(), modes[q].classes.end());
+      disp.insert(disp.end(), modes[q].disp.begin(), modes[q].disp.end());
+      Mmax = std::max(Mmax, md.M); Mmin = std::min(Mmin, md.M);
+    }
+    pl->Mmax = Mmax;
     p.boxes_per_replica = p.nb[0] * p.nb[1] * p.nb[2];
     p.v_entries = g.S * g.S * g.n_shells;
     // default: about four sweeps of the box per phase (amortises the box load/store)
-    int steps = h->tune_steps > 0 ? h->tune_steps : (4 * p.box_sites + p.M - 1) / p.M;
+    int steps = h->tune_steps > 0 ? h->tune_steps : (4 * p.box_sites + Mmax - 1) / Mmax;
     p.steps = std::max(8, std::min(steps, 512));
-    pl->threads = std::min(1024, ((p.M + 31) / 32) * 32);
+    pl->threads = std::min(1024, ((Mmax + 31) / 32) * 32);
     pl->smem = (size_t)p.v_entries * 16 * 8 + (size_t)2 * g.ztot * 4 + 2 * sizeof(BrwStepParams) + 32 * 8 + p.box_sites;
     // offset tables per x-parity of the centre site
     std::vector<int> off(2 * g.ztot);
@@ -499,18 +599,72 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
     BRW_PLAN_CUDA(cudaMemcpy(pl->d_Vrep, vrep.data(), vrep.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (nbr_swap) BRW_PLAN_CUDA(cudaFuncSetAttribute(brw_box_metropolis_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     else BRW_PLAN_CUDA(cudaFuncSetAttribute(brw_box_metropolis_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
-    if (!nbr_swap && !h->disable_fast && p.M <= 768)
+    if (!nbr_swap && !h->disable_fast && Mmax <= 768)
       for (const BrwFastEntry &fe : brw_fast_table)
         if (!pl->fast_fn && fe.lat == g.lattice && fe.nsh == g.n_shells && fe.px == p.bxc && fe.py == p.byc &&
-            ((p.M + 31) / 32) * 32 <= fe.maxt) {
+            ((Mmax + 31) / 32) * 32 <= fe.maxt) {
           // screening needs <= 5 species (four 8-bit count fields + one inferred) and is a per-handle option
-          const bool screen = h->dE_mode == 1 && g.S <= 5;
+          const bool screen = h->dE_mode >= 1 && g.S <= 5;
           pl->fast_fn = (void *)(screen ? fe.fn_screen : fe.fn);
           pl->screened = screen;
           pl->fast_smem = (size_t)p.v_entries * 16 * 8 + 32 * 8 + (size_t)p.steps * sizeof(BrwStepParams) + p.box_sites;
-          pl->threads = std::min(768, ((p.M + 31) / 32) * 32);
+          pl->threads = std::min(768, ((Mmax + 31) / 32) * 32);
           BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)pl->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
         }
+    if (we && h->dE_mode == 2 && !h->disable_fast) {
+      // word-lattice kernel: replace the lane-replicated V by its table blob (layout: word_metropolis.cuh)
+      const int NL = we->nlimb, NSH = g.n_shells, S = g.S, ROWP = NSH * NL + 4;
+      auto species_of = [](int code) { return code == 4 ? 4 : 3 - code; };
+      auto Vn = [&](int n, int centre, int nbr) { return h->hV[(n * S + nbr) * S + centre]; };
+      auto U = [&](int sa, int sb, int n, int s) {
+        double u = Vn(n, sb, s) - Vn(n, sa, s);
+        if (S == 5) u -= Vn(n, sb, 4) - Vn(n, sa, 4);
+        return u;
+      };
+      double umax = 0.0;
+      for (int sa = 0; sa < S; sa++) for (int sb = 0; sb < S; sb++) for (int n = 0; n < NSH; n++)
+        for (int s2 = 0; s2 < std::min(S, 4); s2++) umax = std::max(umax, std::fabs(U(sa, sb, n, s2)));
+      int kexp = 0;
+      if (umax > 0.0) kexp = (int)std::floor(std::log2(std::ldexp(1.0, 8 * NL - 2) / umax));
+      p.fix_scale = std::ldexp(1.0, -kexp);
+      // |fixed-point dE - real dE| <= sum_f |d_f| * 2^-k / 2 <= ztot * 2^-k; the second term covers the f64
+      // rounding difference to the reference association as before
+      p.guard = g.ztot * p.fix_scale + 1e-9 * g.ztot * umax;
+      const int tab_words = (25 * ROWP + 2 * g.ztot + 1) & ~1;
+      std::vector<int> blob(tab_words + 2 * p.v_entries, 0);
+      for (int ca = 0; ca < 5; ca++) for (int cb = 0; cb < 5; cb++) {
+        const int sa = species_of(ca), sb = species_of(cb);
+        if (sa >= S || sb >= S || sa == sb) continue;
+        int *row = blob.data() + (ca * 5 + cb) * ROWP;
+        long long K = 0;
+        for (int n = 0; n < NSH; n++)
+          for (int s2 = 0; s2 < std::min(S, 4); s2++) {
+            long long v = std::llrint(std::ldexp(U(sa, sb, n, s2), kexp));
+            K += 128 * v;
+            for (int k = 0; k < NL; k++) {
+              long long dgt = k == NL - 1 ? v : ((v + 128) & 255) - 128;
+              v = (v - dgt) >> 8;
+              row[n * NL + k] |= (int)((uint32_t)(uint8_t)(int8_t)dgt << (8 * s2));
+            }
+          }
+        std::memcpy(row + NSH * NL, &K, 8);
+      }
+      for (int par = 0; par < 2; par++)
+        for (int k = 0; k < g.ztot; k++) {
+          int dx = g.off[k][0], dy = g.off[k][1], dz = g.off[k][2];
+          int dxc = (par + dx) >> 1, dyc = g.ys ? ((par + dy) >> 1) : dy;
+          blob[25 * ROWP + par * g.ztot + k] = dz * we->plp + dyc * we->pxp + dxc;
+        }
+      std::memcpy(blob.data() + tab_words, h->hV, sizeof(double) * p.v_entries);
+      cudaFree(pl->d_Vrep); pl->d_Vrep = nullptr;
+      BRW_PLAN_CUDA(cudaMalloc(&pl->d_Vrep, blob.size() * sizeof(int)));
+      BRW_PLAN_CUDA(cudaMemcpy(pl->d_Vrep, blob.data(), blob.size() * sizeof(int), cudaMemcpyHostToDevice));
+      pl->fast_fn = (void *)we->fn;
+      pl->screened = true; pl->word = true;
+      pl->fast_smem = blob.size() * sizeof(int) + 32 * 8 + 16 + (size_t)p.steps * sizeof(BrwStepParams) + (size_t)we->plp * p.bzc * 4;
+      pl->threads = std::min(we->maxt, ((Mmax + 31) / 32) * 32);
+      BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)pl->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
+    }
     pl->use_box = true;
     pl->n_slots = p.boxes_per_replica * h->n_replicas;
   } else {
@@ -536,13 +690,15 @@ extern "C" int brawl_cuda_metropolis_tune(brawl_cuda_t *h, int bx, int by, int b
   // cross-check the specialised kernels
   h->disable_fast = steps < 0;
   if (steps < 0) steps = -steps - 1;
+  h->cubic_period_only = steps >= 100000;      // test hook: steps + 100000 restricts the planner to cubic periods
+  if (steps >= 100000) steps -= 100000;
   h->tune_box[0] = bx; h->tune_box[1] = by; h->tune_box[2] = bz; h->tune_steps = steps;
   for (int i = 0; i < 2; i++) { brw_free_plan((BrwPlan *)h->mc_plan[i]); h->mc_plan[i] = nullptr; }
   return 0;
 }
 extern "C" int brawl_cuda_metropolis_set_mode(brawl_cuda_t *h, int dE_mode) {
   BRW_ENTER(h);
-  if (dE_mode != 0 && dE_mode != 1) return brw_fail("dE_mode must be 0 (reference association for every trial) or 1 (screened)");
+  if (dE_mode < 0 || dE_mode > 2) return brw_fail("dE_mode must be 0 (reference association for every trial), 1 (screened, byte lattice) or 2 (screened, word lattice)");
   BRW_CUDA(cudaStreamSynchronize(h->stream));
   h->dE_mode = dE_mode;
   for (int i = 0; i < 2; i++) { brw_free_plan((BrwPlan *)h->mc_plan[i]); h->mc_plan[i] = nullptr; }
@@ -553,9 +709,11 @@ extern "C" int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *o)
   BrwPlan *pl;
   if (brw_build_plan(h, nbr_swap, &pl)) return 1;
   if (o) {
-    o[0] = pl->use_box; o[1] = pl->p.P; o[2] = pl->p.m; o[3] = pl->p.B[0]; o[4] = pl->p.B[1]; o[5] = pl->p.B[2];
-    o[6] = pl->p.M; o[7] = pl->p.boxes_per_replica; o[8] = pl->p.n_disp; o[9] = pl->p.steps;
-    if (pl->fast_fn) o[0] = pl->screened ? 3 : 2;
+    const BrwBoxMode &m0 = pl->p.mode[0];
+    o[0] = pl->use_box; o[1] = m0.P[0] * 10000 + m0.P[1] * 100 + m0.P[2]; o[2] = pl->p.m; o[3] = pl->p.B[0]; o[4] = pl->p.B[1];
+    o[5] = pl->p.B[2]; o[6] = pl->Mmax; o[7] = pl->p.boxes_per_replica; o[8] = m0.n_disp; o[9] = pl->p.steps;
+    if (pl->fast_fn) o[0] = pl->word ? 4 : pl->screened ? 3 : 2;
+    o[0] += 16 * pl->p.n_modes;                 // number of period orientations in bits 4..
   }
   return 0;
 }
@@ -575,27 +733,30 @@ extern "C" int brawl_cuda_metropolis_enqueue(brawl_cuda_t *h, const double *beta
   int64_t done = 0;
   if (pl->use_box) {
     const BrwBoxParams &p = pl->p;
-    const int64_t per_phase = (int64_t)p.M * p.steps * p.boxes_per_replica;
-    int64_t phases = (n_trials + per_phase - 1) / per_phase;
-    for (int64_t ph = 0; ph < phases; ph++) {
-      uint64_t phase = offset + (uint64_t)ph;
+    // each phase uses one orientation of the period (uniform, from the phase counter); loop until at least
+    // n_trials attempts per replica are planned
+    int64_t phases = 0;
+    while (done < n_trials) {
+      uint64_t phase = offset + (uint64_t)phases;
       uint32_t kk1 = k1 ^ (uint32_t)(phase >> 32) * 0x9E3779B9u;
+      const int mode = (int)brw_below(brw_philox(0xFFFFFFFDu, 0u, 0u, (uint32_t)phase, k0, kk1).x, (uint32_t)p.n_modes);
       if (pl->fast_fn)
         ((BrwFastKernel)pl->fast_fn)<<<pl->n_slots, pl->threads, pl->fast_smem, h->stream>>>(
-            h->g, p, h->d_lat, h->d_beta, pl->d_Vrep, pl->d_classes, pl->d_disp, k0, kk1, (uint32_t)phase, pl->d_att,
+            h->g, p, h->d_lat, h->d_beta, pl->d_Vrep, pl->d_classes, pl->d_disp, k0, kk1, (uint32_t)phase, mode, pl->d_att,
             pl->d_acc, pl->d_dE);
       else if (nbr_swap)
         brw_box_metropolis_kernel<1><<<pl->n_slots, pl->threads, pl->smem, h->stream>>>(
-            h->g, p, h->d_lat, h->d_beta, pl->d_Vrep, pl->d_off, pl->d_classes, pl->d_disp, k0, kk1, (uint32_t)phase,
+            h->g, p, h->d_lat, h->d_beta, pl->d_Vrep, pl->d_off, pl->d_classes, pl->d_disp, k0, kk1, (uint32_t)phase, mode,
             pl->d_att, pl->d_acc, pl->d_dE);
       else
         brw_box_metropolis_kernel<0><<<pl->n_slots, pl->threads, pl->smem, h->stream>>>(
-            h->g, p, h->d_lat, h->d_beta, pl->d_Vrep, pl->d_off, pl->d_classes, pl->d_disp, k0, kk1, (uint32_t)phase,
+            h->g, p, h->d_lat, h->d_beta, pl->d_Vrep, pl->d_off, pl->d_classes, pl->d_disp, k0, kk1, (uint32_t)phase, mode,
             pl->d_att, pl->d_acc, pl->d_dE);
       BRW_LAUNCH_CHECK("brw_box_metropolis_kernel");
       launches++;
+      phases++;
+      done += (int64_t)p.mode[mode].M * p.steps * p.boxes_per_replica;
     }
-    done = phases * per_phase;
     if (next_offset) *next_offset = offset + (uint64_t)phases;
   } else {
     if (n_trials > 0) {
@@ -614,6 +775,13 @@ extern "C" int brawl_cuda_metropolis_enqueue(brawl_cuda_t *h, const double *beta
   if (planned) *planned = done;
   if (n_launches) *n_launches = launches;
   h->last_plan = nbr_swap ? 1 : 0;
+  h->last_launches = launches;
+  return 0;
+}
+
+extern "C" int brawl_cuda_metropolis_last_launches(brawl_cuda_t *h, int *n) {
+  if (!h || !n) return brw_fail("null argument");
+  *n = h->last_launches;
   return 0;
 }
 

@@ -23,12 +23,21 @@
 #include <algorithm>
 #include "brawl_common.cuh"
 
+#define BRW_MAX_MODES 3
+struct BrwBoxMode {            // one orientation of the (rectangular) period, see brw_choose_modes
+  int P[3];                    // period per axis (doubled-grid units, even)
+  int A[3], M;                 // coarse cells per axis inside the active region, M = A0*A1*A2 trials per step
+  int cls0, n_classes;         // slice of the residue-class table
+  int d0, n_disp;              // slice of the displacement-class table
+};
 struct BrwBoxParams {          // POD kernel parameter
   double guard;                // screening guard band on dE (Ry); see brw_box_metropolis_fast_kernel
-  int P, m;
-  int B[3], nb[3], A[3], M;
+  double fix_scale;            // word kernel: 2^-k, the unit of its fixed-point dE (word_metropolis.cuh)
+  int m;
+  int B[3], nb[3];
   int bxc, byc, bzc, box_sites;
-  int n_classes, n_disp;
+  int n_modes;
+  BrwBoxMode mode[BRW_MAX_MODES];
   int boxes_per_replica;
   int steps;
   int v_entries;               // S*S*n_shells
@@ -43,9 +52,10 @@ struct BrwPlan {
   int *d_off = nullptr;        // [2][ztot] compact shared-memory offsets, by x-parity of the site
   double *d_Vrep = nullptr;    // [v_entries][16] lane-replicated V (layout [shell][centre][nbr])
   size_t smem = 0;
-  int threads = 0;
+  int threads = 0, Mmax = 0;
   void *fast_fn = nullptr;     // specialised kernel for this (lattice, shells, pitch), if instantiated
   bool screened = false;
+  bool word = false;           // fast_fn is a word-lattice kernel (word_metropolis.cuh); d_Vrep holds its table blob
   size_t fast_smem = 0;
   // per-box counters
   unsigned long long *d_att = nullptr, *d_acc = nullptr;
@@ -56,74 +66,93 @@ struct BrwPlan {
 // ---- host planner -----------------------------------------------------------------------------
 static inline int brw_posmod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 
-// Find the smallest even period P for which (a) no neighbour vector is = 0 mod P and (b) the set
-// D of displacement classes d with no neighbour vector = +-d (mod P) connects all residue
-// classes.  In nbr_swap mode the second site is site1 + e (e in `first`), and the requirement is
-// that no neighbour vector equals P*k, P*k +- e for k != 0.
-static bool brw_choose_period(const BrwGeom &g, int nbr_swap, const std::vector<std::array<int, 3>> &first,
-                              int Pmax, int &P_out, std::vector<int4> &classes, std::vector<int4> &disp) {
-  for (int P = 2; P <= Pmax; P += 2) {
-    bool ok = true;
-    for (int k = 0; k < g.ztot && ok; k++)
-      if (brw_posmod(g.off[k][0], P) == 0 && brw_posmod(g.off[k][1], P) == 0 && brw_posmod(g.off[k][2], P) == 0) ok = false;
-    if (!ok) continue;
-    classes.clear();
-    for (int z = 0; z < P; z++) for (int y = 0; y < P; y++) for (int x = 0; x < P; x++)
-      if (brw_is_site(g, x, y, z)) classes.push_back(make_int4(x, y, z, 0));
-    disp.clear();
-    if (nbr_swap) {
-      // concurrent pairs (i, i+e) and (i', i'+e), i'-i = P*k != 0: differences P*k, P*k+-e
-      for (auto &e : first) {
-        bool good = true;
-        for (int k = 0; k < g.ztot && good; k++)
-          for (int sgn = -1; sgn <= 1 && good; sgn++) {
-            int vx = g.off[k][0] - sgn * e[0], vy = g.off[k][1] - sgn * e[1], vz = g.off[k][2] - sgn * e[2];
-            if (vx == 0 && vy == 0 && vz == 0) continue;              // k = 0: the pair itself
-            if (brw_posmod(vx, P) == 0 && brw_posmod(vy, P) == 0 && brw_posmod(vz, P) == 0) good = false;
-          }
-        // +-e itself must not be = 0 mod P
-        if (brw_posmod(e[0], P) == 0 && brw_posmod(e[1], P) == 0 && brw_posmod(e[2], P) == 0) good = false;
-        if (!good) { ok = false; break; }
-        disp.push_back(make_int4(e[0], e[1], e[2], 0));
-      }
-      if (!ok) continue;
-      P_out = P;
-      return true;
-    }
-    for (auto &c : classes) {
-      if (c.x == 0 && c.y == 0 && c.z == 0) continue;
-      bool good = true;
-      for (int k = 0; k < g.ztot && good; k++)
-        for (int sgn = -1; sgn <= 1; sgn += 2)
-          if (brw_posmod(g.off[k][0] - sgn * c.x, P) == 0 && brw_posmod(g.off[k][1] - sgn * c.y, P) == 0 &&
-              brw_posmod(g.off[k][2] - sgn * c.z, P) == 0) { good = false; break; }
-      if (good) disp.push_back(c);
-    }
-    if (disp.empty()) continue;
-    // connectivity of the class graph under D (composition must be able to flow everywhere)
-    std::vector<char> seen(P * P * P, 0);
-    std::vector<int> stack{0};
-    seen[0] = 1;
-    size_t reached = 0;
-    while (!stack.empty()) {
-      int c = stack.back(); stack.pop_back(); reached++;
-      int cx = c % P, cy = (c / P) % P, cz = c / (P * P);
-      for (auto &d : disp)
-        for (int sgn = -1; sgn <= 1; sgn += 2) {
-          int nx = brw_posmod(cx + sgn * d.x, P), ny = brw_posmod(cy + sgn * d.y, P), nz = brw_posmod(cz + sgn * d.z, P);
-          int n = (nz * P + ny) * P + nx;
-          if (!seen[n]) { seen[n] = 1; stack.push_back(n); }
+// Period search.  For a period vector P = (Px,Py,Pz) (even entries) the residue classes are the
+// lattice sites of the P box.  P is admissible if (a) no neighbour vector is = 0 (mod P) and (b) the set
+// D of displacement classes d with no neighbour vector = +-d (mod P) is non-empty and connects all
+// residue classes (so composition can flow between all sublattices).  Then the sites
+// o + P*(i,j,k) and o + d + P*(i',j',k') are pairwise non-interacting.  In nbr_swap mode the second
+// site is site1 + e (e a first-shell vector) and the requirement is that no neighbour vector equals
+// P*k, P*k +- e for k != 0.
+static bool brw_period_admissible(const BrwGeom &g, int nbr_swap, const std::vector<std::array<int, 3>> &first,
+                                  const int P[3], std::vector<int4> &classes, std::vector<int4> &disp) {
+  auto zero_mod = [&](int x, int y, int z) { return brw_posmod(x, P[0]) == 0 && brw_posmod(y, P[1]) == 0 && brw_posmod(z, P[2]) == 0; };
+  for (int k = 0; k < g.ztot; k++)
+    if (zero_mod(g.off[k][0], g.off[k][1], g.off[k][2])) return false;
+  classes.clear();
+  for (int z = 0; z < P[2]; z++) for (int y = 0; y < P[1]; y++) for (int x = 0; x < P[0]; x++)
+    if (brw_is_site(g, x, y, z)) classes.push_back(make_int4(x, y, z, 0));
+  disp.clear();
+  if (nbr_swap) {
+    // concurrent pairs (i, i+e) and (i', i'+e), i'-i = P*k != 0: differences P*k, P*k+-e
+    for (auto &e : first) {
+      if (zero_mod(e[0], e[1], e[2])) return false;
+      for (int k = 0; k < g.ztot; k++)
+        for (int sgn = -1; sgn <= 1; sgn++) {
+          int vx = g.off[k][0] - sgn * e[0], vy = g.off[k][1] - sgn * e[1], vz = g.off[k][2] - sgn * e[2];
+          if (vx == 0 && vy == 0 && vz == 0) continue;              // k = 0: the pair itself
+          if (zero_mod(vx, vy, vz)) return false;
         }
+      disp.push_back(make_int4(e[0], e[1], e[2], 0));
     }
-    if (reached != classes.size()) continue;
-    P_out = P;
     return true;
   }
-  return false;
+  for (auto &c : classes) {
+    if (c.x == 0 && c.y == 0 && c.z == 0) continue;
+    bool good = true;
+    for (int k = 0; k < g.ztot && good; k++)
+      for (int sgn = -1; sgn <= 1; sgn += 2)
+        if (zero_mod(g.off[k][0] - sgn * c.x, g.off[k][1] - sgn * c.y, g.off[k][2] - sgn * c.z)) { good = false; break; }
+    if (good) disp.push_back(c);
+  }
+  if (disp.empty()) return false;
+  // connectivity of the class graph under D
+  std::vector<char> seen((size_t)P[0] * P[1] * P[2], 0);
+  std::vector<int> stack{0};
+  seen[0] = 1;
+  size_t reached = 0;
+  while (!stack.empty()) {
+    int c = stack.back(); stack.pop_back(); reached++;
+    int cx = c % P[0], cy = (c / P[0]) % P[1], cz = c / (P[0] * P[1]);
+    for (auto &d : disp)
+      for (int sgn = -1; sgn <= 1; sgn += 2) {
+        int nx = brw_posmod(cx + sgn * d.x, P[0]), ny = brw_posmod(cy + sgn * d.y, P[1]), nz = brw_posmod(cz + sgn * d.z, P[2]);
+        int n = (nz * P[1] + ny) * P[0] + nx;
+        if (!seen[n]) { seen[n] = 1; stack.push_back(n); }
+      }
+  }
+  return reached == classes.size();
+}
+
+struct BrwModeChoice { int P[3]; std::vector<int4> classes, disp; };
+// Admissible periods in order of increasing volume: for each sorted triple every admissible orientation
+// (up to BRW_MAX_MODES; phases cycle randomly through them so the move set stays isotropic).  Returns
+// up to `max_sets` candidate sets; the caller scores them for the actual box.
+static void brw_candidate_modes(const BrwGeom &g, int nbr_swap, const std::vector<std::array<int, 3>> &first, int Pmax,
+                                bool cubic_only, int max_sets, std::vector<std::vector<BrwModeChoice>> &sets) {
+  std::vector<std::array<int, 3>> triples;
+  for (int a = 2; a <= Pmax; a += 2) for (int b = a; b <= Pmax; b += 2) for (int c = b; c <= Pmax; c += 2)
+    if (!cubic_only || (a == b && b == c)) triples.push_back({a, b, c});
+  std::sort(triples.begin(), triples.end(), [](const std::array<int, 3> &x, const std::array<int, 3> &y) {
+    long vx = (long)x[0] * x[1] * x[2], vy = (long)y[0] * y[1] * y[2];
+    return vx != vy ? vx < vy : x < y;
+  });
+  sets.clear();
+  for (auto &t : triples) {
+    std::array<int, 3> perm = t;
+    std::vector<BrwModeChoice> modes;
+    do {
+      BrwModeChoice mc;
+      mc.P[0] = perm[0]; mc.P[1] = perm[1]; mc.P[2] = perm[2];
+      if ((int)modes.size() < BRW_MAX_MODES && brw_period_admissible(g, nbr_swap, first, mc.P, mc.classes, mc.disp))
+        modes.push_back(std::move(mc));
+    } while (std::next_permutation(perm.begin(), perm.end()));
+    if (!modes.empty()) sets.push_back(std::move(modes));
+    if ((int)sets.size() >= max_sets) break;
+  }
 }
 
 // ---- kernel -------------------------------------------------------------------------------------
-struct BrwStepParams {     // CTA-uniform per step, double-buffered in shared memory
+struct __align__(16) BrwStepParams {     // CTA-uniform per step, in shared memory
   int c1_base, c2_base;    // compact smem index of site1/site2 for (i,j,k) = 0
   int par1, par2;          // offset-table selector of site1 / site2
   int s[3];                // cyclic shift of the coarse index for site2
@@ -140,20 +169,20 @@ __device__ __host__ __forceinline__ int brw_site_parity(const BrwGeom &g, int X,
 }
 
 template <int NBR>
-__device__ __forceinline__ void brw_make_step(const BrwGeom &g, const BrwBoxParams &p, const int4 *classes,
-                                              const int4 *disp, uint32_t k0, uint32_t k1, uint32_t step,
-                                              uint32_t box_id, uint32_t phase_lo, BrwStepParams *out) {
+__device__ __forceinline__ void brw_make_step(const BrwGeom &g, const BrwBoxParams &p, const BrwBoxMode &md,
+                                              const int4 *classes, const int4 *disp, uint32_t k0, uint32_t k1,
+                                              uint32_t step, uint32_t box_id, uint32_t phase_lo, BrwStepParams *out) {
   BrwPhilox4 r = brw_philox(0xFFFFFFFFu, step, box_id, phase_lo, k0, k1);
-  int4 o = classes[brw_below(r.x, p.n_classes)];
-  int4 d = disp[brw_below(r.y, p.n_disp)];
+  int4 o = classes[md.cls0 + brw_below(r.x, md.n_classes)];
+  int4 d = disp[md.d0 + brw_below(r.y, md.n_disp)];
   int X1 = p.m + o.x, Y1 = p.m + o.y, Z1 = p.m + o.z;
   int X2, Y2, Z2;
   if (NBR) { X2 = X1 + d.x; Y2 = Y1 + d.y; Z2 = Z1 + d.z; out->s[0] = out->s[1] = out->s[2] = 0; }
   else {
-    X2 = p.m + (o.x + d.x) % p.P; Y2 = p.m + (o.y + d.y) % p.P; Z2 = p.m + (o.z + d.z) % p.P;
-    out->s[0] = (int)brw_below(r.z, p.A[0]);
-    out->s[1] = (int)(((r.w & 0xFFFFu) * (uint32_t)p.A[1]) >> 16);   // 16-bit draws; A <= 65535
-    out->s[2] = (int)(((r.w >> 16) * (uint32_t)p.A[2]) >> 16);
+    X2 = p.m + (o.x + d.x) % md.P[0]; Y2 = p.m + (o.y + d.y) % md.P[1]; Z2 = p.m + (o.z + d.z) % md.P[2];
+    out->s[0] = (int)brw_below(r.z, md.A[0]);
+    out->s[1] = (int)(((r.w & 0xFFFFu) * (uint32_t)md.A[1]) >> 16);   // 16-bit draws; A <= 65535
+    out->s[2] = (int)(((r.w >> 16) * (uint32_t)md.A[2]) >> 16);
   }
   out->c1_base = brw_box_compact(g, p, X1, Y1, Z1);
   out->c2_base = brw_box_compact(g, p, X2, Y2, Z2);
@@ -194,9 +223,10 @@ template <int NBR>
 __global__ void __launch_bounds__(1024) brw_box_metropolis_kernel(
     BrwGeom g, BrwBoxParams p, uint8_t *__restrict__ lat, const double *__restrict__ beta,
     const double *__restrict__ Vrep, const int *__restrict__ off_g, const int4 *__restrict__ classes,
-    const int4 *__restrict__ disp, uint32_t k0, uint32_t k1, uint32_t phase_lo,
+    const int4 *__restrict__ disp, uint32_t k0, uint32_t k1, uint32_t phase_lo, int mode,
     unsigned long long *__restrict__ att_out, unsigned long long *__restrict__ acc_out, double *__restrict__ dE_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const BrwBoxMode &md = p.mode[mode];
   double *Vs = reinterpret_cast<double *>(smem_raw);                       // [v_entries][16]
   int *off = reinterpret_cast<int *>(Vs + p.v_entries * 16);               // [2][ztot]
   BrwStepParams *sp = reinterpret_cast<BrwStepParams *>(off + 2 * g.ztot); // [2]
@@ -230,13 +260,13 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_kernel(
     box[idx] = L[brw_grid_to_compact(g, gxx, gyy, gzz)];
   }
   const uint32_t box_id = (uint32_t)blockIdx.x;
-  if (tid == 0) brw_make_step<NBR>(g, p, classes, disp, k0, k1, 0u, box_id, phase_lo, &sp[0]);
+  if (tid == 0) brw_make_step<NBR>(g, p, md, classes, disp, k0, k1, 0u, box_id, phase_lo, &sp[0]);
   __syncthreads();
 
   const double my_beta = beta[replica];
   const double *Vl = Vs + (tid & 15);
   // strides of the coarse lattice in compact shared-memory index units
-  const int stx = p.P >> g.xs, sty = (p.P >> g.ys) * p.bxc, stz = p.P * p.byc * p.bxc;
+  const int stx = md.P[0] >> g.xs, sty = (md.P[1] >> g.ys) * p.bxc, stz = md.P[2] * p.byc * p.bxc;
   unsigned int n_att = 0, n_acc = 0;
   double dE_sum = 0.0;
   BrwPhilox4 rnd = {0, 0, 0, 0};
@@ -244,16 +274,16 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_kernel(
   for (int step = 0; step < p.steps; step++) {
     const BrwStepParams q = sp[step & 1];
     const int *off1 = off + q.par1 * g.ztot, *off2 = off + q.par2 * g.ztot;
-    for (int t = tid; t < p.M; t += blockDim.x) {
-      int i = t % p.A[0], r = t / p.A[0], j = r % p.A[1], k = r / p.A[1];
-      int i2 = i + q.s[0]; if (i2 >= p.A[0]) i2 -= p.A[0];
-      int j2 = j + q.s[1]; if (j2 >= p.A[1]) j2 -= p.A[1];
-      int k2 = k + q.s[2]; if (k2 >= p.A[2]) k2 -= p.A[2];
+    for (int t = tid; t < md.M; t += blockDim.x) {
+      int i = t % md.A[0], r = t / md.A[0], j = r % md.A[1], k = r / md.A[1];
+      int i2 = i + q.s[0]; if (i2 >= md.A[0]) i2 -= md.A[0];
+      int j2 = j + q.s[1]; if (j2 >= md.A[1]) j2 -= md.A[1];
+      int k2 = k + q.s[2]; if (k2 >= md.A[2]) k2 -= md.A[2];
       const int c1 = q.c1_base + i * stx + j * sty + k * stz;
       const int c2 = q.c2_base + i2 * stx + j2 * sty + k2 * stz;
       const int a = box[c1], b = box[c2];
       n_att++;
-      if ((step & 3) == 0 || p.M > (int)blockDim.x)
+      if ((step & 3) == 0 || md.M > (int)blockDim.x)
         rnd = brw_philox((uint32_t)t, (uint32_t)step, box_id, phase_lo, k0, k1);
       if (a == b) { n_acc++; continue; }                       // src/metropolis.F90:774-777
       double E1a, E1b, E2b, E2a;
@@ -270,7 +300,7 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_kernel(
       if (accept) { box[c1] = (uint8_t)b; box[c2] = (uint8_t)a; n_acc++; dE_sum += dE; }
     }
     if (tid == 0 && step + 1 < p.steps)
-      brw_make_step<NBR>(g, p, classes, disp, k0, k1, (uint32_t)(step + 1), box_id, phase_lo, &sp[(step + 1) & 1]);
+      brw_make_step<NBR>(g, p, md, classes, disp, k0, k1, (uint32_t)(step + 1), box_id, phase_lo, &sp[(step + 1) & 1]);
     __syncthreads();
   }
 
@@ -420,9 +450,10 @@ template <int LAT, int NSH, int PX, int PY, bool SCREEN, int MAXT>
 __global__ void __launch_bounds__(MAXT) brw_box_metropolis_fast_kernel(
     BrwGeom g, BrwBoxParams p, uint8_t *__restrict__ lat, const double *__restrict__ beta,
     const double *__restrict__ Vrep, const int4 *__restrict__ classes, const int4 *__restrict__ disp, uint32_t k0,
-    uint32_t k1, uint32_t phase_lo, unsigned long long *__restrict__ att_out,
+    uint32_t k1, uint32_t phase_lo, int mode, unsigned long long *__restrict__ att_out,
     unsigned long long *__restrict__ acc_out, double *__restrict__ dE_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const BrwBoxMode &md = p.mode[mode];
   double *Vs = reinterpret_cast<double *>(smem_raw);                       // [v_entries][16]
   double *red = Vs + p.v_entries * 16;                                     // [32]
   BrwStepParams *sp = reinterpret_cast<BrwStepParams *>(red + 32);         // [steps]
@@ -444,7 +475,7 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_fast_kernel(
   for (int i = tid; i < p.v_entries * 16; i += blockDim.x) Vs[i] = Vrep[i];
   // every step's CTA-uniform parameters, computed in parallel up front (one thread per step)
   for (int st = tid; st < p.steps; st += blockDim.x)
-    brw_make_step<0>(g, p, classes, disp, k0, k1, (uint32_t)st, box_id, phase_lo, &sp[st]);
+    brw_make_step<0>(g, p, md, classes, disp, k0, k1, (uint32_t)st, box_id, phase_lo, &sp[st]);
   brw_box_copy<LAT, PX, PY, false>(g, L, box, PY * p.bzc, ox, oy, oz);
   __syncthreads();
 
@@ -452,10 +483,11 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_fast_kernel(
   const char *Vl = reinterpret_cast<const char *>(Vs + (tid & 15));
   const uint32_t box_s = (uint32_t)__cvta_generic_to_shared(box);
   const int S = g.S;
-  const int stx = p.P >> 1, sty = (LAT == 1 ? (p.P >> 1) : p.P) * PX, stz = p.P * PY * PX;
+  const int stx = md.P[0] >> 1, sty = (LAT == 1 ? (md.P[1] >> 1) : md.P[1]) * PX, stz = md.P[2] * PY * PX;
   // this thread's coarse cell (fixed for the whole phase; blockDim >= M is guaranteed by the host)
-  const bool active = tid < p.M;
-  const int ci = tid % p.A[0], cr = tid / p.A[0], cj = cr % p.A[1], ck = cr / p.A[1];
+  const bool active = tid < md.M;
+  const int A0 = md.A[0], A1 = md.A[1], A2 = md.A[2];
+  const int ci = tid % A0, cr = tid / A0, cj = cr % A1, ck = cr / A1;
   const int base1 = ci * stx + cj * sty + ck * stz;
   unsigned int n_att = 0, n_acc = 0;
   double dE_sum = 0.0;
@@ -464,9 +496,9 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_fast_kernel(
   for (int step = 0; step < p.steps; step++) {
     const BrwStepParams q = sp[step];
     if (active) {
-      int i2 = ci + q.s[0]; if (i2 >= p.A[0]) i2 -= p.A[0];
-      int j2 = cj + q.s[1]; if (j2 >= p.A[1]) j2 -= p.A[1];
-      int k2 = ck + q.s[2]; if (k2 >= p.A[2]) k2 -= p.A[2];
+      int i2 = ci + q.s[0]; if (i2 >= A0) i2 -= A0;
+      int j2 = cj + q.s[1]; if (j2 >= A1) j2 -= A1;
+      int k2 = ck + q.s[2]; if (k2 >= A2) k2 -= A2;
       const int c1 = q.c1_base + base1;
       const int c2 = q.c2_base + i2 * stx + j2 * sty + k2 * stz;
       const int a = box[c1], b = box[c2];

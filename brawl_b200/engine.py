@@ -160,8 +160,9 @@ class Device:
         check(self.L.brawl_cuda_metropolis_tune(self.h, box[0], box[1], box[2], steps_per_phase))
 
     def metropolis_set_mode(self, dE_mode):
-        """0: reference f64 association for every trial; 1 (default): integer-count screening with
-        exact recomputation inside the guard band (decision-identical)."""
+        """0: reference f64 association for every trial; 1: integer-count screening on the byte lattice with
+        exact recomputation inside the guard band; 2 (default): the same screening on a word lattice with
+        fixed-point dp4a dE where a word kernel is instantiated (else like 1).  All decision-identical."""
         check(self.L.brawl_cuda_metropolis_set_mode(self.h, int(dE_mode)))
 
     def metropolis_plan(self, nbr_swap=False):
@@ -169,7 +170,16 @@ class Device:
         check(self.L.brawl_cuda_metropolis_plan(self.h, int(nbr_swap), _p(o)))
         keys = ("use_box", "P", "margin", "box_x", "box_y", "box_z", "trials_per_step", "boxes_per_replica",
                 "n_displacements", "steps_per_phase")
-        return dict(zip(keys, (int(v) for v in o)))
+        d = dict(zip(keys, (int(v) for v in o)))
+        d["n_orientations"] = d["use_box"] >> 4
+        d["use_box"] &= 15
+        d["P"] = (d["P"] // 10000, (d["P"] // 100) % 100, d["P"] % 100)
+        return d
+
+    def metropolis_last_launches(self):
+        n = C.c_int()
+        check(self.L.brawl_cuda_metropolis_last_launches(self.h, C.byref(n)))
+        return n.value
 
     # --- SRO --------------------------------------------------------------------------------------
     def radial_counts(self, wc_range, replica=0):

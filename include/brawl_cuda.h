@@ -118,19 +118,28 @@ int brawl_cuda_metropolis_enqueue(brawl_cuda_t *h, const double *beta, int64_t n
                                   int64_t *n_attempt_planned, int *n_kernel_launches);
 int brawl_cuda_metropolis_counters(brawl_cuda_t *h, int reset, int64_t *n_attempt, int64_t *n_accept,
                                    double *dE_sum);
+/* number of kernel launches of the last metropolis_run / metropolis_enqueue on this handle */
+int brawl_cuda_metropolis_last_launches(brawl_cuda_t *h, int *n_launches);
 /* Tuning of the box decomposition (0 = automatic): box extents in doubled-grid units, trial
- * steps per phase.  steps_per_phase = -(s+1) selects s steps AND forces the generic
- * runtime-geometry kernel instead of a specialised instantiation (test hook). */
+ * steps per phase.  Test hooks: steps_per_phase = -(s+1) selects s steps AND forces the generic
+ * runtime-geometry kernel instead of a specialised instantiation; adding 100000 to the (positive)
+ * step count restricts the planner to cubic periods (P,P,P). */
 int brawl_cuda_metropolis_tune(brawl_cuda_t *h, int box_x, int box_y, int box_z, int steps_per_phase);
 /* How the specialised box kernels form dE.  0: the reference's f64 association for every trial.
- * 1 (default): integer neighbour counts give dE first; any trial whose dE or acceptance test lies
- * within a guard band of a decision boundary is recomputed with the reference's association and
- * decided by it, so accept/reject decisions -- and therefore trajectories -- are identical to mode 0
- * (needs <= 5 species; otherwise mode 0 is used). */
+ * 1: integer neighbour counts (byte lattice in shared memory) give dE first; any trial whose dE or
+ * acceptance test lies within a guard band of a decision boundary is recomputed with the reference's
+ * association and decided by it, so accept/reject decisions -- and therefore trajectories -- are identical
+ * to mode 0 (needs <= 5 species; otherwise mode 0 is used).  2 (default): the same screening on a word
+ * lattice (one 32-bit word per site, fixed-point dp4a dE, ex2.approx acceptance pre-test; bcc 4 shells with
+ * 64x64x32 boxes); where no word kernel is instantiated it behaves like mode 1.  Decisions are identical in
+ * all three modes; the returned sum of accepted dE is exact to f64 rounding in modes 0/1 and to the
+ * fixed-point unit (~1e-11 Ry per accepted swap) in mode 2. */
 int brawl_cuda_metropolis_set_mode(brawl_cuda_t *h, int dE_mode);
-/* Describe the decomposition chosen: period P, margin, box extents, active cells, boxes/replica,
- * |D| (number of allowed displacement classes); out10[0] = 0 chain kernel, 1 generic box kernel,
- * 2 specialised (compile-time geometry) box kernel, 3 specialised + screened dE */
+/* Describe the decomposition chosen: out10 = { kind + 16*n_orientations, period Px*10000+Py*100+Pz of the
+ * first orientation, margin, box_x, box_y, box_z, max trials per step, boxes per replica, |D| (allowed
+ * displacement classes of the first orientation), steps per phase }.  kind: 0 chain kernel, 1 generic box
+ * kernel, 2 specialised (compile-time geometry) box kernel, 3 specialised + screened dE, 4 word-lattice
+ * screened kernel. */
 int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *out10);
 
 /* ---- short-range order ----------------------------------------------------------------------

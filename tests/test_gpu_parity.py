@@ -330,6 +330,34 @@ def test_production_conservation_and_energy_bookkeeping(bw, orc, golden):
         assert abs((e1 - e0) - tot_dE) < 1e-10 * abs(e0) + 1e-12, (lattice, n, e0, e1, tot_dE)
 
 
+def test_production_planner_variants(bw, orc, golden):
+    """Three valid decompositions of the same lattice: the word-lattice plan (default: box 64x64x32, one period
+    orientation (6,6,4)), rectangular multi-orientation periods on a user box, and cubic periods (test hook).
+    Energy bookkeeping holds for each; rectangular periods expose more simultaneous trials than cubic ones."""
+    V = golden["ex_AlTiCrMo_V"][:64]
+    sysm = orc.System("bcc", 32, 32, 32, 4, 4, V)
+    g = random_config(orc, sysm, 8)
+    plans = []
+    for box, steps in (((0, 0, 0), 0), ((32, 32, 32), 0), ((32, 32, 32), 100000)):
+        dev = bw.Device("bcc", 32, 32, 32, 4, 4, V)
+        dev.metropolis_tune(box, steps)
+        plan = dev.metropolis_plan()
+        plans.append(plan)
+        dev.set_config(g)
+        e0 = dev.total_energy()[0]
+        att, acc, dE = dev.metropolis_run(1.0 / (700.0 * bw.K_B_IN_RY), 6 * sysm.n_atoms)
+        e1 = dev.total_energy()[0]
+        # the word kernel sums fixed-point dE (2^-k units, k ~ 37): bookkeeping to ~1e-8 instead of rounding
+        tol = 1e-7 if plan["use_box"] == 4 else 1e-10 * abs(e0) + 1e-12
+        assert abs((e1 - e0) - dE[0]) < tol
+        assert dev.total_energy()[0] == sysm.total_energy(dev.get_config())
+    assert plans[0]["use_box"] == 4 and plans[0]["P"] == (6, 6, 4) and plans[0]["n_orientations"] == 1
+    assert (plans[0]["box_x"], plans[0]["box_y"], plans[0]["box_z"]) == (64, 64, 32) and plans[0]["trials_per_step"] == 486
+    assert plans[2]["P"] == (6, 6, 6) and plans[2]["n_orientations"] == 1
+    assert plans[1]["P"][0] * plans[1]["P"][1] * plans[1]["P"][2] < 216 and plans[1]["n_orientations"] == 3
+    assert plans[1]["trials_per_step"] > plans[2]["trials_per_step"]
+
+
 def test_production_is_deterministic(bw, orc, golden):
     V = golden["ex_AlTiCrMo_V"][:64]
     sysm = orc.System("bcc", 16, 16, 16, 4, 4, V)
@@ -365,22 +393,25 @@ def test_specialised_kernel_equals_generic_kernel(bw, orc, golden, lattice, n, S
         if generic:
             dev.metropolis_tune((0, 0, 0), -1)          # automatic steps, generic kernel forced
         plan = dev.metropolis_plan()
-        assert plan["use_box"] == (1 if generic else 3), plan
+        word = lattice == "bcc" and shells == 4            # a word-lattice kernel exists for this case
+        assert plan["use_box"] == (1 if generic else 4 if word else 3), plan
         dev.set_config(g)
         out = dev.metropolis_run(1.0 / (700.0 * bw.K_B_IN_RY), 3 * int(mask.sum()), seed=77)
         res.append((dev.get_config().copy(), out))
     assert np.array_equal(res[0][0], res[1][0])
     assert np.array_equal(res[0][1][0], res[1][1][0]) and np.array_equal(res[0][1][1], res[1][1][1])
-    # the specialised kernel screens with count-based dE (same decisions, last-bit different dE sum)
-    assert np.allclose(res[0][1][2], res[1][1][2], rtol=0, atol=1e-9)
+    # the specialised kernels screen with count-based dE (same decisions; the dE sum differs in the last bits,
+    # or by ~1e-8 for the word kernel's fixed-point dE)
+    assert np.allclose(res[0][1][2], res[1][1][2], rtol=0, atol=1e-6 if word else 1e-9)
 
 
 @pytest.mark.parametrize("lattice,n,S,shells,key,T", [("bcc", 32, 4, 4, "ex_AlTiCrMo_V", 300.0), ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", 2000.0),
                                                       ("bcc", 32, 5, 4, "ex_AlCrFeCoNi_V", 800.0), ("fcc", 32, 5, 4, "ex_AlCrFeCoNi_V", 600.0),
                                                       ("fcc", 32, 2, 6, "t01_V", 500.0)])
 def test_screened_kernel_trajectory_identical(bw, orc, golden, lattice, n, S, shells, key, T):
-    """dE_mode 1 (integer-count screening, reference association recomputed inside the guard band)
-    takes exactly the accept/reject decisions of dE_mode 0 (reference association for every trial):
+    """dE_mode 1 (integer-count screening on the byte lattice) and dE_mode 2 (word lattice, fixed-point dp4a dE,
+    ex2.approx acceptance test) recompute every trial inside their guard bands with the reference association,
+    so they take exactly the accept/reject decisions of dE_mode 0 (reference association for every trial):
     same seed => identical configuration and identical accept counts after millions of trials."""
     V = golden[key][: 5 * 5 * shells].reshape(shells, 5, 5)[:, :S, :S].copy().ravel() if key != "ex_AlTiCrMo_V" else golden[key][: S * S * shells]
     g = np.zeros((2 * n, 2 * n, 2 * n), dtype=np.int8)
@@ -390,17 +421,20 @@ def test_screened_kernel_trajectory_identical(bw, orc, golden, lattice, n, S, sh
         (((par[None, None, :] + par[None, :, None] + par[:, None, None]) & 1) == 0)
     g[mask] = rng.integers(1, S + 1, size=int(mask.sum()))
     res = []
-    for mode in (0, 1):
+    word = lattice == "bcc" and shells == 4
+    for mode in (0, 1, 2):
         dev = bw.Device(lattice, n, n, n, S, shells, V)
         dev.metropolis_set_mode(mode)
-        assert dev.metropolis_plan()["use_box"] == (3 if mode else 2)
+        assert dev.metropolis_plan()["use_box"] == (2, 3, 4 if word else 3)[mode]
         dev.set_config(g)
         out = dev.metropolis_run(1.0 / (T * bw.K_B_IN_RY), 12 * int(mask.sum()), seed=99)
         res.append((dev.get_config().copy(), out, dev.total_energy()[0]))
-    assert np.array_equal(res[0][0], res[1][0])
-    assert np.array_equal(res[0][1][0], res[1][1][0]) and np.array_equal(res[0][1][1], res[1][1][1])
-    assert res[0][2] == res[1][2]
-    assert abs(res[0][1][2][0] - res[1][1][2][0]) < 1e-9          # sum of accepted dE: same to rounding
+    for m in (1, 2):
+        assert np.array_equal(res[0][0], res[m][0])
+        assert np.array_equal(res[0][1][0], res[m][1][0]) and np.array_equal(res[0][1][1], res[m][1][1])
+        assert res[0][2] == res[m][2]
+        # sum of accepted dE: same to rounding (word kernel: fixed-point dE, ~1e-11 per accepted swap)
+        assert abs(res[0][1][2][0] - res[m][1][2][0]) < (1e-6 if (m == 2 and word) else 1e-9)
 
 
 def test_production_limits(bw, orc, golden):
