@@ -346,8 +346,9 @@ def main():
                        "dE_mode": {0: "reference f64 association for every trial",
                                    1: "integer-count screening + reference association inside the guard band "
                                       "(accept/reject decisions identical to mode 0)",
-                                   2: "word lattice: integer-count screening with fixed-point dp4a dE + reference "
-                                      "association inside the guard band (accept/reject decisions identical to mode 0)"}[args.dE_mode], "acceptance": float(acc.sum()) / max(1, float(att.sum())),
+                                   2: "word lattice + dense non-interacting-set decomposition: integer-count screening "
+                                      "with fixed-point dp4a dE + reference association inside the guard band "
+                                      "(accept/reject decisions identical to mode 0)"}[args.dE_mode], "acceptance": float(acc.sum()) / max(1, float(att.sum())),
                        "energy_per_atom_start_end_Ry": [e_start / N, e_end / N]},
             "e2e": {"value": e2e_value, "unit": "swaps/s", "h2d_bytes_per_step": int(R * (8 * n ** 3 + 8)),
                     "d2h_bytes_per_step": int(R * (8 * n ** 3 + 8 + 24)),
@@ -355,7 +356,7 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": {4: "brw_box_metropolis_word_kernel<1,4,32,32,41,1317,4,512,6,6,4,9,9,6>", 3: "brw_box_metropolis_fast_kernel<1,4,32,32,true>", 2: "brw_box_metropolis_fast_kernel<1,4,32,32,false>", 1: "brw_box_metropolis_kernel<0>", 0: "brw_chain_metropolis_kernel"}[plan["use_box"]],
+                         "traffic": traffic, "kernel": {5: "brw_box_metropolis_word_kernel<1,4,32,32,32,4,32,1024,4,true>", 4: "brw_box_metropolis_word_kernel<1,4,32,32,32,4,32,1024,4,false>", 3: "brw_box_metropolis_fast_kernel<1,4,32,32,true>", 2: "brw_box_metropolis_fast_kernel<1,4,32,32,false>", 1: "brw_box_metropolis_kernel<0>", 0: "brw_chain_metropolis_kernel"}[plan["use_box"]],
                          "algorithmic_bytes_per_attempt": B_ALG, "attempts_per_launch": per_launch_trials,
                          "ms_per_launch": per_launch_ms, "peak_source": peak_src,
                          "note": "lattice is L2/shared-memory resident by design; see DESIGN.md"},

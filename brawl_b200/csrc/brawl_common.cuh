@@ -211,7 +211,8 @@ struct brawl_cuda_ctx {
   void *mc_plan[2];
   int last_plan;
   int tune_box[3], tune_steps, disable_fast, cubic_period_only, last_launches;
-  int dE_mode;                 // 0: reference association for every trial; 1: integer-count screening (default)
+  int dE_mode;                 // 0: reference association for every trial; 1: screened, byte lattice; 2: screened, word lattice (default)
+  int byte_layout;             // 1: never use the word-lattice kernels / dense decomposition (test hook, A/B comparisons)
 };
 
 int brw_fail(const char *fmt, ...);              // sets last error, returns 1

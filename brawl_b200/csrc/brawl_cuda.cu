@@ -379,13 +379,12 @@ static const BrwFastEntry brw_fast_table[] = {
     BRW_FAST(2, 4, 32, 64, 512), BRW_FAST(2, 4, 32, 64, 768), BRW_FAST(2, 6, 32, 64, 512), BRW_FAST(2, 6, 32, 64, 768),
 };
 
-// Word-lattice kernels (word_metropolis.cuh): fixed box and period orientation per entry; the row pitch
-// PXP = 32 + A0 and plane pitch PLP make the 32 lanes of a warp hit 32 different banks.
-struct BrwWordEntry { int lat, nsh, bxc, byc, bzc, P[3], A[3], pxp, plp, nlimb, maxt; BrwFastKernel fn; };
+// Word-lattice kernels with the dense decomposition (word_metropolis.cuh): fixed box and margin per entry.
+struct BrwWordEntry { int lat, nsh, bxc, byc, bzc, margin, pxp, plp, nlimb; BrwFastKernel fn, fn_exact; };
 static const BrwWordEntry brw_word_table[] = {
-    // bcc, 4 shells, box 64x64x32 (doubled-grid units), P = (6,6,4): A = (9,9,6), 486 trials per step
-    {1, 4, 32, 32, 32, {6, 6, 4}, {9, 9, 6}, 41, 1317, 4, 512,
-     brw_box_metropolis_word_kernel<1, 4, 32, 32, 41, 1317, 4, 512, 6, 6, 4, 9, 9, 6>},
+    // bcc, 4 shells, box 64x64x32 (doubled-grid units): 32 warps x 28 = 896 trials per step
+    {1, 4, 32, 32, 32, 4, 32, 1024, 4, brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, 4, false>,
+     brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, 4, true>},
 };
 
 // launch helper for the warp-per-walker kernels: layout + opt-in shared memory
@@ -443,7 +442,7 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
   // box extents: user override or automatic halving of the longest edge, for a given shared-memory
   // footprint per site.  Returns 0 ok, 1 infeasible, 2 error (message set).
   const size_t budget = 200 * 1024;
-  auto size_box = [&](double bytes_per_site, size_t fixed, int minP, const int *P0, int *Bo) -> int {
+  auto size_box = [&](double bytes_per_site, size_t fixed, int minP, const int *P0, int *Bo, const int *stop_at = nullptr) -> int {
     for (int d = 0; d < 3; d++) Bo[d] = d == 0 ? g.gx : d == 1 ? g.gy : g.gz;
     auto bytes = [&](const int *b) { return (size_t)((double)b[0] * b[1] * b[2] / (g.lattice == 1 ? 4 : 2) * bytes_per_site); };
     auto trials = [&](const int *b) { long M = 1; for (int d = 0; d < 3; d++) M *= (b[d] - 2 * m) / P0[d]; return M; };
@@ -464,6 +463,7 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       bool too_big = bytes(Bo) + fixed > budget;
       bool want_more = nbox < 120 && trials(Bo) >= 512;
       if (!too_big && !want_more) return 0;
+      if (!too_big && stop_at && Bo[0] == stop_at[0] && Bo[1] == stop_at[1] && Bo[2] == stop_at[2]) return 0;
       // halve the longest edge that can still be halved
       // (a box that has a specialised kernel is not halved out of it just to get more CTAs)
       auto has_fast = [&](const int *b) {
@@ -486,29 +486,30 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       Bo[best] /= 2;
     }
   };
-  // word-lattice decomposition: if the box sized for 4-byte sites is one a word kernel is instantiated for,
-  // its (single) period orientation is the plan -- for every dE_mode, so that modes 0/1/2 share one
-  // decomposition and produce identical trajectories
+  // word-lattice kernels with the dense decomposition: used when the box sized for 4-byte sites is one an entry is
+  // instantiated for (dE_mode 0 -> its EXACT instantiation, 2 -> screened; dE_mode 1 and byte_layout keep the
+  // byte-lattice path)
   const BrwWordEntry *we = nullptr;
-  if (feasible && !nbr_swap && !h->cubic_period_only && g.S <= 5) {
+  if (feasible && !nbr_swap && !h->cubic_period_only && !h->disable_fast && !h->byte_layout && h->dE_mode != 1 && g.S <= 5) {
     for (const BrwWordEntry &e : brw_word_table) {
-      if (we || e.lat != g.lattice || e.nsh != g.n_shells) continue;
+      if (we || e.lat != g.lattice || e.nsh != g.n_shells || e.margin < rmax + 1) continue;
+      // S_o = o + {(0,0,0),(2,2,2)} + 4Z^3 must be an independent set of the interaction graph
+      bool independent = true;
+      for (int k = 0; k < g.ztot; k++) {
+        const int a = brw_posmod(g.off[k][0], 4), b = brw_posmod(g.off[k][1], 4), c = brw_posmod(g.off[k][2], 4);
+        if ((a == 0 && b == 0 && c == 0) || (a == 2 && b == 2 && c == 2)) independent = false;
+      }
+      if (!independent) continue;
       int Bw[3];
+      const int P4[3] = {4, 4, 4};
       const size_t fixed_w = 32 * 1024;
-      const int st = size_box(4.0 * e.plp / (double)(e.bxc * e.byc), fixed_w, std::max(e.P[0], std::max(e.P[1], e.P[2])), e.P, Bw);
+      const int Be[3] = {e.bxc << g.xs, e.byc << g.ys, e.bzc};
+      const int st = size_box(4.0 * e.plp / (double)(e.bxc * e.byc), fixed_w, 4, P4, Bw, Be);
       if (st != 0) continue;       // (an invalid user box is reported by the byte-lattice sizing below)
       if ((Bw[0] >> g.xs) != e.bxc || (Bw[1] >> g.ys) != e.byc || Bw[2] != e.bzc) continue;
-      BrwModeChoice mc;
-      mc.P[0] = e.P[0]; mc.P[1] = e.P[1]; mc.P[2] = e.P[2];
-      if (!brw_period_admissible(g, nbr_swap, first, mc.P, mc.classes, mc.disp)) continue;
-      bool same_cells = true;
-      for (int d = 0; d < 3; d++) if ((Bw[d] - 2 * m) / e.P[d] != e.A[d]) same_cells = false;
-      if (!same_cells) continue;
       we = &e;
       for (int d = 0; d < 3; d++) B[d] = Bw[d];
-      cands.clear();
-      cands.push_back(std::vector<BrwModeChoice>{mc});
-      modes = cands[0];
+      m = e.margin;
     }
   }
   if (feasible && !we) {
@@ -567,6 +568,18 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       disp.insert(disp.end(), modes[q].disp.begin(), modes[q].disp.end());
       Mmax = std::max(Mmax, md.M); Mmin = std::min(Mmin, md.M);
     }
+    if (we) {
+      // dense decomposition (word_metropolis.cuh, BrwDenseGeom): period 4, one warp per (A row, B row) pair
+      p.n_modes = 1;
+      BrwBoxMode &md = p.mode[0];
+      md.P[0] = md.P[1] = md.P[2] = 4;
+      md.A[0] = (B[0] - 2 * m) / 4;                               // sites per x-row of one sub-class
+      md.A[1] = (((B[1] - 3 * m) / 2) & ~3) / 4;                  // rows per plane in one y half
+      md.A[2] = (B[2] - 2 * m) / 4;                               // planes per sub-class
+      md.M = std::min(32, md.A[1] * md.A[2]) * 2 * md.A[0];
+      md.cls0 = md.d0 = 0; md.n_classes = 16; md.n_disp = 256;    // 16 residue classes mod 4, every (o, o') pair
+      Mmax = md.M;
+    }
     pl->Mmax = Mmax;
     p.boxes_per_replica = p.nb[0] * p.nb[1] * p.nb[2];
     p.v_entries = g.S * g.S * g.n_shells;
@@ -599,7 +612,7 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
     BRW_PLAN_CUDA(cudaMemcpy(pl->d_Vrep, vrep.data(), vrep.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (nbr_swap) BRW_PLAN_CUDA(cudaFuncSetAttribute(brw_box_metropolis_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     else BRW_PLAN_CUDA(cudaFuncSetAttribute(brw_box_metropolis_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
-    if (!nbr_swap && !h->disable_fast && Mmax <= 768)
+    if (!we && !nbr_swap && !h->disable_fast && Mmax <= 768)
       for (const BrwFastEntry &fe : brw_fast_table)
         if (!pl->fast_fn && fe.lat == g.lattice && fe.nsh == g.n_shells && fe.px == p.bxc && fe.py == p.byc &&
             ((Mmax + 31) / 32) * 32 <= fe.maxt) {
@@ -611,9 +624,9 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
           pl->threads = std::min(768, ((Mmax + 31) / 32) * 32);
           BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)pl->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
         }
-    if (we && h->dE_mode == 2 && !h->disable_fast) {
+    if (we) {
       // word-lattice kernel: replace the lane-replicated V by its table blob (layout: word_metropolis.cuh)
-      const int NL = we->nlimb, NSH = g.n_shells, S = g.S, ROWP = NSH * NL + 4;
+      const int NL = we->nlimb, NSH = g.n_shells, S = g.S, PAIRS = NSH * NL / 2;
       auto species_of = [](int code) { return code == 4 ? 4 : 3 - code; };
       auto Vn = [&](int n, int centre, int nbr) { return h->hV[(n * S + nbr) * S + centre]; };
       auto U = [&](int sa, int sb, int n, int s) {
@@ -627,15 +640,18 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       int kexp = 0;
       if (umax > 0.0) kexp = (int)std::floor(std::log2(std::ldexp(1.0, 8 * NL - 2) / umax));
       p.fix_scale = std::ldexp(1.0, -kexp);
+      p.row_mul = S <= 4 ? 4 : 5;
       // |fixed-point dE - real dE| <= sum_f |d_f| * 2^-k / 2 <= ztot * 2^-k; the second term covers the f64
       // rounding difference to the reference association as before
       p.guard = g.ztot * p.fix_scale + 1e-9 * g.ztot * umax;
-      const int tab_words = (25 * ROWP + 2 * g.ztot + 1) & ~1;
+      const int urow_words = (PAIRS + 1) * 64;
+      const int tab_words = (urow_words + 2 * g.ztot + 1) & ~1;
       std::vector<int> blob(tab_words + 2 * p.v_entries, 0);
       for (int ca = 0; ca < 5; ca++) for (int cb = 0; cb < 5; cb++) {
         const int sa = species_of(ca), sb = species_of(cb);
         if (sa >= S || sb >= S || sa == sb) continue;
-        int *row = blob.data() + (ca * 5 + cb) * ROWP;
+        const int r = ca * p.row_mul + cb;                         // < 32
+        auto word = [&](int e) -> int & { return blob[(e / 2) * 64 + r * 2 + (e & 1)]; };
         long long K = 0;
         for (int n = 0; n < NSH; n++)
           for (int s2 = 0; s2 < std::min(S, 4); s2++) {
@@ -644,25 +660,27 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
             for (int k = 0; k < NL; k++) {
               long long dgt = k == NL - 1 ? v : ((v + 128) & 255) - 128;
               v = (v - dgt) >> 8;
-              row[n * NL + k] |= (int)((uint32_t)(uint8_t)(int8_t)dgt << (8 * s2));
+              word(n * NL + k) |= (int)((uint32_t)(uint8_t)(int8_t)dgt << (8 * s2));
             }
           }
-        std::memcpy(row + NSH * NL, &K, 8);
+        word(2 * PAIRS) = (int)(uint32_t)((unsigned long long)K & 0xFFFFFFFFull);
+        word(2 * PAIRS + 1) = (int)(uint32_t)((unsigned long long)K >> 32);
       }
       for (int par = 0; par < 2; par++)
         for (int k = 0; k < g.ztot; k++) {
           int dx = g.off[k][0], dy = g.off[k][1], dz = g.off[k][2];
           int dxc = (par + dx) >> 1, dyc = g.ys ? ((par + dy) >> 1) : dy;
-          blob[25 * ROWP + par * g.ztot + k] = dz * we->plp + dyc * we->pxp + dxc;
+          blob[urow_words + par * g.ztot + k] = dz * we->plp + dyc * we->pxp + dxc;
         }
       std::memcpy(blob.data() + tab_words, h->hV, sizeof(double) * p.v_entries);
       cudaFree(pl->d_Vrep); pl->d_Vrep = nullptr;
       BRW_PLAN_CUDA(cudaMalloc(&pl->d_Vrep, blob.size() * sizeof(int)));
       BRW_PLAN_CUDA(cudaMemcpy(pl->d_Vrep, blob.data(), blob.size() * sizeof(int), cudaMemcpyHostToDevice));
-      pl->fast_fn = (void *)we->fn;
-      pl->screened = true; pl->word = true;
-      pl->fast_smem = blob.size() * sizeof(int) + 32 * 8 + 16 + (size_t)p.steps * sizeof(BrwStepParams) + (size_t)we->plp * p.bzc * 4;
-      pl->threads = std::min(we->maxt, ((Mmax + 31) / 32) * 32);
+      pl->fast_fn = (void *)(h->dE_mode == 0 ? we->fn_exact : we->fn);
+      pl->screened = h->dE_mode != 0; pl->word = true;
+      pl->fast_smem = blob.size() * sizeof(int) + 32 * 8 + 2 * (size_t)p.mode[0].A[1] * p.mode[0].A[2] * 4 + 16 +
+                      (size_t)p.steps * 32 + (size_t)we->plp * p.bzc * 4;
+      pl->threads = 1024;
       BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)pl->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
     }
     pl->use_box = true;
@@ -704,6 +722,13 @@ extern "C" int brawl_cuda_metropolis_set_mode(brawl_cuda_t *h, int dE_mode) {
   for (int i = 0; i < 2; i++) { brw_free_plan((BrwPlan *)h->mc_plan[i]); h->mc_plan[i] = nullptr; }
   return 0;
 }
+extern "C" int brawl_cuda_metropolis_set_layout(brawl_cuda_t *h, int byte_layout_only) {
+  BRW_ENTER(h);
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  h->byte_layout = byte_layout_only != 0;
+  for (int i = 0; i < 2; i++) { brw_free_plan((BrwPlan *)h->mc_plan[i]); h->mc_plan[i] = nullptr; }
+  return 0;
+}
 extern "C" int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *o) {
   BRW_ENTER(h);
   BrwPlan *pl;
@@ -712,7 +737,7 @@ extern "C" int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *o)
     const BrwBoxMode &m0 = pl->p.mode[0];
     o[0] = pl->use_box; o[1] = m0.P[0] * 10000 + m0.P[1] * 100 + m0.P[2]; o[2] = pl->p.m; o[3] = pl->p.B[0]; o[4] = pl->p.B[1];
     o[5] = pl->p.B[2]; o[6] = pl->Mmax; o[7] = pl->p.boxes_per_replica; o[8] = m0.n_disp; o[9] = pl->p.steps;
-    if (pl->fast_fn) o[0] = pl->word ? 4 : pl->screened ? 3 : 2;
+    if (pl->fast_fn) o[0] = pl->word ? (pl->screened ? 4 : 5) : pl->screened ? 3 : 2;
     o[0] += 16 * pl->p.n_modes;                 // number of period orientations in bits 4..
   }
   return 0;

@@ -41,6 +41,7 @@ struct BrwBoxParams {          // POD kernel parameter
   int boxes_per_replica;
   int steps;
   int v_entries;               // S*S*n_shells
+  int row_mul;                 // word kernel: row of its fixed-point table = code_a*row_mul + code_b
 };
 
 struct BrwPlan {

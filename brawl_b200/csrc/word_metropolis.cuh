@@ -1,10 +1,10 @@
 // word_metropolis.cuh -- production Metropolis (nbr_energy,
-// pair_energy, pair_swap, monte_carlo_step_lattice; src/metropolis.F90:751-813) on a WORD lattice.
+// pair_energy, pair_swap, monte_carlo_step_lattice; src/metropolis.F90:751-813) on a WORD lattice
+// with DENSE non-interacting site sets.
 //
-// Same decomposition, same Philox counters and the same decisions as brw_box_metropolis_fast_kernel
-// (tile_metropolis.cuh) -- trajectories are identical -- but the box is held in shared memory as one
-// 32-bit word per site, word = 1 << (8*species) for species 0..3 and 0 for species 4.  The integer
-// neighbour counts of the screened dE then need ONE LDS.32 + half an IADD3 per neighbour:
+// Lattice in shared memory: one 32-bit word per site, word = 1 << (8*species) for species 0..3 and 0
+// for species 4.  The integer neighbour counts of the screened dE then need ONE LDS.32 + half an
+// IADD3 per neighbour:
 //     acc[shell] = 0x80808080 + sum_{nbrs of site1} word - sum_{nbrs of site2} word
 // leaves byte s of acc[shell] = 128 + (c1 - c2)[shell][s] (|c1-c2| <= 24, so no borrow crosses a
 // byte), and
@@ -16,10 +16,25 @@
 // the reference's f64 association (src/bw_hamiltonian.f90:171-173, :1014-1017, :111-112;
 // src/metropolis.F90:792-802) and decided by it, exactly like the byte-lattice screened kernel.  The
 // acceptance test uses ex2.approx.f32 first (relative error < 1e-5 over the non-flushed range) with
-// a correspondingly wider band.
+// a correspondingly wider band.  EXACT = true skips the screening: every trial is decided by the
+// reference association (the trajectory-identity tests compare the two instantiations).
 //
-// Rows are padded (pitch PXP words = 32 + A0, plane pitch PLP) so that the 32 lanes of a warp --
-// consecutive coarse cells, 3 words apart in x -- fall into 32 different banks: bank = 3*lane.
+// Decomposition (per step, CTA-uniform): the densest set of mutually NON-INTERACTING sites of the
+// bcc lattice with <= 4 shells is  S_o = o + {(0,0,0),(2,2,2)} + 4 Z^3  (1/8 of all sites: no
+// neighbour vector of shells 1-4 is = (0,0,0) or (2,2,2) mod 4 -- checked by the host planner).  A
+// step draws two residue classes o, o' (mod 4) and proposes, in parallel, swaps between sites of S_o in
+// the lower-y half of the box's active region and sites of S_o' in the upper-y half; the two halves
+// are separated by a gap >= the interaction reach, so all 2M sites of a step are pairwise
+// non-interacting for ANY o, o' and the M simultaneous Metropolis decisions are exactly equivalent to
+// M sequential ones.  Every pair of residue classes is connected (composition flows between all
+// sublattices), each move is its own inverse and its proposal probability does not depend on the
+// configuration: detailed balance holds move by move.
+//
+// Lane mapping: a warp takes one x-row of sub-class A sites (lanes 0..13, even word addresses) and
+// one x-row of sub-class B = A + (2,2,2) sites (lanes 14..27, odd word addresses): consecutive sites of
+// a row are 2 words apart, so the 28 lanes fall into 28 different banks for every gather.  Site 2 is
+// the same construction in the upper half with a random row rotation, a cyclic x shift and an
+// optional A<->B exchange (all CTA-uniform), which keeps its gathers conflict-free as well.
 #pragma once
 #include "tile_metropolis.cuh"
 
@@ -82,35 +97,82 @@ __device__ __forceinline__ void brw_wbox_copy(const BrwGeom &g, uint8_t *L, uint
 }
 
 // Constant tables of the word kernel, one blob in global memory copied to shared memory per CTA:
-//   int32  urow[25][ROWP]   row (code_a*5 + code_b): words [n*NLIMB + k] = the k-th signed digit of U*2^k for the four
-//                           species fields packed as int8x4; words [NSH*NLIMB .. +1] = int64 K = 128 * sum_f Ufix_f
-//   int32  off[2][ztot]     word offsets of the neighbours per x-parity (fallback path)
-//   double V[n_shells][S][S] reference V_ex in Fortran order V(centre, nbr, shell) (fallback path)
+//   int32  urow[PAIRS+1][32][2]  fixed-point table, pair-major so that different rows (species pairs) fall into
+//                           different banks: element e = n*NLIMB + k of row r (r = code_a*row_mul + code_b) is word
+//                           [e/2][r][e%2] = the k-th signed digit of U*2^k for the four species fields packed as
+//                           int8x4; pair PAIRS = int64 K = 128 * sum_f Ufix_f
+//   int32  off[2][ztot]     word offsets of the neighbours per x-parity (reference-association path)
+//   double V[n_shells][S][S] reference V_ex in Fortran order V(centre, nbr, shell)
 template <int NSH, int NLIMB> struct BrwWordTab {
-  static constexpr int ROWP = NSH * NLIMB + 4;      // 20 (4 limbs) / 28 (6 limbs): 8 rows start in 8 different bank quads
-  static constexpr int urow_words = 25 * ROWP;
+  static constexpr int PAIRS = NSH * NLIMB / 2;
+  static constexpr int urow_words = (PAIRS + 1) * 64;
 };
 
-// P0..P2 / A0..A2: the (single) period orientation and the coarse-cell counts of the plan, compile-time so
-// that the per-step index arithmetic uses immediates (the host checks them against the plan).
-template <int LAT, int NSH, int PX, int PY, int PXP, int PLP, int NLIMB, int MAXT, int P0, int P1, int P2, int A0, int A1,
-          int A2>
-__global__ void __launch_bounds__(MAXT) brw_box_metropolis_word_kernel(
+// geometry of the dense decomposition for one box (compile-time)
+template <int BX, int BY, int BZ, int MARGIN> struct BrwDenseGeom {
+  static constexpr int NI = (BX - 2 * MARGIN) / 4;            // sites per x-row of one sub-class (14)
+  static constexpr int HALF = ((BY - 2 * MARGIN - MARGIN) / 2) & ~3;   // y extent of one half, gap >= MARGIN (24)
+  static constexpr int NJ = HALF / 4;                          // rows per plane and half (6)
+  static constexpr int NP = (BZ - 2 * MARGIN) / 4;             // planes per sub-class (6)
+  static constexpr int NROWS = NJ * NP;                        // rows per sub-class and half (36)
+  static constexpr int Y_UPPER = MARGIN + HALF + MARGIN;       // first y of the upper half (32)
+  static_assert(2 * NI <= 32, "one warp holds an A row and a B row");
+};
+
+struct __align__(16) BrwDenseStep {   // CTA-uniform per step
+  int c1[2];                   // word index of site1 (i = 0, row 0) for sub-class A / B, lower half, class o
+  int c2[2];                   // same for site2: upper half, class o'
+  int rot1, rot2;              // row rotations
+  int si;                      // cyclic x shift of site2
+  int flags;                   // bit0: x-parity of o, bit1: x-parity of o', bit2: site2 takes the other sub-class
+};
+
+template <int BX, int BY, int BZ, int MARGIN, int PXP, int PLP>
+__device__ __forceinline__ void brw_make_dense_step(uint32_t k0, uint32_t k1, uint32_t step, uint32_t box_id,
+                                                    uint32_t phase_lo, BrwDenseStep *out) {
+  using G = BrwDenseGeom<BX, BY, BZ, MARGIN>;
+  BrwPhilox4 r = brw_philox(0xFFFFFFFFu, step, box_id, phase_lo, k0, k1);
+  // residue classes mod 4 of the bcc lattice: parity bit + three "half" bits; 16 classes each
+  const uint32_t q1 = r.x & 15u, q2 = (r.x >> 4) & 15u;
+  int o[2][3];
+  o[0][0] = (q1 & 1) + 2 * ((q1 >> 1) & 1); o[0][1] = (q1 & 1) + 2 * ((q1 >> 2) & 1); o[0][2] = (q1 & 1) + 2 * ((q1 >> 3) & 1);
+  o[1][0] = (q2 & 1) + 2 * ((q2 >> 1) & 1); o[1][1] = (q2 & 1) + 2 * ((q2 >> 2) & 1); o[1][2] = (q2 & 1) + 2 * ((q2 >> 3) & 1);
+  for (int h = 0; h < 2; h++) {
+    const int y_lo = h == 0 ? MARGIN : G::Y_UPPER;
+    for (int sub = 0; sub < 2; sub++) {
+      // first site of the sub-class inside the region: coordinate = lo + ((class + 2*sub - lo) mod 4)
+      const int X = MARGIN + ((o[h][0] + 2 * sub - MARGIN) & 3);
+      const int Y = y_lo + ((o[h][1] + 2 * sub - y_lo) & 3);
+      const int Z = MARGIN + ((o[h][2] + 2 * sub - MARGIN) & 3);
+      const int c = Z * PLP + (Y >> 1) * PXP + (X >> 1);
+      if (h == 0) out->c1[sub] = c; else out->c2[sub] = c;
+    }
+  }
+  out->rot1 = (int)brw_below(r.y, G::NROWS);
+  out->rot2 = (int)brw_below(r.z, G::NROWS);
+  out->si = (int)(((r.w & 0xFFFFu) * (uint32_t)G::NI) >> 16);
+  out->flags = (int)(q1 & 1u) | (int)((q2 & 1u) << 1) | (int)(((r.w >> 16) & 1u) << 2);
+}
+
+template <int LAT, int NSH, int PX, int PY, int PZ, int MARGIN, int PXP, int PLP, int NLIMB, bool EXACT>
+__global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
     BrwGeom g, BrwBoxParams p, uint8_t *__restrict__ lat, const double *__restrict__ beta,
     const double *__restrict__ tab_g, const int4 *__restrict__ classes, const int4 *__restrict__ disp, uint32_t k0,
     uint32_t k1, uint32_t phase_lo, int mode, unsigned long long *__restrict__ att_out,
     unsigned long long *__restrict__ acc_out, double *__restrict__ dE_out) {
+  static_assert(LAT == 1, "dense sets are derived for bcc");
   using T = BrwWordTab<NSH, NLIMB>;
+  using G = BrwDenseGeom<2 * PX, 2 * PY, PZ, MARGIN>;
+  (void)mode; (void)classes; (void)disp;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const BrwBoxMode &md = p.mode[0];                                           // one orientation (P0,P1,P2)
-  (void)mode;
-  int *urow = reinterpret_cast<int *>(smem_raw);                              // [25][ROWP]
+  int *urow = reinterpret_cast<int *>(smem_raw);                              // [(PAIRS+1)][32][2]
   int *off = urow + T::urow_words;                                            // [2][ztot]
   const int tab_words = (T::urow_words + 2 * g.ztot + 1) & ~1;
   double *Vs = reinterpret_cast<double *>(urow + tab_words);                  // [n_shells][S][S]
   double *red = Vs + p.v_entries;                                             // [32]
-  BrwStepParams *sp = reinterpret_cast<BrwStepParams *>(                      // [steps], 16-byte aligned
-      smem_raw + (((size_t)tab_words * 4 + (size_t)p.v_entries * 8 + 32 * 8 + 15) & ~(size_t)15));
+  int *rowoff = reinterpret_cast<int *>(red + 32);                            // [2*NROWS]
+  BrwDenseStep *sp = reinterpret_cast<BrwDenseStep *>(                        // [steps], 16-byte aligned
+      smem_raw + (((size_t)tab_words * 4 + (size_t)p.v_entries * 8 + 32 * 8 + 2 * G::NROWS * 4 + 15) & ~(size_t)15));
   uint32_t *wbox = reinterpret_cast<uint32_t *>(sp + p.steps);                // [bzc][PLP]
   __shared__ unsigned int s_att[32], s_acc[32];
 
@@ -130,16 +192,14 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_word_kernel(
     const int *tg = reinterpret_cast<const int *>(tab_g);
     for (int i = tid; i < tab_words + 2 * p.v_entries; i += blockDim.x) urow[i] = tg[i];
   }
-  for (int st = tid; st < p.steps; st += blockDim.x) {
-    BrwStepParams q;
-    brw_make_step<0>(g, p, md, classes, disp, k0, k1, (uint32_t)st, box_id, phase_lo, &q);
-    // re-express the two base sites in the padded word layout (make_step used pitch bxc/byc)
-    const int z1 = q.c1_base / (PX * PY), r1 = q.c1_base - z1 * PX * PY;
-    const int z2 = q.c2_base / (PX * PY), r2 = q.c2_base - z2 * PX * PY;
-    q.c1_base = z1 * PLP + (r1 / PX) * PXP + (r1 % PX);
-    q.c2_base = z2 * PLP + (r2 / PX) * PXP + (r2 % PX);
-    sp[st] = q;
+  // rows of one sub-class in one half: r -> (j = r % NJ rows of 4 in y, pl = r / NJ planes of 4 in z); doubled so that
+  // (warp + rotation) needs no wrap
+  for (int r = tid; r < 2 * G::NROWS; r += blockDim.x) {
+    const int rr = r % G::NROWS;
+    rowoff[r] = 2 * PXP * (rr % G::NJ) + 4 * PLP * (rr / G::NJ);
   }
+  for (int st = tid; st < p.steps; st += blockDim.x)
+    brw_make_dense_step<2 * PX, 2 * PY, PZ, MARGIN, PXP, PLP>(k0, k1, (uint32_t)st, box_id, phase_lo, &sp[st]);
   brw_wbox_copy<LAT, PX, PY, PXP, PLP, false>(g, L, wbox, PY * p.bzc, ox, oy, oz);
   __syncthreads();
 
@@ -148,63 +208,66 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_word_kernel(
   // relative band of the fast acceptance test: ex2.approx + f32 argument rounding (< 1e-5 for |x| <= 126)
   // plus the dE guard propagated through exp
   const double band = my_beta * p.guard + 4e-5;
-  constexpr int stx = P0 >> 1, sty = (LAT == 1 ? (P1 >> 1) : P1) * PXP, stz = P2 * PLP;
-  const bool active = tid < A0 * A1 * A2;
-  const int ci = tid % A0, cr = tid / A0, cj = cr % A1, ck = cr / A1;
-  const int base1 = ci * stx + cj * sty + ck * stz;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int sub = lane >= G::NI ? 1 : 0;
+  const int li = lane - sub * G::NI;                     // position in the x-row
+  const bool active = lane < 2 * G::NI && warp < G::NROWS;
+  const int row_mul = p.row_mul;
   unsigned int n_att = 0, n_acc = 0;
   double dE_sum = 0.0;
   BrwPhilox4 rnd = {0, 0, 0, 0};
 
   for (int step = 0; step < p.steps; step++) {
-    const BrwStepParams q = sp[step];
+    const BrwDenseStep q = sp[step];
     if (active) {
-      int i2 = ci + q.s[0]; if (i2 >= A0) i2 -= A0;
-      int j2 = cj + q.s[1]; if (j2 >= A1) j2 -= A1;
-      int k2 = ck + q.s[2]; if (k2 >= A2) k2 -= A2;
-      uint32_t *w1 = wbox + q.c1_base + base1;
-      uint32_t *w2 = wbox + q.c2_base + i2 * stx + j2 * sty + k2 * stz;
+      int i2 = li + q.si; if (i2 >= G::NI) i2 -= G::NI;
+      const int sub2 = sub ^ ((q.flags >> 2) & 1);
+      uint32_t *w1 = wbox + (sub ? q.c1[1] : q.c1[0]) + 2 * li + rowoff[warp + q.rot1];
+      uint32_t *w2 = wbox + (sub2 ? q.c2[1] : q.c2[0]) + 2 * i2 + rowoff[warp + q.rot2];
       const uint32_t wa = *w1, wb = *w2;
       n_att++;
       if ((step & 3) == 0) rnd = brw_philox((uint32_t)tid, (uint32_t)step, box_id, phase_lo, k0, k1);
       if (wa != wb) {
         const uint32_t w = (step & 3) == 0 ? rnd.x : (step & 3) == 1 ? rnd.y : (step & 3) == 2 ? rnd.z : rnd.w;
         const double u = brw_u01(w);
-        uint32_t C1[NSH], C2[NSH];
-        if (q.par1) brw_wsum_shells<LAT, NSH, PXP, PLP, 1, 0>(w1, C1);
-        else brw_wsum_shells<LAT, NSH, PXP, PLP, 0, 0>(w1, C1);
-        if (q.par2) brw_wsum_shells<LAT, NSH, PXP, PLP, 1, 0>(w2, C2);
-        else brw_wsum_shells<LAT, NSH, PXP, PLP, 0, 0>(w2, C2);
         const int ca = brw_word_code(wa), cb = brw_word_code(wb);
-        const int4 *row = reinterpret_cast<const int4 *>(urow + (ca * 5 + cb) * T::ROWP);
-        int Sk[NLIMB];
-#pragma unroll
-        for (int k = 0; k < NLIMB; k++) Sk[k] = 0;
-#pragma unroll
-        for (int j = 0; j < NSH * NLIMB / 4; j++) {
-          const int4 Lw = row[j];
-          const int e0 = 4 * j, e1 = 4 * j + 1, e2 = 4 * j + 2, e3 = 4 * j + 3;
-          Sk[e0 % NLIMB] = brw_dp4a_us(0x80808080u + C1[e0 / NLIMB] - C2[e0 / NLIMB], Lw.x, Sk[e0 % NLIMB]);
-          Sk[e1 % NLIMB] = brw_dp4a_us(0x80808080u + C1[e1 / NLIMB] - C2[e1 / NLIMB], Lw.y, Sk[e1 % NLIMB]);
-          Sk[e2 % NLIMB] = brw_dp4a_us(0x80808080u + C1[e2 / NLIMB] - C2[e2 / NLIMB], Lw.z, Sk[e2 % NLIMB]);
-          Sk[e3 % NLIMB] = brw_dp4a_us(0x80808080u + C1[e3 / NLIMB] - C2[e3 / NLIMB], Lw.w, Sk[e3 % NLIMB]);
-        }
-        long long efix = -*reinterpret_cast<const long long *>(urow + (ca * 5 + cb) * T::ROWP + NSH * NLIMB);
-#pragma unroll
-        for (int k = 0; k < NLIMB; k++) efix += (long long)Sk[k] * (1LL << (8 * k));
-        double dE = (double)efix * p.fix_scale;                  // exact: |efix| < 2^53, fix_scale = 2^-k
         bool decided = false, accept = false;
-        if (fabs(dE) > p.guard) {
-          if (dE < 0.0) { accept = true; decided = true; }
-          else {
-            const double t = (double)brw_ex2_approx((float)(-beta_l2e * dE));
-            if (fabs(u - t) > t * band) { accept = u < t; decided = true; }
+        double dE = 0.0;
+        if (!EXACT) {
+          uint32_t C1[NSH], C2[NSH];
+          if (q.flags & 1) brw_wsum_shells<LAT, NSH, PXP, PLP, 1, 0>(w1, C1);
+          else brw_wsum_shells<LAT, NSH, PXP, PLP, 0, 0>(w1, C1);
+          if (q.flags & 2) brw_wsum_shells<LAT, NSH, PXP, PLP, 1, 0>(w2, C2);
+          else brw_wsum_shells<LAT, NSH, PXP, PLP, 0, 0>(w2, C2);
+          const int2 *row = reinterpret_cast<const int2 *>(urow) + (ca * row_mul + cb);
+          int Sk[NLIMB];
+#pragma unroll
+          for (int k = 0; k < NLIMB; k++) Sk[k] = 0;
+#pragma unroll
+          for (int j = 0; j < T::PAIRS; j++) {
+            const int2 Lw = row[j * 32];
+            const int e0 = 2 * j, e1 = 2 * j + 1;
+            Sk[e0 % NLIMB] = brw_dp4a_us(0x80808080u + C1[e0 / NLIMB] - C2[e0 / NLIMB], Lw.x, Sk[e0 % NLIMB]);
+            Sk[e1 % NLIMB] = brw_dp4a_us(0x80808080u + C1[e1 / NLIMB] - C2[e1 / NLIMB], Lw.y, Sk[e1 % NLIMB]);
+          }
+          const int2 Kw = row[T::PAIRS * 32];
+          long long efix = -(long long)(((unsigned long long)(uint32_t)Kw.y << 32) | (uint32_t)Kw.x);
+#pragma unroll
+          for (int k = 0; k < NLIMB; k++) efix += (long long)Sk[k] * (1LL << (8 * k));
+          dE = (double)efix * p.fix_scale;                       // exact: |efix| < 2^53, fix_scale = 2^-k
+          if (fabs(dE) > p.guard) {
+            if (dE < 0.0) { accept = true; decided = true; }
+            else {
+              const double t = (double)brw_ex2_approx((float)(-beta_l2e * dE));
+              if (fabs(u - t) > t * band) { accept = u < t; decided = true; }
+            }
           }
         }
         if (!decided) {
-          // reference association, generic loop (rare: ~1e-5 of trials)
+          // reference association, generic loop (screened kernel: ~1e-5 of the trials)
           const int sa = brw_code_species(ca), sb = brw_code_species(cb);
           const int S = g.S;
+          const int *off1 = off + (q.flags & 1) * g.ztot, *off2 = off + ((q.flags >> 1) & 1) * g.ztot;
           double E1a = 0.0, E1b = 0.0, E2b = 0.0, E2a = 0.0;
           int k = 0;
 #pragma unroll 1
@@ -214,8 +277,8 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_word_kernel(
             const int end = g.shell_end[n];
 #pragma unroll 1
             for (; k < end; k++) {
-              const int s1 = brw_code_species(brw_word_code(w1[off[q.par1 * g.ztot + k]]));
-              const int s2 = brw_code_species(brw_word_code(w2[off[q.par2 * g.ztot + k]]));
+              const int s1 = brw_code_species(brw_word_code(w1[off1[k]]));
+              const int s2 = brw_code_species(brw_word_code(w2[off2[k]]));
               e1a = __dadd_rn(e1a, Vn[s1 * S + sa]); e1b = __dadd_rn(e1b, Vn[s1 * S + sb]);
               e2b = __dadd_rn(e2b, Vn[s2 * S + sb]); e2a = __dadd_rn(e2a, Vn[s2 * S + sa]);
             }

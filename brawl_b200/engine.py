@@ -162,8 +162,13 @@ class Device:
     def metropolis_set_mode(self, dE_mode):
         """0: reference f64 association for every trial; 1: integer-count screening on the byte lattice with
         exact recomputation inside the guard band; 2 (default): the same screening on a word lattice with
-        fixed-point dp4a dE where a word kernel is instantiated (else like 1).  All decision-identical."""
+        fixed-point dp4a dE and the dense decomposition where a word kernel is instantiated (else like 1).
+        Screened and exact kernels on the same decomposition take identical decisions."""
         check(self.L.brawl_cuda_metropolis_set_mode(self.h, int(dE_mode)))
+
+    def metropolis_set_layout(self, byte_layout_only):
+        """True: never use the word-lattice kernels / dense decomposition (A/B comparisons); False: automatic."""
+        check(self.L.brawl_cuda_metropolis_set_layout(self.h, int(bool(byte_layout_only))))
 
     def metropolis_plan(self, nbr_swap=False):
         o = np.zeros(10, dtype=np.int32)

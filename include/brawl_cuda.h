@@ -129,17 +129,22 @@ int brawl_cuda_metropolis_tune(brawl_cuda_t *h, int box_x, int box_y, int box_z,
  * 1: integer neighbour counts (byte lattice in shared memory) give dE first; any trial whose dE or
  * acceptance test lies within a guard band of a decision boundary is recomputed with the reference's
  * association and decided by it, so accept/reject decisions -- and therefore trajectories -- are identical
- * to mode 0 (needs <= 5 species; otherwise mode 0 is used).  2 (default): the same screening on a word
- * lattice (one 32-bit word per site, fixed-point dp4a dE, ex2.approx acceptance pre-test; bcc 4 shells with
- * 64x64x32 boxes); where no word kernel is instantiated it behaves like mode 1.  Decisions are identical in
- * all three modes; the returned sum of accepted dE is exact to f64 rounding in modes 0/1 and to the
- * fixed-point unit (~1e-11 Ry per accepted swap) in mode 2. */
+ * to mode 0 on the same decomposition (needs <= 5 species; otherwise mode 0 is used).  2 (default): the same
+ * screening on a word lattice (one 32-bit word per site, fixed-point dp4a dE, ex2.approx acceptance pre-test)
+ * with the dense non-interacting-set decomposition (bcc, 4 shells, 64x64x32 boxes); where no word kernel is
+ * instantiated it behaves like mode 1.  Where a word kernel exists, mode 0 runs its EXACT instantiation (same
+ * decomposition, reference association for every trial), so modes 0 and 2 give identical trajectories; mode 1
+ * keeps the byte-lattice decomposition.  The returned sum of accepted dE is exact to f64 rounding in modes 0/1
+ * and to the fixed-point unit (~1e-11 Ry per accepted swap) in mode 2. */
 int brawl_cuda_metropolis_set_mode(brawl_cuda_t *h, int dE_mode);
+/* byte_layout_only != 0: never use the word-lattice kernels and their dense decomposition (A/B comparisons,
+ * tests); 0 (default): automatic. */
+int brawl_cuda_metropolis_set_layout(brawl_cuda_t *h, int byte_layout_only);
 /* Describe the decomposition chosen: out10 = { kind + 16*n_orientations, period Px*10000+Py*100+Pz of the
  * first orientation, margin, box_x, box_y, box_z, max trials per step, boxes per replica, |D| (allowed
  * displacement classes of the first orientation), steps per phase }.  kind: 0 chain kernel, 1 generic box
  * kernel, 2 specialised (compile-time geometry) box kernel, 3 specialised + screened dE, 4 word-lattice
- * screened kernel. */
+ * screened kernel (dense decomposition), 5 word-lattice kernel deciding every trial with the reference association. */
 int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *out10);
 
 /* ---- short-range order ----------------------------------------------------------------------

@@ -1,0 +1,81 @@
+"""Host-side restatement of the dense non-interacting-set decomposition of the word-lattice Metropolis kernel
+(brawl_b200/csrc/word_metropolis.cuh: BrwDenseGeom, brw_make_dense_step and the lane mapping).  CPU only: checks
+the invariant the GPU kernel's exactness rests on -- all 2M sites touched in one step are distinct lattice sites
+inside the active region and NO two of them are neighbours in shells 1-4 of the bcc Hamiltonian
+(reference tables: src/bw_hamiltonian.f90:162-169, 225-230, 286-297, 361-384)."""
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def bcc_offsets(n_shells=4):
+    src = open(os.path.join(ROOT, "brawl_b200", "csrc", "shell_tables.inc")).read()
+    body = re.search(r"brw_bcc_off\[168\]\[3\] = \{(.*?)\};", src, re.S).group(1)
+    offs = [tuple(int(v) for v in t.split(",")) for t in re.findall(r"\{(-?\d+,-?\d+,-?\d+)\}", body)]
+    return offs[: (8, 14, 26, 50)[n_shells - 1]]
+
+
+def dense_step_sites(q1, q2, rot1, rot2, si, swap, BX=64, BY=64, BZ=32, M=4):
+    NI = (BX - 2 * M) // 4
+    HALF = ((BY - 3 * M) // 2) & ~3
+    NJ, NP = HALF // 4, (BZ - 2 * M) // 4
+    NROWS, YU = NJ * NP, M + HALF + M
+
+    def cls(q):
+        return [(q & 1) + 2 * ((q >> 1) & 1), (q & 1) + 2 * ((q >> 2) & 1), (q & 1) + 2 * ((q >> 3) & 1)]
+    o = [cls(q1), cls(q2)]
+    base = {}
+    for h in range(2):
+        ylo = M if h == 0 else YU
+        for sub in range(2):
+            base[(h, sub)] = (M + ((o[h][0] + 2 * sub - M) & 3), ylo + ((o[h][1] + 2 * sub - ylo) & 3),
+                              M + ((o[h][2] + 2 * sub - M) & 3))
+    s1, s2 = [], []
+    for warp in range(min(32, NROWS)):
+        for lane in range(2 * NI):
+            sub = 1 if lane >= NI else 0
+            li = lane - sub * NI
+            r1, r2 = (warp + rot1) % NROWS, (warp + rot2) % NROWS
+            X, Y, Z = base[(0, sub)]
+            s1.append((X + 4 * li, Y + 4 * (r1 % NJ), Z + 4 * (r1 // NJ)))
+            X, Y, Z = base[(1, sub ^ swap)]
+            s2.append((X + 4 * ((li + si) % NI), Y + 4 * (r2 % NJ), Z + 4 * (r2 // NJ)))
+    return s1, s2, (NI, NROWS)
+
+
+def test_dense_step_sites_are_pairwise_non_interacting():
+    offs = bcc_offsets(4)
+    rng = np.random.default_rng(0)
+    BX, BY, BZ, M = 64, 64, 32, 4
+    cases = [(q1, q2, 0, 0, 0, 0) for q1 in range(16) for q2 in range(16)]
+    cases += [tuple(int(v) for v in (rng.integers(16), rng.integers(16), rng.integers(36), rng.integers(36),
+                                     rng.integers(14), rng.integers(2))) for _ in range(150)]
+    for c in cases:
+        s1, s2, (NI, NROWS) = dense_step_sites(*c)
+        assert len(s1) == len(s2) == 896
+        sites = s1 + s2
+        S = set(sites)
+        assert len(S) == len(sites)                                  # all distinct
+        for (x, y, z) in sites:
+            assert (x - z) % 2 == 0 and (y - z) % 2 == 0             # bcc sites
+            assert M <= x < BX - M and M <= y < BY - M and M <= z < BZ - M   # every neighbour is inside the box
+            for d in offs:
+                assert (x + d[0], y + d[1], z + d[2]) not in S       # no two touched sites interact
+
+
+def test_dense_lanes_hit_distinct_banks():
+    """Row pitch 32 words, plane pitch 1024: the 28 active lanes of a warp (14 A sites 2 words apart + 14 B sites, odd
+    word offset) address 28 different shared-memory banks for site 1 and for site 2."""
+    PXP, PLP = 32, 1024
+    rng = np.random.default_rng(1)
+    for _ in range(100):
+        c = tuple(int(v) for v in (rng.integers(16), rng.integers(16), rng.integers(36), rng.integers(36), rng.integers(14),
+                                   rng.integers(2)))
+        s1, s2, _ = dense_step_sites(*c)
+        for sites in (s1, s2):
+            for w in range(32):
+                banks = [((z * PLP + (y >> 1) * PXP + (x >> 1)) & 31) for (x, y, z) in sites[28 * w: 28 * w + 28]]
+                assert len(set(banks)) == 28

@@ -331,9 +331,10 @@ def test_production_conservation_and_energy_bookkeeping(bw, orc, golden):
 
 
 def test_production_planner_variants(bw, orc, golden):
-    """Three valid decompositions of the same lattice: the word-lattice plan (default: box 64x64x32, one period
-    orientation (6,6,4)), rectangular multi-orientation periods on a user box, and cubic periods (test hook).
-    Energy bookkeeping holds for each; rectangular periods expose more simultaneous trials than cubic ones."""
+    """Three valid decompositions of the same lattice: the dense non-interacting-set plan of the word-lattice
+    kernel (default: box 64x64x32, period 4, 896 trials per step), rectangular multi-orientation periods on a
+    user box, and cubic periods (test hook).  Energy bookkeeping holds for each (it would not if two simultaneous
+    trials interacted); rectangular periods expose more simultaneous trials than cubic ones."""
     V = golden["ex_AlTiCrMo_V"][:64]
     sysm = orc.System("bcc", 32, 32, 32, 4, 4, V)
     g = random_config(orc, sysm, 8)
@@ -350,12 +351,71 @@ def test_production_planner_variants(bw, orc, golden):
         # the word kernel sums fixed-point dE (2^-k units, k ~ 37): bookkeeping to ~1e-8 instead of rounding
         tol = 1e-7 if plan["use_box"] == 4 else 1e-10 * abs(e0) + 1e-12
         assert abs((e1 - e0) - dE[0]) < tol
-        assert dev.total_energy()[0] == sysm.total_energy(dev.get_config())
-    assert plans[0]["use_box"] == 4 and plans[0]["P"] == (6, 6, 4) and plans[0]["n_orientations"] == 1
-    assert (plans[0]["box_x"], plans[0]["box_y"], plans[0]["box_z"]) == (64, 64, 32) and plans[0]["trials_per_step"] == 486
+        g1 = dev.get_config()
+        assert dev.total_energy()[0] == sysm.total_energy(g1)
+        assert np.array_equal(np.bincount(g1.ravel(), minlength=5), np.bincount(g.ravel(), minlength=5))
+    assert plans[0]["use_box"] == 4 and plans[0]["P"] == (4, 4, 4) and plans[0]["n_orientations"] == 1
+    assert (plans[0]["box_x"], plans[0]["box_y"], plans[0]["box_z"]) == (64, 64, 32) and plans[0]["trials_per_step"] == 896
     assert plans[2]["P"] == (6, 6, 6) and plans[2]["n_orientations"] == 1
     assert plans[1]["P"][0] * plans[1]["P"][1] * plans[1]["P"][2] < 216 and plans[1]["n_orientations"] == 3
     assert plans[1]["trials_per_step"] > plans[2]["trials_per_step"]
+
+
+def test_dense_decomposition_conservation_exact(bw, orc, golden):
+    """Word-lattice kernel, EXACT instantiation (dE_mode 0: reference association for every trial) on the dense
+    decomposition, 4 and 5 species: the sum of accepted dE equals the change of the oracle's total energy to
+    rounding -- any two interacting simultaneous trials would break it -- and species counts are conserved."""
+    for S, key in ((4, "ex_AlTiCrMo_V"), (5, "ex_AlCrFeCoNi_V")):
+        V = golden[key][: S * S * 4]
+        sysm = orc.System("bcc", 32, 32, 32, S, 4, V)
+        g = random_config(orc, sysm, 21)
+        dev = bw.Device("bcc", 32, 32, 32, S, 4, V)
+        dev.metropolis_set_mode(0)
+        assert dev.metropolis_plan()["use_box"] == 5
+        dev.set_config(g)
+        e0 = sysm.total_energy(g)
+        tot = 0.0
+        for rep in range(2):
+            att, acc, dE = dev.metropolis_run(1.0 / (900.0 * bw.K_B_IN_RY), 10 * sysm.n_atoms, seed=5 + rep)
+            assert att[0] >= 10 * sysm.n_atoms and 0 < acc[0] < att[0]
+            tot += dE[0]
+        g1 = dev.get_config()
+        assert np.array_equal(np.bincount(g1.ravel(), minlength=S + 1), np.bincount(g.ravel(), minlength=S + 1))
+        assert np.array_equal(g1 == 0, g == 0)
+        e1 = sysm.total_energy(g1)
+        assert e1 < e0
+        assert abs((e1 - e0) - tot) < 1e-10 * abs(e1 - e0) + 1e-11, (S, e0, e1, tot)
+
+
+def test_dense_decomposition_statistics(bw, orc, golden):
+    """Equilibrium energy per atom and first/second-shell pair counts of the dense-set sampler (word kernel) agree
+    with the period-P sublattice sampler (byte kernels, itself checked against the oracle's sequential sampler in
+    test_production_statistics_match_oracle).  Tolerance: 5 standard errors from block averages + 2e-6 Ry."""
+    V = golden["ex_AlTiCrMo_V"][:64]
+    n, T = 32, 1200.0
+    sysm = orc.System("bcc", n, n, n, 4, 4, V)
+    g = random_config(orc, sysm, 3)
+    N = sysm.n_atoms
+    stats = []
+    for byte_layout in (False, True):
+        dev = bw.Device("bcc", n, n, n, 4, 4, V)
+        dev.metropolis_set_layout(byte_layout)
+        assert dev.metropolis_plan()["use_box"] == (3 if byte_layout else 4)
+        dev.set_config(g)
+        beta = 1.0 / (T * bw.K_B_IN_RY)
+        dev.metropolis_run(beta, 150 * N, seed=11)                # equilibrate
+        es, cs = [], []
+        for k in range(60):
+            dev.metropolis_run(beta, 4 * N, seed=100 + k)
+            es.append(dev.total_energy()[0] / N)
+            cnt, spc = dev.radial_counts(3)
+            cs.append(cnt[1:3].astype(np.float64) / N)
+        es, cs = np.array(es), np.array(cs)
+        blocks = es.reshape(6, 10).mean(axis=1)
+        stats.append((es.mean(), blocks.std(ddof=1) / np.sqrt(6), cs.mean(axis=0), cs.reshape(6, 10, *cs.shape[1:]).mean(axis=1).std(axis=0, ddof=1) / np.sqrt(6)))
+    (e0, s0, c0, sc0), (e1, s1, c1, sc1) = stats
+    assert abs(e0 - e1) < 5 * np.hypot(s0, s1) + 2e-6, (e0, e1, s0, s1)
+    assert np.all(np.abs(c0 - c1) < 5 * np.hypot(sc0, sc1) + 2e-3), (c0, c1)
 
 
 def test_production_is_deterministic(bw, orc, golden):
@@ -390,19 +450,18 @@ def test_specialised_kernel_equals_generic_kernel(bw, orc, golden, lattice, n, S
     res = []
     for generic in (False, True):
         dev = bw.Device(lattice, n, n, n, S, shells, V)
+        dev.metropolis_set_layout(True)                 # byte-lattice kernels (the word kernel has its own decomposition)
         if generic:
             dev.metropolis_tune((0, 0, 0), -1)          # automatic steps, generic kernel forced
         plan = dev.metropolis_plan()
-        word = lattice == "bcc" and shells == 4            # a word-lattice kernel exists for this case
-        assert plan["use_box"] == (1 if generic else 4 if word else 3), plan
+        assert plan["use_box"] == (1 if generic else 3), plan
         dev.set_config(g)
         out = dev.metropolis_run(1.0 / (700.0 * bw.K_B_IN_RY), 3 * int(mask.sum()), seed=77)
         res.append((dev.get_config().copy(), out))
     assert np.array_equal(res[0][0], res[1][0])
     assert np.array_equal(res[0][1][0], res[1][1][0]) and np.array_equal(res[0][1][1], res[1][1][1])
-    # the specialised kernels screen with count-based dE (same decisions; the dE sum differs in the last bits,
-    # or by ~1e-8 for the word kernel's fixed-point dE)
-    assert np.allclose(res[0][1][2], res[1][1][2], rtol=0, atol=1e-6 if word else 1e-9)
+    # the specialised kernel screens with count-based dE (same decisions, last-bit different dE sum)
+    assert np.allclose(res[0][1][2], res[1][1][2], rtol=0, atol=1e-9)
 
 
 @pytest.mark.parametrize("lattice,n,S,shells,key,T", [("bcc", 32, 4, 4, "ex_AlTiCrMo_V", 300.0), ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", 2000.0),
@@ -422,19 +481,25 @@ def test_screened_kernel_trajectory_identical(bw, orc, golden, lattice, n, S, sh
     g[mask] = rng.integers(1, S + 1, size=int(mask.sum()))
     res = []
     word = lattice == "bcc" and shells == 4
-    for mode in (0, 1, 2):
+    # (layout, mode, expected kernel kind); runs with the same layout share one decomposition
+    runs = [(True, 0, 2), (True, 1, 3)] + ([(False, 0, 5), (False, 2, 4)] if word else [(False, 2, 3)])
+    res = {}
+    for byte_layout, mode, kind in runs:
         dev = bw.Device(lattice, n, n, n, S, shells, V)
+        dev.metropolis_set_layout(byte_layout)
         dev.metropolis_set_mode(mode)
-        assert dev.metropolis_plan()["use_box"] == (2, 3, 4 if word else 3)[mode]
+        assert dev.metropolis_plan()["use_box"] == kind
         dev.set_config(g)
         out = dev.metropolis_run(1.0 / (T * bw.K_B_IN_RY), 12 * int(mask.sum()), seed=99)
-        res.append((dev.get_config().copy(), out, dev.total_energy()[0]))
-    for m in (1, 2):
-        assert np.array_equal(res[0][0], res[m][0])
-        assert np.array_equal(res[0][1][0], res[m][1][0]) and np.array_equal(res[0][1][1], res[m][1][1])
-        assert res[0][2] == res[m][2]
+        res[(byte_layout, mode)] = (dev.get_config().copy(), out, dev.total_energy()[0])
+    pairs = [((True, 0), (True, 1), 1e-9)] + ([((False, 0), (False, 2), 1e-6)] if word else [((True, 1), (False, 2), 1e-9)])
+    for ka, kb, tol in pairs:
+        a, b = res[ka], res[kb]
+        assert np.array_equal(a[0], b[0])
+        assert np.array_equal(a[1][0], b[1][0]) and np.array_equal(a[1][1], b[1][1])
+        assert a[2] == b[2]
         # sum of accepted dE: same to rounding (word kernel: fixed-point dE, ~1e-11 per accepted swap)
-        assert abs(res[0][1][2][0] - res[m][1][2][0]) < (1e-6 if (m == 2 and word) else 1e-9)
+        assert abs(a[1][2][0] - b[1][2][0]) < tol
 
 
 def test_production_limits(bw, orc, golden):

@@ -1,3 +1,5 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-ncu --set full --clock-control none --import-source on -k regex:word_kernel -s 6 -c 1 -f -o gpurun_out/prof_r01_word python bench.py --steps 1 --warmup 3 --sweeps 16 --no-cpu-baseline > gpurun_out/ncu_word.log 2>&1
-tail -3 gpurun_out/ncu_word.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -25
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r01_dense.json 2> gpurun_out/bench_dense.err
+tail -c 400 gpurun_out/bench_dense.err
+python -c "
+import json;d=json.load(open('gpurun_out/bench_r01_dense.json'));print(d['value'],d['e2e']['value'],d['roofline']['frac'],d['config']['decomposition'],d['config']['acceptance'],d['config']['energy_per_atom_start_end_Ry'])"
