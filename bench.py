@@ -329,10 +329,13 @@ def main():
                    "Metropolis whole-lattice swaps, T ladder 3000->100 K" % R)
         achieved = per_launch_trials * B_ALG / (per_launch_ms * 1e-3) / 1e9
         traffic = None
+        smem_pipe = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("dram_bytes_per_launch")
+                smem_pipe = tj.get("shared_memory_pipe")
             except Exception:
                 traffic = None
         out = {
@@ -359,7 +362,9 @@ def main():
                          "traffic": traffic, "kernel": {5: "brw_box_metropolis_word_kernel<1,4,32,32,32,4,32,1024,4,true>", 4: "brw_box_metropolis_word_kernel<1,4,32,32,32,4,32,1024,4,false>", 3: "brw_box_metropolis_fast_kernel<1,4,32,32,true>", 2: "brw_box_metropolis_fast_kernel<1,4,32,32,false>", 1: "brw_box_metropolis_kernel<0>", 0: "brw_chain_metropolis_kernel"}[plan["use_box"]],
                          "algorithmic_bytes_per_attempt": B_ALG, "attempts_per_launch": per_launch_trials,
                          "ms_per_launch": per_launch_ms, "peak_source": peak_src,
-                         "note": "lattice is L2/shared-memory resident by design; see DESIGN.md"},
+                         "shared_memory_pipe_ncu": smem_pipe,
+                         "note": "lattice is L2/shared-memory resident by design: the binding resource is the shared-memory "
+                                 "(LSU) pipe, see shared_memory_pipe_ncu and DESIGN.md"},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
