@@ -359,7 +359,7 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": {5: "brw_box_metropolis_word_kernel<1,4,32,32,32,4,32,1024,4,true>", 4: "brw_box_metropolis_word_kernel<1,4,32,32,32,4,32,1024,4,false>", 3: "brw_box_metropolis_fast_kernel<1,4,32,32,true>", 2: "brw_box_metropolis_fast_kernel<1,4,32,32,false>", 1: "brw_box_metropolis_kernel<0>", 0: "brw_chain_metropolis_kernel"}[plan["use_box"]],
+                         "traffic": traffic, "kernel": {5: "brw_box_metropolis_word_kernel<1,4,32,32,%d,4,32,1024,4,true>" % plan["box_z"], 4: "brw_box_metropolis_word_kernel<1,4,32,32,%d,4,32,1024,4,false>" % plan["box_z"], 3: "brw_box_metropolis_fast_kernel<1,4,32,32,true>", 2: "brw_box_metropolis_fast_kernel<1,4,32,32,false>", 1: "brw_box_metropolis_kernel<0>", 0: "brw_chain_metropolis_kernel"}[plan["use_box"]],
                          "algorithmic_bytes_per_attempt": B_ALG, "attempts_per_launch": per_launch_trials,
                          "ms_per_launch": per_launch_ms, "peak_source": peak_src,
                          "shared_memory_pipe_ncu": smem_pipe,

@@ -385,6 +385,9 @@ static const BrwWordEntry brw_word_table[] = {
     // bcc, 4 shells, box 64x64x32 (doubled-grid units): 32 warps x 28 = 896 trials per step
     {1, 4, 32, 32, 32, 4, 32, 1024, 4, brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, 4, false>,
      brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, 4, true>},
+    // box 64x64x28: 30 warps x 28 = 840 trials per step; 9 z-layers of a 256-plane lattice give 144 boxes (of 148 SMs)
+    {1, 4, 32, 32, 28, 4, 32, 1024, 4, brw_box_metropolis_word_kernel<1, 4, 32, 32, 28, 4, 32, 1024, 4, false>,
+     brw_box_metropolis_word_kernel<1, 4, 32, 32, 28, 4, 32, 1024, 4, true>},
 };
 
 // launch helper for the warp-per-walker kernels: layout + opt-in shared memory
@@ -491,8 +494,11 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
   // byte-lattice path)
   const BrwWordEntry *we = nullptr;
   if (feasible && !nbr_swap && !h->cubic_period_only && !h->disable_fast && !h->byte_layout && h->dE_mode != 1 && g.S <= 5) {
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
+    double best_rate = 0.0;
     for (const BrwWordEntry &e : brw_word_table) {
-      if (we || e.lat != g.lattice || e.nsh != g.n_shells || e.margin < rmax + 1) continue;
+      if (e.lat != g.lattice || e.nsh != g.n_shells || e.margin < rmax + 1) continue;
       // S_o = o + {(0,0,0),(2,2,2)} + 4Z^3 must be an independent set of the interaction graph
       bool independent = true;
       for (int k = 0; k < g.ztot; k++) {
@@ -500,16 +506,24 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
         if ((a == 0 && b == 0 && c == 0) || (a == 2 && b == 2 && c == 2)) independent = false;
       }
       if (!independent) continue;
-      int Bw[3];
-      const int P4[3] = {4, 4, 4};
-      const size_t fixed_w = 32 * 1024;
       const int Be[3] = {e.bxc << g.xs, e.byc << g.ys, e.bzc};
-      const int st = size_box(4.0 * e.plp / (double)(e.bxc * e.byc), fixed_w, 4, P4, Bw, Be);
-      if (st != 0) continue;       // (an invalid user box is reported by the byte-lattice sizing below)
-      if ((Bw[0] >> g.xs) != e.bxc || (Bw[1] >> g.ys) != e.byc || Bw[2] != e.bzc) continue;
-      we = &e;
-      for (int d = 0; d < 3; d++) B[d] = Bw[d];
-      m = e.margin;
+      if (h->tune_box[0] > 0) {          // user box: must be exactly this entry's box
+        if (h->tune_box[0] != Be[0] || h->tune_box[1] != Be[1] || h->tune_box[2] != Be[2]) continue;
+      }
+      // boxes tile x and y; along z they need not (the slab left over is visited in later phases: the origin is random)
+      if (g.gx % Be[0] || g.gy % Be[1] || Be[2] > g.gz) continue;
+      const long n_boxes = (long)(g.gx / Be[0]) * (g.gy / Be[1]) * (g.gz / Be[2]) * h->n_replicas;
+      const int rows = std::min(32, ((((Be[1] - 3 * e.margin) / 2) & ~3) / 4) * ((Be[2] - 2 * e.margin) / 4));
+      const long trials_box = (long)rows * 2 * ((Be[0] - 2 * e.margin) / 4);
+      // one CTA per SM; a step costs ~rows warp-gathers on the shared-memory pipe
+      const long waves = (n_boxes + n_sm - 1) / n_sm;
+      double rate = (double)n_boxes * trials_box / ((double)waves * rows);
+      if (g.gz % Be[2] == 0) rate *= 1.02;                       // prefer exact tilings when (nearly) equal
+      if (rate > best_rate) { best_rate = rate; we = &e; }
+    }
+    if (we) {
+      B[0] = we->bxc << g.xs; B[1] = we->byc << g.ys; B[2] = we->bzc;
+      m = we->margin;
     }
   }
   if (feasible && !we) {
@@ -680,7 +694,7 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       pl->screened = h->dE_mode != 0; pl->word = true;
       pl->fast_smem = blob.size() * sizeof(int) + 32 * 8 + 2 * (size_t)p.mode[0].A[1] * p.mode[0].A[2] * 4 + 16 +
                       (size_t)p.steps * 32 + (size_t)we->plp * p.bzc * 4;
-      pl->threads = 1024;
+      pl->threads = 32 * std::min(32, p.mode[0].A[1] * p.mode[0].A[2]);
       BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)pl->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
     }
     pl->use_box = true;

@@ -1,6 +1,5 @@
-for v in BASE ROWTAB F2I32 BOTH; do
-  cp brawl_b200/libbrawl_cuda_$v.so brawl_b200/libbrawl_cuda.so
-  python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ab_$v.json 2> gpurun_out/ab.err
-  python -c "
-import json;d=json.load(open('gpurun_out/ab_$v.json'));print('$v', d['value'],d['e2e']['value'],d['config']['acceptance'],d['config']['energy_per_atom_start_end_Ry'][1])"
-done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r01_dense3.json 2> gpurun_out/bench_dense.err
+tail -c 400 gpurun_out/bench_dense.err
+python -c "
+import json;d=json.load(open('gpurun_out/bench_r01_dense3.json'));print(d['value'],d['e2e']['value'],d['roofline']['frac'],d['config']['decomposition'],d['config']['acceptance'],d['config']['energy_per_atom_start_end_Ry'])"
