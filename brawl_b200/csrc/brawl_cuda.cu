@@ -380,14 +380,17 @@ static const BrwFastEntry brw_fast_table[] = {
 };
 
 // Word-lattice kernels with the dense decomposition (word_metropolis.cuh): fixed box and margin per entry.
+#ifndef BRW_PAIRW
+#define BRW_PAIRW true      // pair words (two sites per LDS.32); false: one-hot byte word per site
+#endif
 struct BrwWordEntry { int lat, nsh, bxc, byc, bzc, margin, pxp, plp, nlimb; BrwFastKernel fn, fn_exact; };
 static const BrwWordEntry brw_word_table[] = {
     // bcc, 4 shells, box 64x64x32 (doubled-grid units): 32 warps x 28 = 896 trials per step
-    {1, 4, 32, 32, 32, 4, 32, 1024, 4, brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, 4, false>,
-     brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, 4, true>},
+    {1, 4, 32, 32, 32, 4, 32, 1024, 4, brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, 4, false, BRW_PAIRW>,
+     brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, 4, true, BRW_PAIRW>},
     // box 64x64x28: 30 warps x 28 = 840 trials per step; 9 z-layers of a 256-plane lattice give 144 boxes (of 148 SMs)
-    {1, 4, 32, 32, 28, 4, 32, 1024, 4, brw_box_metropolis_word_kernel<1, 4, 32, 32, 28, 4, 32, 1024, 4, false>,
-     brw_box_metropolis_word_kernel<1, 4, 32, 32, 28, 4, 32, 1024, 4, true>},
+    {1, 4, 32, 32, 28, 4, 32, 1024, 4, brw_box_metropolis_word_kernel<1, 4, 32, 32, 28, 4, 32, 1024, 4, false, BRW_PAIRW>,
+     brw_box_metropolis_word_kernel<1, 4, 32, 32, 28, 4, 32, 1024, 4, true, BRW_PAIRW>},
 };
 
 // launch helper for the warp-per-walker kernels: layout + opt-in shared memory

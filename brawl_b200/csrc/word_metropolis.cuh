@@ -73,12 +73,25 @@ __device__ __forceinline__ int brw_word_code(uint32_t w) { return __clz((int)w) 
 __device__ __forceinline__ int brw_code_species(int code) { return code == 4 ? 4 : 3 - code; }
 __host__ __device__ __forceinline__ uint32_t brw_species_word(int s) { return s < 4 ? 1u << (8 * s) : 0u; }
 
+// ---- pair words (PAIRW): W[c] = nibbles(site c) | nibbles(site c+1) << 16, nibbles = 1 << 4*species (species 4: 0).
+// One LDS.32 returns two x-adjacent sites for ANY c, so 30 loads cover the 50 neighbours (pair_gather.inc, generated
+// by tools/gen_pair_gather.py; its plan is re-derived and emulated on the CPU in tests/test_dense_plan.py).
+__host__ __device__ __forceinline__ uint32_t brw_species_nibbles(int s) { return s < 4 ? 1u << (4 * s) : 0u; }
+// species code of the low lane: 3,2,1,0 for species 0..3 and 4 for species 4 (same codes as brw_word_code)
+__device__ __forceinline__ int brw_pair_code(uint32_t w) { return (__clz((int)(w & 0xFFFFu)) - 16) >> 2; }
+// four 4-bit fields of the low 16 bits -> four 8-bit fields
+__device__ __forceinline__ uint32_t brw_nib2byte(uint32_t x) {
+  const uint32_t t = __byte_perm(x, 0u, 0x4140);          // [b0, 0, b1, 0]
+  return (t | (t << 4)) & 0x0F0F0F0Fu;
+}
+#include "pair_gather.inc"
+
 // box <-> global copy, one warp per compact-x row of PX sites.  STORE=false: global bytes -> shared words.
-template <int LAT, int PX, int PY, int PXP, int PLP, bool STORE>
+template <int LAT, int PX, int PY, int PXP, int PLP, bool STORE, bool PAIRW>
 __device__ __forceinline__ void brw_wbox_copy(const BrwGeom &g, uint8_t *L, uint32_t *wbox, int n_rows, int ox, int oy,
                                               int oz) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  static_assert(PX <= 32, "one warp covers a row");
+  static_assert(PX <= 32 && (!PAIRW || PX == 32), "one warp covers a row");
   const int oxc = ox >> 1;
 #pragma unroll 8
   for (int r = warp; r < n_rows; r += nwarps) {
@@ -90,8 +103,18 @@ __device__ __forceinline__ void brw_wbox_copy(const BrwGeom &g, uint8_t *L, uint
       int gxc = oxc + lane; if (gxc >= g.cx) gxc -= g.cx; if (gxc >= g.cx) gxc -= g.cx;
       const long gi = ((long)gzz * g.cy + (gyy >> g.ys)) * g.cx + gxc;
       uint32_t *w = wbox + lz * PLP + lyc * PXP + lane;
-      if (STORE) L[gi] = (uint8_t)brw_code_species(brw_word_code(*w));
-      else *w = brw_species_word(L[gi]);
+      if (PAIRW) {
+        if (STORE) L[gi] = (uint8_t)brw_code_species(brw_pair_code(*w));
+        else {
+          const uint32_t v = brw_species_nibbles(L[gi]);
+          uint32_t hi = __shfl_down_sync(0xffffffffu, v, 1);    // the x-neighbour's nibbles (PX == 32: all lanes active)
+          if (lane == 31) hi = 0u;                              // beyond the row: never a useful lane (margin)
+          *w = v | (hi << 16);
+        }
+      } else {
+        if (STORE) L[gi] = (uint8_t)brw_code_species(brw_word_code(*w));
+        else *w = brw_species_word(L[gi]);
+      }
     }
   }
 }
@@ -154,7 +177,7 @@ __device__ __forceinline__ void brw_make_dense_step(uint32_t k0, uint32_t k1, ui
   out->flags = (int)(q1 & 1u) | (int)((q2 & 1u) << 1) | (int)(((r.w >> 16) & 1u) << 2);
 }
 
-template <int LAT, int NSH, int PX, int PY, int PZ, int MARGIN, int PXP, int PLP, int NLIMB, bool EXACT>
+template <int LAT, int NSH, int PX, int PY, int PZ, int MARGIN, int PXP, int PLP, int NLIMB, bool EXACT, bool PAIRW>
 __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
     BrwGeom g, BrwBoxParams p, uint8_t *__restrict__ lat, const double *__restrict__ beta,
     const double *__restrict__ tab_g, const int4 *__restrict__ classes, const int4 *__restrict__ disp, uint32_t k0,
@@ -200,7 +223,7 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
   }
   for (int st = tid; st < p.steps; st += blockDim.x)
     brw_make_dense_step<2 * PX, 2 * PY, PZ, MARGIN, PXP, PLP>(k0, k1, (uint32_t)st, box_id, phase_lo, &sp[st]);
-  brw_wbox_copy<LAT, PX, PY, PXP, PLP, false>(g, L, wbox, PY * p.bzc, ox, oy, oz);
+  brw_wbox_copy<LAT, PX, PY, PXP, PLP, false, PAIRW>(g, L, wbox, PY * p.bzc, ox, oy, oz);
   __syncthreads();
 
   const double my_beta = beta[replica];
@@ -224,21 +247,28 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
       const int sub2 = sub ^ ((q.flags >> 2) & 1);
       uint32_t *w1 = wbox + (sub ? q.c1[1] : q.c1[0]) + 2 * li + rowoff[warp + q.rot1];
       uint32_t *w2 = wbox + (sub2 ? q.c2[1] : q.c2[0]) + 2 * i2 + rowoff[warp + q.rot2];
-      const uint32_t wa = *w1, wb = *w2;
+      const uint32_t wa = PAIRW ? (*w1 & 0xFFFFu) : *w1, wb = PAIRW ? (*w2 & 0xFFFFu) : *w2;
       n_att++;
       if ((step & 3) == 0) rnd = brw_philox((uint32_t)tid, (uint32_t)step, box_id, phase_lo, k0, k1);
       if (wa != wb) {
         const uint32_t w = (step & 3) == 0 ? rnd.x : (step & 3) == 1 ? rnd.y : (step & 3) == 2 ? rnd.z : rnd.w;
         const double u = brw_u01(w);
-        const int ca = brw_word_code(wa), cb = brw_word_code(wb);
+        const int ca = PAIRW ? brw_pair_code(wa) : brw_word_code(wa), cb = PAIRW ? brw_pair_code(wb) : brw_word_code(wb);
         bool decided = false, accept = false;
         double dE = 0.0;
         if (!EXACT) {
           uint32_t C1[NSH], C2[NSH];
-          if (q.flags & 1) brw_wsum_shells<LAT, NSH, PXP, PLP, 1, 0>(w1, C1);
-          else brw_wsum_shells<LAT, NSH, PXP, PLP, 0, 0>(w1, C1);
-          if (q.flags & 2) brw_wsum_shells<LAT, NSH, PXP, PLP, 1, 0>(w2, C2);
-          else brw_wsum_shells<LAT, NSH, PXP, PLP, 0, 0>(w2, C2);
+          if (PAIRW) {
+            if (q.flags & 1) BrwPairGatherBcc<NSH, PXP, PLP, 1>::run(w1, C1);
+            else BrwPairGatherBcc<NSH, PXP, PLP, 0>::run(w1, C1);
+            if (q.flags & 2) BrwPairGatherBcc<NSH, PXP, PLP, 1>::run(w2, C2);
+            else BrwPairGatherBcc<NSH, PXP, PLP, 0>::run(w2, C2);
+          } else {
+            if (q.flags & 1) brw_wsum_shells<LAT, NSH, PXP, PLP, 1, 0>(w1, C1);
+            else brw_wsum_shells<LAT, NSH, PXP, PLP, 0, 0>(w1, C1);
+            if (q.flags & 2) brw_wsum_shells<LAT, NSH, PXP, PLP, 1, 0>(w2, C2);
+            else brw_wsum_shells<LAT, NSH, PXP, PLP, 0, 0>(w2, C2);
+          }
           const int2 *row = reinterpret_cast<const int2 *>(urow) + (ca * row_mul + cb);
           int Sk[NLIMB];
 #pragma unroll
@@ -277,8 +307,8 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
             const int end = g.shell_end[n];
 #pragma unroll 1
             for (; k < end; k++) {
-              const int s1 = brw_code_species(brw_word_code(w1[off1[k]]));
-              const int s2 = brw_code_species(brw_word_code(w2[off2[k]]));
+              const int s1 = brw_code_species(PAIRW ? brw_pair_code(w1[off1[k]]) : brw_word_code(w1[off1[k]]));
+              const int s2 = brw_code_species(PAIRW ? brw_pair_code(w2[off2[k]]) : brw_word_code(w2[off2[k]]));
               e1a = __dadd_rn(e1a, Vn[s1 * S + sa]); e1b = __dadd_rn(e1b, Vn[s1 * S + sb]);
               e2b = __dadd_rn(e2b, Vn[s2 * S + sb]); e2a = __dadd_rn(e2a, Vn[s2 * S + sa]);
             }
@@ -291,13 +321,21 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
           accept = dE < 0.0;                                     // :796
           if (!accept) accept = u < exp(-my_beta * dE);          // :802
         }
-        if (accept) { *w1 = wb; *w2 = wa; n_acc++; dE_sum += dE; }
+        if (accept) {
+          if (PAIRW) {
+            // a site's nibbles live in the low half of its own word and in the high half of its left neighbour's
+            uint16_t *h1 = reinterpret_cast<uint16_t *>(w1), *h2 = reinterpret_cast<uint16_t *>(w2);
+            h1[0] = (uint16_t)wb; h1[-1] = (uint16_t)wb;
+            h2[0] = (uint16_t)wa; h2[-1] = (uint16_t)wa;
+          } else { *w1 = wb; *w2 = wa; }
+          n_acc++; dE_sum += dE;
+        }
       } else n_acc++;                                            // :774-777
     }
     __syncthreads();
   }
 
-  brw_wbox_copy<LAT, PX, PY, PXP, PLP, true>(g, L, wbox, PY * p.bzc, ox, oy, oz);
+  brw_wbox_copy<LAT, PX, PY, PXP, PLP, true, PAIRW>(g, L, wbox, PY * p.bzc, ox, oy, oz);
   for (int o = 16; o > 0; o >>= 1) {
     n_att += __shfl_down_sync(0xffffffffu, n_att, o);
     n_acc += __shfl_down_sync(0xffffffffu, n_acc, o);

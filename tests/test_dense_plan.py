@@ -79,3 +79,38 @@ def test_dense_lanes_hit_distinct_banks():
             for w in range(32):
                 banks = [((z * PLP + (y >> 1) * PXP + (x >> 1)) & 31) for (x, y, z) in sites[28 * w: 28 * w + 28]]
                 assert len(set(banks)) == 28
+
+
+def test_pair_word_gather_plan_counts_every_neighbour_once():
+    """tools/gen_pair_gather.py (the generator of brawl_b200/csrc/pair_gather.inc): emulate the pair-word lattice
+    W[c] = nibbles(c) | nibbles(c+1) << 16, the 30 loads, the nibble accumulators and the nibble->byte expansion on a
+    random configuration and compare with a direct count of every shell's neighbours per species."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_pair_gather", os.path.join(ROOT, "tools", "gen_pair_gather.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    rng = np.random.default_rng(5)
+    PX, PY, PZ = 32, 32, 12
+    spec_c = rng.integers(0, 5, size=(PZ, PY, PX))                       # species 0..4 on the compact box
+    nib = np.where(spec_c < 4, 1 << (4 * np.minimum(spec_c, 3)), 0).astype(np.uint64)
+    W = nib.copy()
+    W[:, :, :-1] |= nib[:, :, 1:] << np.uint64(16)
+
+    def nib2byte(x):
+        x = int(x) & 0xFFFF
+        return sum(((x >> (4 * k)) & 15) << (8 * k) for k in range(4))
+    offs = gen.bcc_offsets(4)
+    for par in (0, 1):
+        names, groups = gen.build(4, par)
+        assert sum(len(o) for _, _, o in names) == 30
+        for _ in range(40):
+            zc, yc, xc = (int(v) for v in (rng.integers(4, PZ - 4), rng.integers(4, PY - 4), rng.integers(4, PX - 4)))
+            acc = {nm: sum(int(W[zc + dz, yc + dyc, xc + dxc]) for dz, dyc, dxc in o) & 0xFFFFFFFF for nm, _, o in names}
+            C = [sum(nib2byte(sum((acc[nm] >> (16 * lane)) for nm, lane in g)) for g in gs) for gs in groups]
+            want = [[0] * 4 for _ in range(4)]
+            for (dx, dy, dz), n in offs:
+                s = spec_c[zc + dz, yc + (par + dy) // 2, xc + (par + dx) // 2]
+                if s < 4:
+                    want[n][s] += 1
+            got = [[(C[n] >> (8 * s)) & 255 for s in range(4)] for n in range(4)]
+            assert got == want, (par, got, want)
