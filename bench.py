@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--box", default="", help="override box extents, e.g. 64,64,32")
     ap.add_argument("--steps-per-phase", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layout", type=int, default=0, choices=[0, 1, 2],
+                    help="0 automatic, 1 byte-lattice kernels only, 2 word kernels without the warp-group split (A/B runs)")
     ap.add_argument("--n-cells", type=int, default=N_CELLS)
     ap.add_argument("--workload", default="chain", choices=["chain", "replicas"],
                     help="chain: BASELINE configs[1] (headline); replicas: configs[4], R x 32^3 bcc AlCrFeCoNi per GPU")
@@ -231,6 +233,8 @@ def main():
     N = 2 * n ** 3
     dev = brawl_b200.Device("bcc", n, n, n, S, 4, V, device=local_rank, n_replicas=R)
     dev.metropolis_set_mode(args.dE_mode)
+    if args.layout:
+        dev.metropolis_set_layout(args.layout)
     stream = torch.cuda.Stream()            # non-default stream shared by torch events and the library
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
@@ -359,7 +363,7 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": {5: "brw_box_metropolis_word_kernel<1,4,32,32,%d,4,32,1024,4,true>" % plan["box_z"], 4: "brw_box_metropolis_word_kernel<1,4,32,32,%d,4,32,1024,4,false>" % plan["box_z"], 3: "brw_box_metropolis_fast_kernel<1,4,32,32,true>", 2: "brw_box_metropolis_fast_kernel<1,4,32,32,false>", 1: "brw_box_metropolis_kernel<0>", 0: "brw_chain_metropolis_kernel"}[plan["use_box"]],
+                         "traffic": traffic, "kernel": {5: "brw_box_metropolis_word_kernel<1,4,32,32,%d,4,32,1024,4,true,true,%s>" % (plan["box_z"] + 4 * (plan["warp_groups"] - 1), "true" if plan["warp_groups"] == 2 else "false"), 4: "brw_box_metropolis_word_kernel<1,4,32,32,%d,4,32,1024,4,false,true,%s>" % (plan["box_z"] + 4 * (plan["warp_groups"] - 1), "true" if plan["warp_groups"] == 2 else "false"), 3: "brw_box_metropolis_fast_kernel<1,4,32,32,true>", 2: "brw_box_metropolis_fast_kernel<1,4,32,32,false>", 1: "brw_box_metropolis_kernel<0>", 0: "brw_chain_metropolis_kernel"}[plan["use_box"]],
                          "algorithmic_bytes_per_attempt": B_ALG, "attempts_per_launch": per_launch_trials,
                          "ms_per_launch": per_launch_ms, "peak_source": peak_src,
                          "shared_memory_pipe_ncu": smem_pipe,

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbrawl_cuda.so")
+LIB_PATH = os.environ.get("BRAWL_CUDA_LIB") or os.path.join(HERE, "libbrawl_cuda.so")   # override: A/B builds of the same ABI
 
 
 class BrawlCudaError(RuntimeError):

@@ -212,6 +212,7 @@ struct brawl_cuda_ctx {
   int last_plan;
   int tune_box[3], tune_steps, disable_fast, cubic_period_only, last_launches;
   int dE_mode;                 // 0: reference association for every trial; 1: screened, byte lattice; 2: screened, word lattice (default)
+  int word_split;              // 1 (default): the planner may pick the two-warp-group (SPLIT) word kernels
   int byte_layout;             // 1: never use the word-lattice kernels / dense decomposition (test hook, A/B comparisons)
 };
 

@@ -136,6 +136,7 @@ extern "C" int brawl_cuda_create(int lattice, int n1, int n2, int n3, int S, int
   h->grid_cells = (int64_t)g.gx * g.gy * g.gz;
   h->tune_box[0] = h->tune_box[1] = h->tune_box[2] = 0; h->tune_steps = 0;
   h->dE_mode = 2;
+  h->word_split = 1;
 #define BRW_CREATE_CUDA(x) do { if (brw_cuda_check((x), #x)) { brawl_cuda_destroy(h); return 1; } } while (0)
   BRW_CREATE_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
@@ -380,17 +381,26 @@ static const BrwFastEntry brw_fast_table[] = {
 };
 
 // Word-lattice kernels with the dense decomposition (word_metropolis.cuh): fixed box and margin per entry.
+#ifndef BRW_NLIMB
+#define BRW_NLIMB 4         // signed 8-bit digits of the fixed-point table (word_metropolis.cuh)
+#endif
 #ifndef BRW_PAIRW
 #define BRW_PAIRW true      // pair words (two sites per LDS.32); false: one-hot byte word per site
 #endif
-struct BrwWordEntry { int lat, nsh, bxc, byc, bzc, margin, pxp, plp, nlimb; BrwFastKernel fn, fn_exact; };
+// pitchz < bzc: consecutive z layers share their frozen margin planes (box extent bzc, layer pitch pitchz = bzc - margin);
+// split: two independent warp groups per CTA on disjoint z zones (word_metropolis.cuh, SPLIT)
+struct BrwWordEntry { int lat, nsh, bxc, byc, bzc, margin, pxp, plp, nlimb; BrwFastKernel fn, fn_exact; int pitchz; bool split; };
 static const BrwWordEntry brw_word_table[] = {
     // bcc, 4 shells, box 64x64x32 (doubled-grid units): 32 warps x 28 = 896 trials per step
-    {1, 4, 32, 32, 32, 4, 32, 1024, 4, brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, 4, false, BRW_PAIRW>,
-     brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, 4, true, BRW_PAIRW>},
+    {1, 4, 32, 32, 32, 4, 32, 1024, BRW_NLIMB, brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, BRW_NLIMB, false, BRW_PAIRW>,
+     brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, BRW_NLIMB, true, BRW_PAIRW>, 32, false},
     // box 64x64x28: 30 warps x 28 = 840 trials per step; 9 z-layers of a 256-plane lattice give 144 boxes (of 148 SMs)
-    {1, 4, 32, 32, 28, 4, 32, 1024, 4, brw_box_metropolis_word_kernel<1, 4, 32, 32, 28, 4, 32, 1024, 4, false, BRW_PAIRW>,
-     brw_box_metropolis_word_kernel<1, 4, 32, 32, 28, 4, 32, 1024, 4, true, BRW_PAIRW>},
+    {1, 4, 32, 32, 28, 4, 32, 1024, BRW_NLIMB, brw_box_metropolis_word_kernel<1, 4, 32, 32, 28, 4, 32, 1024, BRW_NLIMB, false, BRW_PAIRW>,
+     brw_box_metropolis_word_kernel<1, 4, 32, 32, 28, 4, 32, 1024, BRW_NLIMB, true, BRW_PAIRW>, 28, false},
+    // box 64x64x32 at z pitch 28 (shared margin planes), two warp groups of 12 + 18 warps on z planes {0,1} / {3,4,5}:
+    // 840 trials per step like the 64x64x28 box, but the groups' gather and arithmetic phases overlap
+    {1, 4, 32, 32, 32, 4, 32, 1024, BRW_NLIMB, brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, BRW_NLIMB, false, BRW_PAIRW, true>,
+     brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, BRW_NLIMB, true, BRW_PAIRW, true>, 28, true},
 };
 
 // launch helper for the warp-per-walker kernels: layout + opt-in shared memory
@@ -510,22 +520,26 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       }
       if (!independent) continue;
       const int Be[3] = {e.bxc << g.xs, e.byc << g.ys, e.bzc};
-      if (h->tune_box[0] > 0) {          // user box: must be exactly this entry's box
-        if (h->tune_box[0] != Be[0] || h->tune_box[1] != Be[1] || h->tune_box[2] != Be[2]) continue;
-      }
+      if (h->tune_box[0] > 0) {          // user box: must be exactly this entry's box (tune_box z = layer pitch)
+        if (h->tune_box[0] != Be[0] || h->tune_box[1] != Be[1] || h->tune_box[2] != e.pitchz) continue;
+        if (e.split != (h->word_split != 0)) continue;
+      } else if (e.split && h->word_split == 0) continue;
       // boxes tile x and y; along z they need not (the slab left over is visited in later phases: the origin is random)
       if (g.gx % Be[0] || g.gy % Be[1] || Be[2] > g.gz) continue;
-      const long n_boxes = (long)(g.gx / Be[0]) * (g.gy / Be[1]) * (g.gz / Be[2]) * h->n_replicas;
-      const int rows = std::min(32, ((((Be[1] - 3 * e.margin) / 2) & ~3) / 4) * ((Be[2] - 2 * e.margin) / 4));
+      const int nbz = (g.gz - (e.bzc - e.pitchz)) / e.pitchz;
+      const long n_boxes = (long)(g.gx / Be[0]) * (g.gy / Be[1]) * nbz * h->n_replicas;
+      const int planes = (Be[2] - 2 * e.margin) / 4 - (e.split ? 1 : 0);
+      const int rows = std::min(32, ((((Be[1] - 3 * e.margin) / 2) & ~3) / 4) * planes);
       const long trials_box = (long)rows * 2 * ((Be[0] - 2 * e.margin) / 4);
-      // one CTA per SM; a step costs ~rows warp-gathers on the shared-memory pipe
+      // one CTA per SM; a step costs ~rows warp-gathers on the shared-memory pipe (overlapped with the arithmetic of
+      // the other group's in the split kernels: measured +5 %)
       const long waves = (n_boxes + n_sm - 1) / n_sm;
-      double rate = (double)n_boxes * trials_box / ((double)waves * rows);
-      if (g.gz % Be[2] == 0) rate *= 1.02;                       // prefer exact tilings when (nearly) equal
+      double rate = (double)n_boxes * trials_box / ((double)waves * rows) * (e.split ? 1.05 : 1.0);
+      if (nbz * e.pitchz + (e.bzc - e.pitchz) == g.gz) rate *= 1.02;                       // prefer exact tilings when (nearly) equal
       if (rate > best_rate) { best_rate = rate; we = &e; }
     }
     if (we) {
-      B[0] = we->bxc << g.xs; B[1] = we->byc << g.ys; B[2] = we->bzc;
+      B[0] = we->bxc << g.xs; B[1] = we->byc << g.ys; B[2] = we->pitchz;     // B = box pitch (origin stride)
       m = we->margin;
     }
   }
@@ -546,7 +560,8 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       int G = d == 0 ? g.gx : d == 1 ? g.gy : g.gz;
       p.B[d] = B[d]; p.nb[d] = G / B[d];
     }
-    p.bxc = B[0] >> g.xs; p.byc = B[1] >> g.ys; p.bzc = B[2];
+    if (we) p.nb[2] = (g.gz - (we->bzc - we->pitchz)) / we->pitchz;
+    p.bxc = B[0] >> g.xs; p.byc = B[1] >> g.ys; p.bzc = we ? we->bzc : B[2];
     p.box_sites = p.bxc * p.byc * p.bzc;
     // is a specialised kernel instantiated for this lattice / shell count / box pitch?  Its CTAs hold at
     // most 768 threads, one trial each.
@@ -592,16 +607,17 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       md.P[0] = md.P[1] = md.P[2] = 4;
       md.A[0] = (B[0] - 2 * m) / 4;                               // sites per x-row of one sub-class
       md.A[1] = (((B[1] - 3 * m) / 2) & ~3) / 4;                  // rows per plane in one y half
-      md.A[2] = (B[2] - 2 * m) / 4;                               // planes per sub-class
-      md.M = std::min(32, md.A[1] * md.A[2]) * 2 * md.A[0];
+      md.A[2] = (we->bzc - 2 * m) / 4;                            // planes per sub-class
+      md.M = std::min(32, md.A[1] * (md.A[2] - (we->split ? 1 : 0))) * 2 * md.A[0];
       md.cls0 = md.d0 = 0; md.n_classes = 16; md.n_disp = 256;    // 16 residue classes mod 4, every (o, o') pair
       Mmax = md.M;
     }
     pl->Mmax = Mmax;
     p.boxes_per_replica = p.nb[0] * p.nb[1] * p.nb[2];
     p.v_entries = g.S * g.S * g.n_shells;
-    // default: about four sweeps of the box per phase (amortises the box load/store)
-    int steps = h->tune_steps > 0 ? h->tune_steps : (4 * p.box_sites + Mmax - 1) / Mmax;
+    // default: about four sweeps of the box per phase (amortises the box load/store); six for the word kernels,
+    // whose steps are short enough for the box copies to be 9 % of a four-sweep phase
+    int steps = h->tune_steps > 0 ? h->tune_steps : ((we ? 6 : 4) * p.box_sites + Mmax - 1) / Mmax;
     p.steps = std::max(8, std::min(steps, 512));
     pl->threads = std::min(1024, ((Mmax + 31) / 32) * 32);
     pl->smem = (size_t)p.v_entries * 16 * 8 + (size_t)2 * g.ztot * 4 + 2 * sizeof(BrwStepParams) + 32 * 8 + p.box_sites;
@@ -694,10 +710,10 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       BRW_PLAN_CUDA(cudaMalloc(&pl->d_Vrep, blob.size() * sizeof(int)));
       BRW_PLAN_CUDA(cudaMemcpy(pl->d_Vrep, blob.data(), blob.size() * sizeof(int), cudaMemcpyHostToDevice));
       pl->fast_fn = (void *)(h->dE_mode == 0 ? we->fn_exact : we->fn);
-      pl->screened = h->dE_mode != 0; pl->word = true;
+      pl->screened = h->dE_mode != 0; pl->word = true; pl->split = we->split;
       pl->fast_smem = blob.size() * sizeof(int) + 32 * 8 + 2 * (size_t)p.mode[0].A[1] * p.mode[0].A[2] * 4 + 16 +
-                      (size_t)p.steps * 32 + (size_t)we->plp * p.bzc * 4;
-      pl->threads = 32 * std::min(32, p.mode[0].A[1] * p.mode[0].A[2]);
+                      (size_t)(p.steps + 1) * 32 + (size_t)we->plp * p.bzc * 4;
+      pl->threads = 32 * std::min(32, p.mode[0].A[1] * (p.mode[0].A[2] - (we->split ? 1 : 0)));
       BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)pl->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
     }
     pl->use_box = true;
@@ -742,7 +758,8 @@ extern "C" int brawl_cuda_metropolis_set_mode(brawl_cuda_t *h, int dE_mode) {
 extern "C" int brawl_cuda_metropolis_set_layout(brawl_cuda_t *h, int byte_layout_only) {
   BRW_ENTER(h);
   BRW_CUDA(cudaStreamSynchronize(h->stream));
-  h->byte_layout = byte_layout_only != 0;
+  h->byte_layout = byte_layout_only == 1;
+  h->word_split = byte_layout_only == 2 ? 0 : 1;      // 2: word kernels without the two-warp-group split
   for (int i = 0; i < 2; i++) { brw_free_plan((BrwPlan *)h->mc_plan[i]); h->mc_plan[i] = nullptr; }
   return 0;
 }
@@ -755,7 +772,8 @@ extern "C" int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *o)
     o[0] = pl->use_box; o[1] = m0.P[0] * 10000 + m0.P[1] * 100 + m0.P[2]; o[2] = pl->p.m; o[3] = pl->p.B[0]; o[4] = pl->p.B[1];
     o[5] = pl->p.B[2]; o[6] = pl->Mmax; o[7] = pl->p.boxes_per_replica; o[8] = m0.n_disp; o[9] = pl->p.steps;
     if (pl->fast_fn) o[0] = pl->word ? (pl->screened ? 4 : 5) : pl->screened ? 3 : 2;
-    o[0] += 16 * pl->p.n_modes;                 // number of period orientations in bits 4..
+    o[0] += 16 * pl->p.n_modes;                 // number of period orientations in bits 4..11
+    if (pl->word && pl->split) o[0] += 4096;    // bit 12: two warp groups per CTA, box_z = layer pitch (box depth = pitch + margin)
   }
   return 0;
 }

@@ -56,6 +56,7 @@ struct BrwPlan {
   int threads = 0, Mmax = 0;
   void *fast_fn = nullptr;     // specialised kernel for this (lattice, shells, pitch), if instantiated
   bool screened = false;
+  bool split = false;          // word kernel with two warp groups per CTA and shared z margin planes
   bool word = false;           // fast_fn is a word-lattice kernel (word_metropolis.cuh); d_Vrep holds its table blob
   size_t fast_smem = 0;
   // per-box counters

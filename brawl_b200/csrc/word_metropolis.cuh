@@ -35,6 +35,11 @@
 // a row are 2 words apart, so the 28 lanes fall into 28 different banks for every gather.  Site 2 is
 // the same construction in the upper half with a random row rotation, a cyclic x shift and an
 // optional A<->B exchange (all CTA-uniform), which keeps its gathers conflict-free as well.
+//
+// SPLIT: the rows of a box are divided between two warp groups on disjoint z zones (a frozen gap plane of 4 grid
+// units >= the interaction reach between them), each with its own named barrier, so a step of one group (gather,
+// arithmetic, barrier wait, the rare reference-association trial) does not stall the other.  Boxes of such a
+// kernel are 32 planes deep at a layer pitch of 28: consecutive layers share their frozen margin planes.
 #pragma once
 #include "tile_metropolis.cuh"
 
@@ -79,22 +84,34 @@ __host__ __device__ __forceinline__ uint32_t brw_species_word(int s) { return s 
 __host__ __device__ __forceinline__ uint32_t brw_species_nibbles(int s) { return s < 4 ? 1u << (4 * s) : 0u; }
 // species code of the low lane: 3,2,1,0 for species 0..3 and 4 for species 4 (same codes as brw_word_code)
 __device__ __forceinline__ int brw_pair_code(uint32_t w) { return (__clz((int)(w & 0xFFFFu)) - 16) >> 2; }
+// the same code without the XU pipe (FLO): (w * 0x1234) >> 12 & 7 = species + 1 for the one-hot nibbles 1, 16, 256, 4096 and
+// 0 for species 4 (w = 0); 4 - that = brw_pair_code(w).  One IMAD + SHF + LOP3 + IADD on the FMA/ALU pipes.
+__device__ __forceinline__ int brw_pair_code_alu(uint32_t w16) { return 4 - (int)(((w16 * 0x1234u) >> 12) & 7u); }
 // four 4-bit fields of the low 16 bits -> four 8-bit fields
 __device__ __forceinline__ uint32_t brw_nib2byte(uint32_t x) {
   const uint32_t t = __byte_perm(x, 0u, 0x4140);          // [b0, 0, b1, 0]
   return (t | (t << 4)) & 0x0F0F0F0Fu;
 }
 #include "pair_gather.inc"
+#ifndef BRW_XP
+#define BRW_XP 0        // timing experiments only (results invalid): 1 skips the dE arithmetic, 2 skips the gathers
+#endif
+#ifndef BRW_INTDEC
+#define BRW_INTDEC 0    // 1: acceptance test without conversions / MUFU / fp64 (FMA + ALU pipes only); measured slower
+#endif
+#ifndef BRW_TABG
+#define BRW_TABG 0      // 1: the fixed-point table row is loaded in the gather half (costs registers across the barrier)
+#endif
 
 // box <-> global copy, one warp per compact-x row of PX sites.  STORE=false: global bytes -> shared words.
 template <int LAT, int PX, int PY, int PXP, int PLP, bool STORE, bool PAIRW>
-__device__ __forceinline__ void brw_wbox_copy(const BrwGeom &g, uint8_t *L, uint32_t *wbox, int n_rows, int ox, int oy,
-                                              int oz) {
+__device__ __forceinline__ void brw_wbox_copy(const BrwGeom &g, uint8_t *L, uint32_t *wbox, int row_begin, int n_rows,
+                                              int ox, int oy, int oz) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   static_assert(PX <= 32 && (!PAIRW || PX == 32), "one warp covers a row");
   const int oxc = ox >> 1;
 #pragma unroll 8
-  for (int r = warp; r < n_rows; r += nwarps) {
+  for (int r = row_begin + warp; r < n_rows; r += nwarps) {
     const int lyc = r % PY, lz = r / PY;
     int gzz = oz + lz; if (gzz >= g.gz) gzz -= g.gz; if (gzz >= g.gz) gzz -= g.gz;
     const int Y = LAT == 1 ? 2 * lyc + (lz & 1) : lyc;
@@ -140,17 +157,21 @@ template <int BX, int BY, int BZ, int MARGIN> struct BrwDenseGeom {
   static constexpr int NROWS = NJ * NP;                        // rows per sub-class and half (36)
   static constexpr int Y_UPPER = MARGIN + HALF + MARGIN;       // first y of the upper half (32)
   static_assert(2 * NI <= 32, "one warp holds an A row and a B row");
+  // SPLIT: two independent warp groups on disjoint z zones (planes [0, NPA) and [NPA+1, NP); plane NPA is a frozen
+  // gap of 4 grid units >= the interaction reach), each with its own named barrier
+  static constexpr int NPA = (NP - 1) / 2, NPB = NP - 1 - NPA;
+  static constexpr int NRA = NJ * NPA, NRB = NJ * NPB;
 };
 
 struct __align__(16) BrwDenseStep {   // CTA-uniform per step
   int c1[2];                   // word index of site1 (i = 0, row 0) for sub-class A / B, lower half, class o
   int c2[2];                   // same for site2: upper half, class o'
-  int rot1, rot2;              // row rotations
+  int rot1, rot2;              // row rotations (SPLIT: group A in the low 16 bits, group B in the high 16 bits)
   int si;                      // cyclic x shift of site2
   int flags;                   // bit0: x-parity of o, bit1: x-parity of o', bit2: site2 takes the other sub-class
 };
 
-template <int BX, int BY, int BZ, int MARGIN, int PXP, int PLP>
+template <int BX, int BY, int BZ, int MARGIN, int PXP, int PLP, bool SPLIT>
 __device__ __forceinline__ void brw_make_dense_step(uint32_t k0, uint32_t k1, uint32_t step, uint32_t box_id,
                                                     uint32_t phase_lo, BrwDenseStep *out) {
   using G = BrwDenseGeom<BX, BY, BZ, MARGIN>;
@@ -171,13 +192,19 @@ __device__ __forceinline__ void brw_make_dense_step(uint32_t k0, uint32_t k1, ui
       if (h == 0) out->c1[sub] = c; else out->c2[sub] = c;
     }
   }
-  out->rot1 = (int)brw_below(r.y, G::NROWS);
-  out->rot2 = (int)brw_below(r.z, G::NROWS);
+  if (SPLIT) {
+    out->rot1 = (int)brw_below(r.y & 0xFFFF0000u, G::NRA) | (int)brw_below(r.y << 16, G::NRB) << 16;
+    out->rot2 = (int)brw_below(r.z & 0xFFFF0000u, G::NRA) | (int)brw_below(r.z << 16, G::NRB) << 16;
+  } else {
+    out->rot1 = (int)brw_below(r.y, G::NROWS);
+    out->rot2 = (int)brw_below(r.z, G::NROWS);
+  }
   out->si = (int)(((r.w & 0xFFFFu) * (uint32_t)G::NI) >> 16);
   out->flags = (int)(q1 & 1u) | (int)((q2 & 1u) << 1) | (int)(((r.w >> 16) & 1u) << 2);
 }
 
-template <int LAT, int NSH, int PX, int PY, int PZ, int MARGIN, int PXP, int PLP, int NLIMB, bool EXACT, bool PAIRW>
+template <int LAT, int NSH, int PX, int PY, int PZ, int MARGIN, int PXP, int PLP, int NLIMB, bool EXACT, bool PAIRW,
+          bool SPLIT = false>
 __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
     BrwGeom g, BrwBoxParams p, uint8_t *__restrict__ lat, const double *__restrict__ beta,
     const double *__restrict__ tab_g, const int4 *__restrict__ classes, const int4 *__restrict__ disp, uint32_t k0,
@@ -196,7 +223,7 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
   int *rowoff = reinterpret_cast<int *>(red + 32);                            // [2*NROWS]
   BrwDenseStep *sp = reinterpret_cast<BrwDenseStep *>(                        // [steps], 16-byte aligned
       smem_raw + (((size_t)tab_words * 4 + (size_t)p.v_entries * 8 + 32 * 8 + 2 * G::NROWS * 4 + 15) & ~(size_t)15));
-  uint32_t *wbox = reinterpret_cast<uint32_t *>(sp + p.steps);                // [bzc][PLP]
+  uint32_t *wbox = reinterpret_cast<uint32_t *>(sp + p.steps + 1);            // [bzc][PLP]
   __shared__ unsigned int s_att[32], s_acc[32];
 
   const int tid = threadIdx.x;
@@ -217,13 +244,22 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
   }
   // rows of one sub-class in one half: r -> (j = r % NJ rows of 4 in y, pl = r / NJ planes of 4 in z); doubled so that
   // (warp + rotation) needs no wrap
-  for (int r = tid; r < 2 * G::NROWS; r += blockDim.x) {
-    const int rr = r % G::NROWS;
-    rowoff[r] = 2 * PXP * (rr % G::NJ) + 4 * PLP * (rr / G::NJ);
+  if (SPLIT) {
+    // group A: rowoff[0 .. 2 NRA), planes [0, NPA); group B: rowoff[2 NRA .. 2 NRA + 2 NRB), planes [NPA + 1, NP)
+    for (int r = tid; r < 2 * (G::NRA + G::NRB); r += blockDim.x) {
+      const bool b = r >= 2 * G::NRA;
+      const int rr = b ? (r - 2 * G::NRA) % G::NRB : r % G::NRA;
+      rowoff[r] = 2 * PXP * (rr % G::NJ) + 4 * PLP * (rr / G::NJ + (b ? G::NPA + 1 : 0));
+    }
+  } else {
+    for (int r = tid; r < 2 * G::NROWS; r += blockDim.x) {
+      const int rr = r % G::NROWS;
+      rowoff[r] = 2 * PXP * (rr % G::NJ) + 4 * PLP * (rr / G::NJ);
+    }
   }
-  for (int st = tid; st < p.steps; st += blockDim.x)
-    brw_make_dense_step<2 * PX, 2 * PY, PZ, MARGIN, PXP, PLP>(k0, k1, (uint32_t)st, box_id, phase_lo, &sp[st]);
-  brw_wbox_copy<LAT, PX, PY, PXP, PLP, false, PAIRW>(g, L, wbox, PY * p.bzc, ox, oy, oz);
+  for (int st = tid; st <= p.steps; st += blockDim.x)         // one entry past the last step (header prefetch)
+    brw_make_dense_step<2 * PX, 2 * PY, PZ, MARGIN, PXP, PLP, SPLIT>(k0, k1, (uint32_t)st, box_id, phase_lo, &sp[st]);
+  brw_wbox_copy<LAT, PX, PY, PXP, PLP, false, PAIRW>(g, L, wbox, 0, PY * p.bzc, ox, oy, oz);
   __syncthreads();
 
   const double my_beta = beta[replica];
@@ -231,73 +267,142 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
   // relative band of the fast acceptance test: ex2.approx + f32 argument rounding (< 1e-5 for |x| <= 126)
   // plus the dE guard propagated through exp
   const double band = my_beta * p.guard + 4e-5;
+  const float bandf = (float)(my_beta * p.guard) + 1e-6f;
+  const float c0 = (float)(beta_l2e * p.fix_scale), c20 = (float)(beta_l2e * p.fix_scale * 1048576.0);
+  const long long gfix = (long long)ceil(p.guard / p.fix_scale) + 1;     // guard band in fixed-point units
+  long long efix_sum = 0;                                                 // accepted fixed-point dE (exact)
   const int warp = tid >> 5, lane = tid & 31;
   const int sub = lane >= G::NI ? 1 : 0;
   const int li = lane - sub * G::NI;                     // position in the x-row
-  const bool active = lane < 2 * G::NI && warp < G::NROWS;
+  const int grp = SPLIT && warp >= G::NRA ? 1 : 0;            // SPLIT: warp group (z zone)
+  const int n_work = SPLIT ? G::NRA + G::NRB : G::NROWS;      // warps that hold a row pair
+  const bool active = lane < 2 * G::NI && warp < n_work;
+  const int *my_rowoff = rowoff + (SPLIT ? (grp ? 2 * G::NRA + (warp - G::NRA) : warp) : warp);
   const int row_mul = p.row_mul;
   unsigned int n_att = 0, n_acc = 0;
   double dE_sum = 0.0;
   BrwPhilox4 rnd = {0, 0, 0, 0};
 
-  for (int step = 0; step < p.steps; step++) {
+  // One trial = a GATHER part (site words, Philox word, integer neighbour-count differences D[n] and the fixed-point
+  // table row: shared-memory pipe) and a DECIDE part (dp4a dE, acceptance test, swap: ALU/FMA pipes).  The state
+  // between the two lives in registers.
+  uint32_t *w1 = wbox, *w2 = wbox;
+  uint32_t wa = 0, wb = 0, rw = 0, D[NSH];
+  int2 Tw[T::PAIRS + 1];
+  int flags = 0;
+  bool distinct = false;
+  auto gather = [&](int step) {
     const BrwDenseStep q = sp[step];
+    const int rot1 = SPLIT ? (grp ? q.rot1 >> 16 : q.rot1 & 0xFFFF) : q.rot1;
+    const int rot2 = SPLIT ? (grp ? q.rot2 >> 16 : q.rot2 & 0xFFFF) : q.rot2;
+    distinct = false;
     if (active) {
       int i2 = li + q.si; if (i2 >= G::NI) i2 -= G::NI;
       const int sub2 = sub ^ ((q.flags >> 2) & 1);
-      uint32_t *w1 = wbox + (sub ? q.c1[1] : q.c1[0]) + 2 * li + rowoff[warp + q.rot1];
-      uint32_t *w2 = wbox + (sub2 ? q.c2[1] : q.c2[0]) + 2 * i2 + rowoff[warp + q.rot2];
-      const uint32_t wa = PAIRW ? (*w1 & 0xFFFFu) : *w1, wb = PAIRW ? (*w2 & 0xFFFFu) : *w2;
+      w1 = wbox + (sub ? q.c1[1] : q.c1[0]) + 2 * li + my_rowoff[rot1];
+      w2 = wbox + (sub2 ? q.c2[1] : q.c2[0]) + 2 * i2 + my_rowoff[rot2];
+      flags = q.flags;
+      wa = PAIRW ? (*w1 & 0xFFFFu) : *w1; wb = PAIRW ? (*w2 & 0xFFFFu) : *w2;
       n_att++;
       if ((step & 3) == 0) rnd = brw_philox((uint32_t)tid, (uint32_t)step, box_id, phase_lo, k0, k1);
-      if (wa != wb) {
-        const uint32_t w = (step & 3) == 0 ? rnd.x : (step & 3) == 1 ? rnd.y : (step & 3) == 2 ? rnd.z : rnd.w;
-        const double u = brw_u01(w);
-        const int ca = PAIRW ? brw_pair_code(wa) : brw_word_code(wa), cb = PAIRW ? brw_pair_code(wb) : brw_word_code(wb);
+      rw = (step & 3) == 0 ? rnd.x : (step & 3) == 1 ? rnd.y : (step & 3) == 2 ? rnd.z : rnd.w;
+      distinct = wa != wb;
+      if (distinct && !EXACT) {
+        const int ca = PAIRW ? brw_pair_code_alu(wa) : brw_word_code(wa), cb = PAIRW ? brw_pair_code_alu(wb) : brw_word_code(wb);
+        const int2 *row = reinterpret_cast<const int2 *>(urow) + (ca * row_mul + cb);
+        if (BRW_TABG) {
+#pragma unroll
+          for (int j = 0; j <= T::PAIRS; j++) Tw[j] = row[j * 32];
+        }
+        uint32_t C1[NSH], C2[NSH];
+        if (BRW_XP & 2) {
+#pragma unroll
+          for (int n = 0; n < NSH; n++) { C1[n] = wa * (n + 3); C2[n] = wb * (n + 5); }
+        } else if (PAIRW) {
+          if (flags & 1) BrwPairGatherBcc<NSH, PXP, PLP, 1>::run(w1, C1);
+          else BrwPairGatherBcc<NSH, PXP, PLP, 0>::run(w1, C1);
+          if (flags & 2) BrwPairGatherBcc<NSH, PXP, PLP, 1>::run(w2, C2);
+          else BrwPairGatherBcc<NSH, PXP, PLP, 0>::run(w2, C2);
+        } else {
+          if (flags & 1) brw_wsum_shells<LAT, NSH, PXP, PLP, 1, 0>(w1, C1);
+          else brw_wsum_shells<LAT, NSH, PXP, PLP, 0, 0>(w1, C1);
+          if (flags & 2) brw_wsum_shells<LAT, NSH, PXP, PLP, 1, 0>(w2, C2);
+          else brw_wsum_shells<LAT, NSH, PXP, PLP, 0, 0>(w2, C2);
+        }
+#pragma unroll
+        for (int n = 0; n < NSH; n++) D[n] = 0x80808080u + C1[n] - C2[n];
+      }
+    }
+  };
+  auto decide = [&]() {
+    if (active) {
+      if (distinct) {
         bool decided = false, accept = false;
         double dE = 0.0;
-        if (!EXACT) {
-          uint32_t C1[NSH], C2[NSH];
-          if (PAIRW) {
-            if (q.flags & 1) BrwPairGatherBcc<NSH, PXP, PLP, 1>::run(w1, C1);
-            else BrwPairGatherBcc<NSH, PXP, PLP, 0>::run(w1, C1);
-            if (q.flags & 2) BrwPairGatherBcc<NSH, PXP, PLP, 1>::run(w2, C2);
-            else BrwPairGatherBcc<NSH, PXP, PLP, 0>::run(w2, C2);
-          } else {
-            if (q.flags & 1) brw_wsum_shells<LAT, NSH, PXP, PLP, 1, 0>(w1, C1);
-            else brw_wsum_shells<LAT, NSH, PXP, PLP, 0, 0>(w1, C1);
-            if (q.flags & 2) brw_wsum_shells<LAT, NSH, PXP, PLP, 1, 0>(w2, C2);
-            else brw_wsum_shells<LAT, NSH, PXP, PLP, 0, 0>(w2, C2);
+        if (BRW_XP & 1) { decided = true; accept = ((rw ^ D[0] ^ D[1] ^ D[2] ^ D[3]) & 3u) == 0u; }
+        else if (!EXACT) {
+          if (!BRW_TABG) {
+            const int ca = PAIRW ? brw_pair_code_alu(wa) : brw_word_code(wa), cb = PAIRW ? brw_pair_code_alu(wb) : brw_word_code(wb);
+            const int2 *row = reinterpret_cast<const int2 *>(urow) + (ca * row_mul + cb);
+#pragma unroll
+            for (int j = 0; j <= T::PAIRS; j++) Tw[j] = row[j * 32];
           }
-          const int2 *row = reinterpret_cast<const int2 *>(urow) + (ca * row_mul + cb);
           int Sk[NLIMB];
 #pragma unroll
           for (int k = 0; k < NLIMB; k++) Sk[k] = 0;
 #pragma unroll
           for (int j = 0; j < T::PAIRS; j++) {
-            const int2 Lw = row[j * 32];
             const int e0 = 2 * j, e1 = 2 * j + 1;
-            Sk[e0 % NLIMB] = brw_dp4a_us(0x80808080u + C1[e0 / NLIMB] - C2[e0 / NLIMB], Lw.x, Sk[e0 % NLIMB]);
-            Sk[e1 % NLIMB] = brw_dp4a_us(0x80808080u + C1[e1 / NLIMB] - C2[e1 / NLIMB], Lw.y, Sk[e1 % NLIMB]);
+            Sk[e0 % NLIMB] = brw_dp4a_us(D[e0 / NLIMB], Tw[j].x, Sk[e0 % NLIMB]);
+            Sk[e1 % NLIMB] = brw_dp4a_us(D[e1 / NLIMB], Tw[j].y, Sk[e1 % NLIMB]);
           }
-          const int2 Kw = row[T::PAIRS * 32];
+          const int2 Kw = Tw[T::PAIRS];
           long long efix = -(long long)(((unsigned long long)(uint32_t)Kw.y << 32) | (uint32_t)Kw.x);
 #pragma unroll
           for (int k = 0; k < NLIMB; k++) efix += (long long)Sk[k] * (1LL << (8 * k));
-          dE = (double)efix * p.fix_scale;                       // exact: |efix| < 2^53, fix_scale = 2^-k
-          if (fabs(dE) > p.guard) {
-            if (dE < 0.0) { accept = true; decided = true; }
-            else {
-              const double t = (double)brw_ex2_approx((float)(-beta_l2e * dE));
+          if (BRW_INTDEC) {
+          // Decision on the FMA/ALU pipes only (no conversions, no MUFU, no fp64: nothing that goes through the MIO
+            // queue the other warp group's gathers are filling).  dE = efix * 2^-k exactly; outside the guard band its
+            // sign is the reference's.  For dE > 0: x = -beta*log2(e)*dE in f32 from two 20-bit chunks (magic-number
+            // int->float), t = 2^x by round-to-nearest split + degree-7 polynomial + exponent add, u from the top 23 bits
+            // of the Philox word.  |t/t_true - 1| < 3e-7 + 1.4e-7 |x| (+ beta*guard), |u_f - u| < 2^-23: the trial is decided
+            // here only if |u_f - t| exceeds three times those bounds, else by the reference association below.
+            if (efix < -gfix) { accept = true; decided = true; }
+            else if (efix > gfix) {
+              const uint32_t lo = (uint32_t)efix & 0xFFFFFu, hi = min((uint32_t)(efix >> 20), 0x7FFFFFu);
+              const float flo = __int_as_float(0x4B000000u | lo) - 8388608.0f;
+              const float fhi = __int_as_float(0x4B000000u | hi) - 8388608.0f;
+              const float x = fmaxf(-fmaf(fhi, c20, flo * c0), -100.0f);
+              const float xr = x + 12582912.0f;
+              const float f = x - (xr - 12582912.0f);
+              const float y = f * 0.693147180559945f;
+              float pz = 1.98412698e-4f;
+              pz = fmaf(pz, y, 1.38888889e-3f); pz = fmaf(pz, y, 8.33333333e-3f); pz = fmaf(pz, y, 4.16666667e-2f);
+              pz = fmaf(pz, y, 1.66666667e-1f); pz = fmaf(pz, y, 0.5f); pz = fmaf(pz, y, 1.0f); pz = fmaf(pz, y, 1.0f);
+              const int nexp = __float_as_int(xr) - 0x4B400000;
+              const float t = __int_as_float(__float_as_int(pz) + (nexp << 23));
+              const float uf = __int_as_float(0x3F800000u | (rw >> 9)) - 1.0f;
+              if (fabsf(uf - t) > fmaf(t, fmaf(fabsf(x), 5e-7f, bandf), 2.5e-7f)) { accept = uf < t; decided = true; }
+            }
+          } else {
+            // fixed-point sign test, then ex2.approx.ftz.f32 (relative error < 2^-22, argument rounded to f32:
+            // < 1e-5 for |x| <= 126) with a correspondingly wide band
+            if (efix < -gfix) { accept = true; decided = true; }
+            else if (efix > gfix) {
+              const double t = (double)brw_ex2_approx((float)(-beta_l2e * ((double)efix * p.fix_scale)));
+              const double u = brw_u01(rw);
               if (fabs(u - t) > t * band) { accept = u < t; decided = true; }
             }
           }
+          if (decided && accept) efix_sum += efix;
         }
         if (!decided) {
           // reference association, generic loop (screened kernel: ~1e-5 of the trials)
+          const double u = brw_u01(rw);
+          const int ca = PAIRW ? brw_pair_code(wa) : brw_word_code(wa), cb = PAIRW ? brw_pair_code(wb) : brw_word_code(wb);
           const int sa = brw_code_species(ca), sb = brw_code_species(cb);
           const int S = g.S;
-          const int *off1 = off + (q.flags & 1) * g.ztot, *off2 = off + ((q.flags >> 1) & 1) * g.ztot;
+          const int *off1 = off + (flags & 1) * g.ztot, *off2 = off + ((flags >> 1) & 1) * g.ztot;
           double E1a = 0.0, E1b = 0.0, E2b = 0.0, E2a = 0.0;
           int k = 0;
 #pragma unroll 1
@@ -320,6 +425,7 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
           dE = __dsub_rn(after, before);                         // src/metropolis.F90:792
           accept = dE < 0.0;                                     // :796
           if (!accept) accept = u < exp(-my_beta * dE);          // :802
+          if (accept) dE_sum += dE;
         }
         if (accept) {
           if (PAIRW) {
@@ -328,14 +434,28 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
             h1[0] = (uint16_t)wb; h1[-1] = (uint16_t)wb;
             h2[0] = (uint16_t)wa; h2[-1] = (uint16_t)wa;
           } else { *w1 = wb; *w2 = wa; }
-          n_acc++; dE_sum += dE;
+          n_acc++;
         }
       } else n_acc++;                                            // :774-777
     }
-    __syncthreads();
-  }
+  };
 
-  brw_wbox_copy<LAT, PX, PY, PXP, PLP, true, PAIRW>(g, L, wbox, PY * p.bzc, ox, oy, oz);
+  for (int step = 0; step < p.steps; step++) {
+    if (SPLIT && warp >= n_work) break;                        // no row pair: not a member of either group barrier
+    gather(step);
+    decide();
+    if (SPLIT) {
+      // the two groups never touch each other's active sites: independent barriers (the groups drift apart, a slow
+      // trial -- reference-association path -- stalls only its own group)
+      if (grp) asm volatile("bar.sync 2, %0;" ::"n"(32 * G::NRB) : "memory");
+      else asm volatile("bar.sync 1, %0;" ::"n"(32 * G::NRA) : "memory");
+    } else __syncthreads();
+  }
+  if (SPLIT) __syncthreads();
+
+  // frozen margin planes are unchanged (and, with a z pitch < PZ, shared with the neighbouring box): not stored
+  brw_wbox_copy<LAT, PX, PY, PXP, PLP, true, PAIRW>(g, L, wbox, PY * MARGIN, PY * (p.bzc - MARGIN), ox, oy, oz);
+  dE_sum += (double)efix_sum * p.fix_scale;
   for (int o = 16; o > 0; o >>= 1) {
     n_att += __shfl_down_sync(0xffffffffu, n_att, o);
     n_acc += __shfl_down_sync(0xffffffffu, n_acc, o);

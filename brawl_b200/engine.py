@@ -168,7 +168,7 @@ class Device:
 
     def metropolis_set_layout(self, byte_layout_only):
         """True: never use the word-lattice kernels / dense decomposition (A/B comparisons); False: automatic."""
-        check(self.L.brawl_cuda_metropolis_set_layout(self.h, int(bool(byte_layout_only))))
+        check(self.L.brawl_cuda_metropolis_set_layout(self.h, int(byte_layout_only)))
 
     def metropolis_plan(self, nbr_swap=False):
         o = np.zeros(10, dtype=np.int32)
@@ -176,7 +176,8 @@ class Device:
         keys = ("use_box", "P", "margin", "box_x", "box_y", "box_z", "trials_per_step", "boxes_per_replica",
                 "n_displacements", "steps_per_phase")
         d = dict(zip(keys, (int(v) for v in o)))
-        d["n_orientations"] = d["use_box"] >> 4
+        d["n_orientations"] = (d["use_box"] >> 4) & 255
+        d["warp_groups"] = 2 if (d["use_box"] >> 12) & 1 else 1
         d["use_box"] &= 15
         d["P"] = (d["P"] // 10000, (d["P"] // 100) % 100, d["P"] % 100)
         return d

@@ -137,14 +137,16 @@ int brawl_cuda_metropolis_tune(brawl_cuda_t *h, int box_x, int box_y, int box_z,
  * keeps the byte-lattice decomposition.  The returned sum of accepted dE is exact to f64 rounding in modes 0/1
  * and to the fixed-point unit (~1e-11 Ry per accepted swap) in mode 2. */
 int brawl_cuda_metropolis_set_mode(brawl_cuda_t *h, int dE_mode);
-/* byte_layout_only != 0: never use the word-lattice kernels and their dense decomposition (A/B comparisons,
- * tests); 0 (default): automatic. */
+/* byte_layout_only: 0 (default) automatic; 1 never use the word-lattice kernels and their dense decomposition; 2 word
+ * kernels, but without the two-warp-group split and the shared z margins (A/B comparisons, tests). */
 int brawl_cuda_metropolis_set_layout(brawl_cuda_t *h, int byte_layout_only);
 /* Describe the decomposition chosen: out10 = { kind + 16*n_orientations, period Px*10000+Py*100+Pz of the
  * first orientation, margin, box_x, box_y, box_z, max trials per step, boxes per replica, |D| (allowed
  * displacement classes of the first orientation), steps per phase }.  kind: 0 chain kernel, 1 generic box
  * kernel, 2 specialised (compile-time geometry) box kernel, 3 specialised + screened dE, 4 word-lattice
- * screened kernel (dense decomposition), 5 word-lattice kernel deciding every trial with the reference association. */
+ * screened kernel (dense decomposition), 5 word-lattice kernel deciding every trial with the reference association.
+ * out10[0] bit 12: the word kernel runs two independent warp groups per CTA; box_z is then the z pitch of the box
+ * layers (box depth = pitch + margin: consecutive layers share their frozen margin planes). */
 int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *out10);
 
 /* ---- short-range order ----------------------------------------------------------------------

@@ -18,11 +18,19 @@ def bcc_offsets(n_shells=4):
     return offs[: (8, 14, 26, 50)[n_shells - 1]]
 
 
-def dense_step_sites(q1, q2, rot1, rot2, si, swap, BX=64, BY=64, BZ=32, M=4):
+def dense_step_sites(q1, q2, rot1, rot2, si, swap, BX=64, BY=64, BZ=32, M=4, group=None):
+    """group=None: one warp group over all NP planes (SPLIT=false).  group=0/1: the rows of warp group A (planes
+    [0, NPA)) / B (planes [NPA+1, NP)) of the SPLIT kernels; rot1/rot2 are then rotations within the group."""
     NI = (BX - 2 * M) // 4
     HALF = ((BY - 3 * M) // 2) & ~3
     NJ, NP = HALF // 4, (BZ - 2 * M) // 4
     NROWS, YU = NJ * NP, M + HALF + M
+    plane0 = 0
+    if group is not None:
+        NPA = (NP - 1) // 2
+        NPB = NP - 1 - NPA
+        NROWS = NJ * (NPA if group == 0 else NPB)
+        plane0 = 0 if group == 0 else NPA + 1
 
     def cls(q):
         return [(q & 1) + 2 * ((q >> 1) & 1), (q & 1) + 2 * ((q >> 2) & 1), (q & 1) + 2 * ((q >> 3) & 1)]
@@ -40,9 +48,9 @@ def dense_step_sites(q1, q2, rot1, rot2, si, swap, BX=64, BY=64, BZ=32, M=4):
             li = lane - sub * NI
             r1, r2 = (warp + rot1) % NROWS, (warp + rot2) % NROWS
             X, Y, Z = base[(0, sub)]
-            s1.append((X + 4 * li, Y + 4 * (r1 % NJ), Z + 4 * (r1 // NJ)))
+            s1.append((X + 4 * li, Y + 4 * (r1 % NJ), Z + 4 * (r1 // NJ + plane0)))
             X, Y, Z = base[(1, sub ^ swap)]
-            s2.append((X + 4 * ((li + si) % NI), Y + 4 * (r2 % NJ), Z + 4 * (r2 // NJ)))
+            s2.append((X + 4 * ((li + si) % NI), Y + 4 * (r2 % NJ), Z + 4 * (r2 // NJ + plane0)))
     return s1, s2, (NI, NROWS)
 
 
@@ -64,6 +72,34 @@ def test_dense_step_sites_are_pairwise_non_interacting():
             assert M <= x < BX - M and M <= y < BY - M and M <= z < BZ - M   # every neighbour is inside the box
             for d in offs:
                 assert (x + d[0], y + d[1], z + d[2]) not in S       # no two touched sites interact
+
+
+def test_split_groups_never_touch_each_others_zone():
+    """SPLIT kernels (two warp groups per CTA with independent barriers, word_metropolis.cuh): 64x64x32 box, planes
+    {0,1} -> group A (12 warps), plane 2 = frozen gap, planes {3,4,5} -> group B (18 warps).  For ANY pair of steps
+    (the groups are not synchronised) the sites one group touches, and every neighbour it reads, are disjoint from the
+    sites the other group may write; within a group the dense-set invariant holds as before.  The layer pitch of 28
+    with a box depth of 32 tiles a 256-plane lattice with shared frozen margins: 9 * 28 + 4 = 256."""
+    offs = bcc_offsets(4)
+    rng = np.random.default_rng(7)
+    M, BZ = 4, 32
+    zoneA = range(M, M + 8)                       # active z of group A: planes 0, 1
+    zoneB = range(M + 12, BZ - M)                 # planes 3, 4, 5
+    for _ in range(60):
+        ca = tuple(int(v) for v in (rng.integers(16), rng.integers(16), rng.integers(12), rng.integers(12), rng.integers(14), rng.integers(2)))
+        cb = tuple(int(v) for v in (rng.integers(16), rng.integers(16), rng.integers(18), rng.integers(18), rng.integers(14), rng.integers(2)))
+        a1, a2, _ = dense_step_sites(*ca, group=0)
+        b1, b2, _ = dense_step_sites(*cb, group=1)
+        assert len(a1) == 12 * 28 and len(b1) == 18 * 28
+        for sites, zone, other in ((a1 + a2, zoneA, zoneB), (b1 + b2, zoneB, zoneA)):
+            S = set(sites)
+            assert len(S) == len(sites)
+            for (x, y, z) in sites:
+                assert z in zone and M <= x < 64 - M and M <= y < 64 - M
+                for d in offs:
+                    assert (x + d[0], y + d[1], z + d[2]) not in S
+                    assert z + d[2] not in other                      # reads stay out of the other group's zone
+    assert 9 * 28 + (32 - 28) == 256 and (32 - 28) >= 3             # shared margin planes >= interaction reach
 
 
 def test_dense_lanes_hit_distinct_banks():
