@@ -367,8 +367,9 @@ def main():
                          "algorithmic_bytes_per_attempt": B_ALG, "attempts_per_launch": per_launch_trials,
                          "ms_per_launch": per_launch_ms, "peak_source": peak_src,
                          "shared_memory_pipe_ncu": smem_pipe,
-                         "note": "lattice is L2/shared-memory resident by design: the binding resource is the shared-memory "
-                                 "(LSU) pipe, see shared_memory_pipe_ncu and DESIGN.md"},
+                         "note": "lattice is L2/shared-memory resident by design (traffic = one read of the lattice per launch): "
+                                 "the kernel is bound by instruction issue and the shared-memory (LSU) pipe together, see "
+                                 "shared_memory_pipe_ncu and DESIGN.md 4.3"},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

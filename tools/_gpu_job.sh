@@ -1,17 +1,13 @@
 mkdir -p gpurun_out
-for X in "" xpB xpC xpD; do
-if [ -n "$X" ]; then export BRAWL_CUDA_LIB=$PWD/brawl_b200/libbrawl_$X.so; else unset BRAWL_CUDA_LIB; fi
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "dense or screened or planner or word" 2>&1 | tail -1
-for L in 0 2; do
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --layout $L > gpurun_out/bench_L$L.json 2> gpurun_out/bench_L$L.err
-tail -c 300 gpurun_out/bench_L$L.err
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r01_reference.json 2> gpurun_out/bench_ref.err
+python bench.py > gpurun_out/bench_r01.json 2> gpurun_out/bench.err
+tail -c 400 gpurun_out/bench.err
 python -c "
-import json;d=json.load(open('gpurun_out/bench_L$L.json'));print('chain lib=$X layout $L', d['value'],d['e2e']['value'],d['config']['acceptance'],d['config']['energy_per_atom_start_end_Ry'])"
-done
-done
-unset BRAWL_CUDA_LIB
-for SP in 236 314; do
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --steps-per-phase $SP > gpurun_out/bench_sp.json 2> gpurun_out/bench_sp.err
+import json;d=json.load(open('gpurun_out/bench_r01.json'));print(d['value'],d['e2e']['value'],d['roofline']['frac'],d['config']['acceptance'],d['config']['energy_per_atom_start_end_Ry'], d['cpu_baseline'], d['config']['decomposition'])"
+python bench.py --workload replicas --no-cpu-baseline > gpurun_out/bench_r01_replicas.json 2> gpurun_out/bench_rep.err
 python -c "
-import json;d=json.load(open('gpurun_out/bench_sp.json'));print('chain steps/phase $SP', d['value'],d['e2e']['value'],d['config']['acceptance'],d['config']['energy_per_atom_start_end_Ry'])"
-done
+import json;d=json.load(open('gpurun_out/bench_r01_replicas.json'));print('replicas', d['value'],d['e2e']['value'],d['config']['decomposition'])"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --sweeps 16 --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:brw_box_metropolis_word -s 20 -c 1 -o gpurun_out/prof_split -f python bench.py --steps 2 --warmup 3 --sweeps 16 --no-cpu-baseline > gpurun_out/b_ncu2.log 2>&1
+ls -la gpurun_out
