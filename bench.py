@@ -210,6 +210,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version line to stdout: keep stdout = one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n = args.n_cells

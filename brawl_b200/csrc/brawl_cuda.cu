@@ -228,7 +228,10 @@ extern "C" int brawl_cuda_set_config(brawl_cuda_t *h, int first, int n, const in
     size_t bytes = (size_t)h->grid_cells * m;
     if (brw_ensure_stage(h, bytes)) return 1;
     BRW_CUDA(cudaMemcpyAsync(h->d_stage, grids + (size_t)r0 * h->grid_cells, bytes, cudaMemcpyHostToDevice, h->stream));
-    brw_pack_kernel<<<grid_for((long)bytes, 256), 256, 0, h->stream>>>(h->g, h->d_stage, h->d_lat + (size_t)(first + r0) * h->g.n_sites, m, h->d_flag);
+    if (h->g.gx % 16 == 0)
+      brw_pack16_kernel<<<grid_for((long)(bytes / 16), 256), 256, 0, h->stream>>>(h->g, h->d_stage, h->d_lat + (size_t)(first + r0) * h->g.n_sites, m, h->d_flag);
+    else
+      brw_pack_kernel<<<grid_for((long)bytes, 256), 256, 0, h->stream>>>(h->g, h->d_stage, h->d_lat + (size_t)(first + r0) * h->g.n_sites, m, h->d_flag);
     BRW_LAUNCH_CHECK("brw_pack_kernel");
   }
   return brw_check_flag(h, "set_config");
@@ -242,7 +245,10 @@ extern "C" int brawl_cuda_get_config(brawl_cuda_t *h, int first, int n, int8_t *
     int m = std::min(per, n - r0);
     size_t bytes = (size_t)h->grid_cells * m;
     if (brw_ensure_stage(h, bytes)) return 1;
-    brw_unpack_kernel<<<grid_for((long)bytes, 256), 256, 0, h->stream>>>(h->g, h->d_lat + (size_t)(first + r0) * h->g.n_sites, h->d_stage, m);
+    if (h->g.gx % 16 == 0)
+      brw_unpack16_kernel<<<grid_for((long)(bytes / 16), 256), 256, 0, h->stream>>>(h->g, h->d_lat + (size_t)(first + r0) * h->g.n_sites, h->d_stage, m);
+    else
+      brw_unpack_kernel<<<grid_for((long)bytes, 256), 256, 0, h->stream>>>(h->g, h->d_lat + (size_t)(first + r0) * h->g.n_sites, h->d_stage, m);
     BRW_LAUNCH_CHECK("brw_unpack_kernel");
     BRW_CUDA(cudaMemcpyAsync(grids + (size_t)r0 * h->grid_cells, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
     BRW_CUDA(cudaStreamSynchronize(h->stream));
@@ -274,7 +280,25 @@ static int brw_total_energy_dev(brawl_cuda_ctx *h, int first, int n, int exact, 
       BRW_LAUNCH_CHECK("brw_ordered_sum_kernel");
     }
   } else {
-    // one CTA per compact row, grid-strided; many replicas: fewer CTAs each
+    // tiled kernel (compile-time gathers from shared memory) where it is instantiated and the lattice is a whole
+    // number of 32 x 16 x 8 tiles; else one CTA per compact row, grid-strided
+    typedef void (*BrwETileKernel)(BrwGeom, const double *, const uint8_t *, double *, int, int);
+    BrwETileKernel tk = nullptr;
+    if (g.S <= 5 && g.cx % 32 == 0 && g.cy % 16 == 0 && g.cz % 8 == 0 && !h->disable_fast) {
+      if (g.lattice == 1 && g.n_shells == 4) tk = brw_energy_tile_kernel<1, 4>;
+      else if (g.lattice == 1 && g.n_shells == 6) tk = brw_energy_tile_kernel<1, 6>;
+      else if (g.lattice == 2 && g.n_shells == 4) tk = brw_energy_tile_kernel<2, 4>;
+      else if (g.lattice == 2 && g.n_shells == 6) tk = brw_energy_tile_kernel<2, 6>;
+    }
+    if (tk) {
+      const int ntx = g.cx / 32, nty = g.cy / 16, ntz = g.cz / 8, ntile = ntx * nty * ntz;
+      if (brw_ensure_scratch(h, (size_t)ntile * n * sizeof(double))) return 1;
+      tk<<<dim3(ntile, n), 256, 0, h->stream>>>(g, h->d_V, h->d_lat + (size_t)first * g.n_sites, h->d_scratch, ntx, nty);
+      BRW_LAUNCH_CHECK("brw_energy_tile_kernel");
+      brw_tree_final_kernel<<<n, 128, 0, h->stream>>>(h->d_scratch, ntile, d_out, n);
+      BRW_LAUNCH_CHECK("brw_tree_final_kernel");
+      return 0;
+    }
     int n_rows = g.cy * g.cz;
     int nblk = std::max(1, std::min(n_rows, n >= 148 ? 8 : (n >= 8 ? 148 : 1184)));
     if (brw_ensure_scratch(h, (size_t)nblk * n * sizeof(double))) return 1;
@@ -283,7 +307,7 @@ static int brw_total_energy_dev(brawl_cuda_ctx *h, int first, int n, int exact, 
     brw_energy_partial_kernel<<<grid, threads, sizeof(double) * g.S * g.S * g.n_shells, h->stream>>>(
         g, h->d_V, h->d_lat + (size_t)first * g.n_sites, h->d_scratch, nblk);
     BRW_LAUNCH_CHECK("brw_energy_partial_kernel");
-    brw_tree_final_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_scratch, nblk, d_out, n);
+    brw_tree_final_kernel<<<n, 128, 0, h->stream>>>(h->d_scratch, nblk, d_out, n);
     BRW_LAUNCH_CHECK("brw_tree_final_kernel");
   }
   return 0;

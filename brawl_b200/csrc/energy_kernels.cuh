@@ -31,6 +31,68 @@ __global__ void brw_unpack_kernel(BrwGeom g, const uint8_t *__restrict__ lat, in
   }
 }
 
+// 16 grid cells (one uint4) per thread, for grids whose x extent is a multiple of 16: the 16 cells lie in one row
+// (y, z), whose site parity is thread-uniform, and map to 8 (bcc, fcc) or 16 (sc) consecutive compact bytes.
+__global__ void __launch_bounds__(256) brw_pack16_kernel(BrwGeom g, const int8_t *__restrict__ grid,
+                                                         uint8_t *__restrict__ lat, int n_rep, int *flag) {
+  const long cells = (long)g.gx * g.gy * g.gz, chunks = cells / 16, total = chunks * n_rep;
+  const int cpr = g.gx / 16;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / chunks, c = i - r * chunks;
+    const int k = (int)(c % cpr), row = (int)(c / cpr), y = row % g.gy, z = row / g.gy;
+    const uint4 v = reinterpret_cast<const uint4 *>(grid)[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    // x-parity of the sites of this row (-1: the row holds no sites)
+    const int par = g.lattice == 1 ? (((y ^ z) & 1) ? -1 : (z & 1)) : g.lattice == 2 ? ((y + z) & 1) : 0;
+    int bad = 0;
+    uint32_t o[4] = {0, 0, 0, 0};
+    int no = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const int cell = (int)(int8_t)((w[j >> 2] >> (8 * (j & 3))) & 255u);
+      const bool site = g.lattice == 0 ? true : (par >= 0 && (j & 1) == par);
+      if (site) {
+        int sp = cell;
+        if (sp < 1 || sp > g.S) { bad |= 1; sp = 1; }
+        o[no >> 2] |= (uint32_t)(sp - 1) << (8 * (no & 3));
+        no++;
+      } else if (cell != 0) bad |= 2;
+    }
+    if (bad) atomicOr(flag, bad);
+    if (g.lattice == 0) reinterpret_cast<uint4 *>(lat + r * g.n_sites + ((long)row * g.cx + 16 * k))[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    else if (par >= 0) reinterpret_cast<uint2 *>(lat + r * g.n_sites + ((long)(z * g.cy + (y >> g.ys)) * g.cx + 8 * k))[0] = make_uint2(o[0], o[1]);
+  }
+}
+__global__ void __launch_bounds__(256) brw_unpack16_kernel(BrwGeom g, const uint8_t *__restrict__ lat,
+                                                           int8_t *__restrict__ grid, int n_rep) {
+  const long cells = (long)g.gx * g.gy * g.gz, chunks = cells / 16, total = chunks * n_rep;
+  const int cpr = g.gx / 16;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / chunks, c = i - r * chunks;
+    const int k = (int)(c % cpr), row = (int)(c / cpr), y = row % g.gy, z = row / g.gy;
+    const int par = g.lattice == 1 ? (((y ^ z) & 1) ? -1 : (z & 1)) : g.lattice == 2 ? ((y + z) & 1) : 0;
+    uint32_t in[4] = {0, 0, 0, 0};
+    if (g.lattice == 0) {
+      const uint4 v = reinterpret_cast<const uint4 *>(lat + r * g.n_sites + ((long)row * g.cx + 16 * k))[0];
+      in[0] = v.x; in[1] = v.y; in[2] = v.z; in[3] = v.w;
+    } else if (par >= 0) {
+      const uint2 v = reinterpret_cast<const uint2 *>(lat + r * g.n_sites + ((long)(z * g.cy + (y >> g.ys)) * g.cx + 8 * k))[0];
+      in[0] = v.x; in[1] = v.y;
+    }
+    uint32_t w[4] = {0, 0, 0, 0};
+    int ni = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const bool site = g.lattice == 0 ? true : (par >= 0 && (j & 1) == par);
+      if (site) {
+        w[j >> 2] |= (((in[ni >> 2] >> (8 * (ni & 3))) & 255u) + 1u) << (8 * (j & 3));
+        ni++;
+      }
+    }
+    reinterpret_cast<uint4 *>(grid)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // ---- per-site energies -----------------------------------------------------------------------
 // out[r*n_sites + c] = nbr_energy of compact site c of replica r.  One thread per site.
 // HBM-bound in principle (1 B read + 8 B written per site); gathers hit L1/L2.
@@ -140,12 +202,21 @@ __global__ void __launch_bounds__(128) brw_energy_partial_kernel(BrwGeom g, cons
     partial[(long)r * nblk + blockIdx.x] = s;
   }
 }
-__global__ void brw_tree_final_kernel(const double *__restrict__ partial, int nblk, double *__restrict__ out, int n_rep) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
+// one CTA of 128 threads per replica: strided partial sums, then a fixed shared-memory tree (deterministic)
+__global__ void __launch_bounds__(128) brw_tree_final_kernel(const double *__restrict__ partial, int nblk,
+                                                             double *__restrict__ out, int n_rep) {
+  __shared__ double red[128];
+  const int r = blockIdx.x;
   if (r >= n_rep) return;
   double s = 0.0;
-  for (int b = 0; b < nblk; b++) s += partial[(long)r * nblk + b];
-  out[r] = 0.5 * s;
+  for (int b = threadIdx.x; b < nblk; b += 128) s += partial[(long)r * nblk + b];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[r] = 0.5 * red[0];
 }
 
 // ---- per-swap dE batch -----------------------------------------------------------------------

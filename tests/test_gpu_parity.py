@@ -66,6 +66,30 @@ def test_config_roundtrip_and_validation(bw, orc, golden):
         dev.set_config(gs, 2, 3)                  # replica range overflow
 
 
+def test_config_roundtrip_vectorised_converters(bw, orc):
+    """Grids whose x extent is a multiple of 16 use the 16-cells-per-thread converters (brw_pack16/unpack16_kernel):
+    round trip, several replicas, the energy of the packed lattice, and the same validation errors -- bcc, fcc and
+    simple cubic, extents that differ per axis."""
+    rng = np.random.default_rng(4)
+    for lattice, dims, S in (("bcc", (8, 4, 3), 4), ("fcc", (16, 3, 2), 5), ("simple_cubic", (16, 3, 2), 3)):
+        shells = 2
+        V = rng.normal(scale=1e-3, size=shells * S * S)
+        sysm = orc.System(lattice, *dims, S, shells, V)
+        dev = bw.Device(lattice, *dims, S, shells, V, n_replicas=3)
+        gs = np.stack([random_config(orc, sysm, s) for s in (11, 12, 13)])
+        assert gs.shape[-1] % 16 == 0
+        dev.set_config(gs)
+        assert np.array_equal(dev.get_config(0, 3), gs)
+        assert dev.total_energy(2, 1)[0] == sysm.total_energy(gs[2])
+        bad = gs[0].copy(); bad[bad > 0] = S + 1
+        with pytest.raises(bw.BrawlCudaError, match="species"):
+            dev.set_config(bad, 1, 1)
+        if lattice != "simple_cubic":
+            bad = gs[0].copy(); bad[0, 0, 1] = 1      # (x=1,y=0,z=0) is not a bcc / fcc site
+            with pytest.raises(bw.BrawlCudaError, match="not a lattice site"):
+                dev.set_config(bad, 1, 1)
+
+
 CASES = [("bcc", n) for n in range(1, 11)] + [("fcc", n) for n in range(1, 7)] + [("simple_cubic", 1), ("simple_cubic", 2)]
 
 
@@ -667,6 +691,26 @@ def test_edge_cases_empty_and_degenerate_inputs(bw, orc, golden):
     assert d16.total_energy()[0] == s16.total_energy(g16)
     with pytest.raises(bw.BrawlCudaError, match="n_species"):
         bw.Device("fcc", 3, 3, 3, 17, 2, np.zeros(17 * 17 * 2))
+
+
+def test_tiled_total_energy_matches_reference_order(bw, orc):
+    """Production total_energy (exact_order=False) on lattices that are a whole number of 32x16x8 tiles runs
+    brw_energy_tile_kernel (integer neighbour counts x V); it must agree with the bit-exact reference-order sum, and
+    with the oracle's total_energy, to f64 rounding -- bcc and fcc, 4 and 6 shells, 2..5 species, unsymmetric V so a
+    centre/neighbour index mix-up would show."""
+    rng = np.random.default_rng(17)
+    for lattice, n, S, shells in (("bcc", 32, 4, 4), ("bcc", 32, 5, 6), ("bcc", 32, 2, 4), ("fcc", 32, 5, 4), ("fcc", 32, 3, 6)):
+        V = rng.normal(scale=2e-3, size=shells * S * S)
+        sysm = orc.System(lattice, n, n, n, S, shells, V)
+        g = random_config(orc, sysm, 31 + S)
+        dev = bw.Device(lattice, n, n, n, S, shells, V)
+        dev.set_config(g)
+        e_exact = dev.total_energy(exact_order=True)[0]
+        e_tile = dev.total_energy(exact_order=False)[0]
+        assert e_exact == sysm.total_energy(g)
+        assert abs(e_tile - e_exact) <= 1e-12 * abs(e_exact) + 1e-13, (lattice, S, shells, e_tile, e_exact)
+        dev.metropolis_tune((0, 0, 0), -1)                       # test hook: generic kernels (row energy kernel)
+        assert abs(dev.total_energy(exact_order=False)[0] - e_tile) <= 1e-12 * abs(e_exact) + 1e-13
 
 
 def test_full_size_128_cubed_properties(bw, golden):

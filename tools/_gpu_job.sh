@@ -1,13 +1,11 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r01_reference.json 2> gpurun_out/bench_ref.err
-python bench.py > gpurun_out/bench_r01.json 2> gpurun_out/bench.err
-tail -c 400 gpurun_out/bench.err
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_x.json 2> gpurun_out/bench_x.err
+tail -c 300 gpurun_out/bench_x.err
 python -c "
-import json;d=json.load(open('gpurun_out/bench_r01.json'));print(d['value'],d['e2e']['value'],d['roofline']['frac'],d['config']['acceptance'],d['config']['energy_per_atom_start_end_Ry'], d['cpu_baseline'], d['config']['decomposition'])"
-python bench.py --workload replicas --no-cpu-baseline > gpurun_out/bench_r01_replicas.json 2> gpurun_out/bench_rep.err
+import json;d=json.load(open('gpurun_out/bench_x.json'));print('chain', d['value'],d['e2e']['value'],d['config']['acceptance'],d['config']['energy_per_atom_start_end_Ry'])"
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --workload replicas > gpurun_out/bench_xr.json 2> gpurun_out/bench_xr.err
 python -c "
-import json;d=json.load(open('gpurun_out/bench_r01_replicas.json'));print('replicas', d['value'],d['e2e']['value'],d['config']['decomposition'])"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --sweeps 16 --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:brw_box_metropolis_word -s 20 -c 1 -o gpurun_out/prof_split -f python bench.py --steps 2 --warmup 3 --sweeps 16 --no-cpu-baseline > gpurun_out/b_ncu2.log 2>&1
-ls -la gpurun_out
+import json;d=json.load(open('gpurun_out/bench_xr.json'));print('replicas', d['value'],d['e2e']['value'])"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_x.csv python bench.py --steps 2 --warmup 3 --sweeps 16 --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1
+grep -E "energy|pack|tree" gpurun_out/launches_x.csv | awk -F'","' '{print substr($5,1,40), $NF}' | sort | uniq -c | sort -k2 | head -12
