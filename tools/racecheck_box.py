@@ -13,11 +13,16 @@ import brawl_b200
 
 gold = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "brawl_golden.npz"))
 rng = np.random.default_rng(0)
-for lattice, n, S, shells, key, nbr, mode, generic in (("bcc", 32, 4, 4, "ex_AlTiCrMo_V", False, 1, False),
-                                                     ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", False, 0, False),
-                                                     ("fcc", 32, 5, 4, "ex_AlCrFeCoNi_V", False, 1, False),
-                                                     ("bcc", 16, 4, 6, "t02_V", False, 0, True),
-                                                     ("bcc", 16, 4, 4, "ex_AlTiCrMo_V", True, 0, True)):
+# layout: 0 automatic (word kernel with two warp groups where instantiated), 1 byte-lattice kernels, 2 word kernel, one group
+for lattice, n, S, shells, key, nbr, mode, generic, layout in (
+        ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", False, 2, False, 0),      # word kernel, pair words, two warp groups (named barriers)
+        ("bcc", 32, 5, 4, "ex_AlCrFeCoNi_V", False, 2, False, 2),    # word kernel, one warp group, 5 species
+        ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", False, 0, False, 0),      # word kernel, EXACT instantiation
+        ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", False, 1, False, 1),
+        ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", False, 0, False, 1),
+        ("fcc", 32, 5, 4, "ex_AlCrFeCoNi_V", False, 1, False, 1),
+        ("bcc", 16, 4, 6, "t02_V", False, 0, True, 1),
+        ("bcc", 16, 4, 4, "ex_AlTiCrMo_V", True, 0, True, 1)):
     V = gold[key][: S * S * shells]
     par = np.arange(2 * n) & 1
     mask = ((par[None, None, :] == par[:, None, None]) & (par[None, :, None] == par[:, None, None])) if lattice == "bcc" else \
@@ -26,9 +31,12 @@ for lattice, n, S, shells, key, nbr, mode, generic in (("bcc", 32, 4, 4, "ex_AlT
     g[mask] = rng.integers(1, S + 1, size=int(mask.sum()))
     dev = brawl_b200.Device(lattice, n, n, n, S, shells, V)
     dev.metropolis_set_mode(mode)
+    dev.metropolis_set_layout(layout)
     dev.metropolis_tune((0, 0, 0), -7 if generic else 6)        # 6 steps per phase; negative: generic kernel
     dev.set_config(g)
     plan = dev.metropolis_plan(nbr)
     att, acc, dE = dev.metropolis_run(1.0 / (800.0 * brawl_b200.K_B_IN_RY), 1, nbr_swap=nbr)   # exactly one phase
-    print(lattice, n, shells, "nbr" if nbr else "lattice", "mode", mode, plan["use_box"], int(att[0]), int(acc[0]))
+    e_tile = dev.total_energy(exact_order=False)[0]            # tiled energy kernel (shared-memory tile + halo)
+    print(lattice, n, shells, "nbr" if nbr else "lattice", "mode", mode, "layout", layout, "kind", plan["use_box"],
+          "groups", plan["warp_groups"], int(att[0]), int(acc[0]), e_tile)
 print("done")
