@@ -92,6 +92,7 @@ __device__ __forceinline__ uint32_t brw_nib2byte(uint32_t x) {
   const uint32_t t = __byte_perm(x, 0u, 0x4140);          // [b0, 0, b1, 0]
   return (t | (t << 4)) & 0x0F0F0F0Fu;
 }
+__device__ __forceinline__ uint32_t brw_lo16(const uint32_t *p) { return *reinterpret_cast<const uint16_t *>(p); }
 #include "pair_gather.inc"
 #ifndef BRW_XP
 #define BRW_XP 0        // timing experiments only (results invalid): 1 skips the dE arithmetic, 2 skips the gathers
@@ -412,8 +413,8 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
             const int end = g.shell_end[n];
 #pragma unroll 1
             for (; k < end; k++) {
-              const int s1 = brw_code_species(PAIRW ? brw_pair_code(w1[off1[k]]) : brw_word_code(w1[off1[k]]));
-              const int s2 = brw_code_species(PAIRW ? brw_pair_code(w2[off2[k]]) : brw_word_code(w2[off2[k]]));
+              const int s1 = brw_code_species(PAIRW ? brw_pair_code(brw_lo16(w1 + off1[k])) : brw_word_code(w1[off1[k]]));
+              const int s2 = brw_code_species(PAIRW ? brw_pair_code(brw_lo16(w2 + off2[k])) : brw_word_code(w2[off2[k]]));
               e1a = __dadd_rn(e1a, Vn[s1 * S + sa]); e1b = __dadd_rn(e1b, Vn[s1 * S + sb]);
               e2b = __dadd_rn(e2b, Vn[s2 * S + sb]); e2a = __dadd_rn(e2a, Vn[s2 * S + sa]);
             }

@@ -141,7 +141,9 @@ def test_pair_word_gather_plan_counts_every_neighbour_once():
         assert sum(len(o) for _, _, o in names) == 30
         for _ in range(40):
             zc, yc, xc = (int(v) for v in (rng.integers(4, PZ - 4), rng.integers(4, PY - 4), rng.integers(4, PX - 4)))
-            acc = {nm: sum(int(W[zc + dz, yc + dyc, xc + dxc]) for dz, dyc, dxc in o) & 0xFFFFFFFF for nm, _, o in names}
+            # accumulators whose high lane is not a neighbour load the low 16 bits only (LDS.U16)
+            acc = {nm: sum(int(W[zc + dz, yc + dyc, xc + dxc]) & (0xFFFF if role[1] is None else 0xFFFFFFFF)
+                           for dz, dyc, dxc in o) & 0xFFFFFFFF for nm, role, o in names}
             C = [sum(nib2byte(sum((acc[nm] >> (16 * lane)) for nm, lane in g)) for g in gs) for gs in groups]
             want = [[0] * 4 for _ in range(4)]
             for (dx, dy, dz), n in offs:

@@ -3,7 +3,7 @@
 (word_metropolis.cuh, PAIRW = true).
 
 Shared-memory word of compact site c:  W[c] = n(c) | n(c+1) << 16,  n = one-hot nibble of the species
-(1 << 4*species for species 0..3, 0 for species 4).  One LDS.32 therefore returns TWO x-adjacent sites for any c,
+(1 << 4*species for species 0..3, 0 for species 4).  One LDS.32 therefore returns TWO x-adjacent sites for any c (loads whose high lane is not a neighbour are LDS.U16),
 and the 50 neighbours of a bcc site (shells 1-4, reference tables src/bw_hamiltonian.f90:162-169, 225-230, 286-297,
 361-384 via shell_tables.inc) are covered by 30 loads.  Each load is added to an accumulator chosen by the pair of
 shells its two 16-bit lanes belong to ("X" = a lane that is not a neighbour; its sums are never used).  An
@@ -96,7 +96,10 @@ def emit(n_shells, par):
     names, groups = build(n_shells, par)
     lines = []
     for nm, role, offs in names:
-        terms = ["wc[(%d) * PLP + (%d) * PXP + (%d)]" % o for o in offs]
+        # hi lane unused ("x"): 16-bit load of the low half only -- the high half may be another thread's trial site of
+        # the same step (offset = (2,2,2) mod 4), which that thread is free to rewrite
+        fmt = "brw_lo16(wc + (%d) * PLP + (%d) * PXP + (%d))" if role[1] is None else "wc[(%d) * PLP + (%d) * PXP + (%d)]"
+        terms = [fmt % o for o in offs]
         lines.append("    const uint32_t %s = %s;" % (nm, " + ".join(terms)))
     for n, gs in enumerate(groups):
         ex = []
