@@ -433,7 +433,7 @@ static int brw_walker_prepare(const BrwGeom &g, int extra_doubles, K kernel, Brw
   lay = brw_walker_layout(g, extra_doubles);
   if (lay.total() + sizeof(BrwWarpScratch) * BRW_WALKER_WARPS > 220 * 1024) {
     // too much per-walker state for shared memory: drop the table, then the staging
-    lay.use_tab = 0; lay.tab_bytes = 0;
+    lay.use_tab = 0; lay.tab_bytes = 0; lay.ksh_bytes = 0; lay.fast_delta = 0;
     if (lay.total() + sizeof(BrwWarpScratch) * BRW_WALKER_WARPS > 220 * 1024) return brw_fail("walker state does not fit in shared memory");
   }
   if (brw_cuda_check(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total()), "cudaFuncSetAttribute")) return 1;
@@ -846,6 +846,7 @@ extern "C" int brawl_cuda_metropolis_enqueue(brawl_cuda_t *h, const double *beta
     if (n_trials > 0) {
       BrwWalkerLayout lay;
       if (brw_walker_prepare(h->g, 0, brw_chain_metropolis_kernel, lay)) return 1;
+      if (h->dE_mode == 0) lay.fast_delta = 0;      // reference association for every trial
       brw_chain_metropolis_kernel<<<(h->n_replicas + BRW_WALKER_WARPS - 1) / BRW_WALKER_WARPS, 32 * BRW_WALKER_WARPS,
                                     lay.total(), h->stream>>>(
           h->g, lay, h->d_V, h->d_lat, h->d_beta, h->n_replicas, (long)n_trials, nbr_swap, k0, k1, (uint32_t)offset,
@@ -1050,6 +1051,7 @@ extern "C" int brawl_cuda_wl_sweeps(brawl_cuda_t *h, int n_walkers, double *lng,
   }
   BrwWalkerLayout lay;
   if (brw_walker_prepare(g, bins + hist_stride, brw_wl_walker_kernel, lay)) return 1;
+  if (h->dE_mode == 0) lay.fast_delta = 0;      // reference association for every trial
   brw_wl_walker_kernel<<<(n_walkers + BRW_WALKER_WARPS - 1) / BRW_WALKER_WARPS, 32 * BRW_WALKER_WARPS, lay.total(), h->stream>>>(g, lay, h->d_V, h->d_lat, d_lng, d_hist, edges[0], range, bins, d_lo, d_hi,
                                                                     hist_stride, wl_f, (long)n_trials, hist_every, nbr_swap, (uint32_t)seed,
                                                                     (uint32_t)(seed >> 32), (uint32_t)offset, (uint32_t)(offset >> 32),
@@ -1083,6 +1085,7 @@ extern "C" int brawl_cuda_wl_enter_window(brawl_cuda_t *h, int n_walkers, const 
   if (brw_total_energy_dev(h, 0, n_walkers, 1, d_e)) return 1;                    // :658
   BrwWalkerLayout lay;
   if (brw_walker_prepare(h->g, 0, brw_wl_enter_window_kernel, lay)) return 1;
+  if (h->dE_mode == 0) lay.fast_delta = 0;      // reference association for every trial
   brw_wl_enter_window_kernel<<<(n_walkers + BRW_WALKER_WARPS - 1) / BRW_WALKER_WARPS, 32 * BRW_WALKER_WARPS, lay.total(), h->stream>>>(
       h->g, lay, h->d_V, h->d_lat, d_t, d_lo, d_hi, inv_two_sigma_sq, (long)max_trials, (uint32_t)seed, (uint32_t)(seed >> 32),
       (uint32_t)offset, (uint32_t)(offset >> 32), n_walkers, d_e, d_ent);
@@ -1166,6 +1169,7 @@ extern "C" int brawl_cuda_ns_walk(brawl_cuda_t *h, int n_walkers, const int32_t 
   BRW_CUDA(cudaMemcpyAsync(d_ids, ids, sizeof(int) * n_walkers, cudaMemcpyHostToDevice, h->stream));
   BrwWalkerLayout lay;
   if (brw_walker_prepare(h->g, 0, brw_ns_walker_kernel, lay)) return 1;
+  if (h->dE_mode == 0) lay.fast_delta = 0;      // reference association for every trial
   brw_ns_walker_kernel<<<(n_walkers + BRW_WALKER_WARPS - 1) / BRW_WALKER_WARPS, 32 * BRW_WALKER_WARPS, lay.total(), h->stream>>>(h->g, lay, h->d_V, h->d_lat, d_ids, d_e, d_lim, (long)n_steps, (uint32_t)seed,
                                                                     (uint32_t)(seed >> 32), (uint32_t)offset, (uint32_t)(offset >> 32),
                                                                     n_walkers, d_acc);

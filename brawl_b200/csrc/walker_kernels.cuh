@@ -1,7 +1,13 @@
 // walker_kernels.cuh -- production (Philox) kernels for batches of independent walkers/replicas on
 // small lattices: ONE WARP PER WALKER, each an exact sequential chain with the reference's proposal
-// distribution and f64 energy association (brw_warp_pair_energies); the walker's lattice is staged
-// in shared memory for the whole call.
+// distribution; the walker's lattice is staged in shared memory for the whole call.  The energy change of a trial
+// is either the reference's f64 association (brw_warp_pair_energies: per-shell sequential sums through a
+// shared-memory scratch, ~1000 cycles of dependent latency; handles with dE_mode 0, and lattices without a neighbour
+// table) or -- the default -- a lane-parallel sum: every lane adds the V differences of its <= ceil(Z/32)
+// neighbours of both sites, then a 5-stage xor butterfly (same value in all lanes, fixed order => deterministic):
+// ~300 cycles.  It differs from the reference association by f64 rounding only (a walker's running energy stays
+// within 1e-11 Ry of the exact total energy over 10^4 trials, tested); bit-exact trajectories are the job of the
+// replay kernels.
 //   Metropolis : src/metropolis.F90:751-891 (k-loop :348-354), lattices too small for boxes
 //   WL         : src/wang-landau.F90:539-626 (sweeps), :515-523 (bin_index), :643-741 (enter_energy_window)
 //   NS         : src/nested_sampling.f90:157-192
@@ -19,8 +25,9 @@
 //   then per warp: [ lattice : n_sites bytes, padded to 8 (optional) ][ extra f64 words ]
 struct BrwWalkerLayout {
   int use_tab, staged;
-  int v_bytes, tab_bytes, lat_bytes, extra_bytes;   // extra = per-warp f64 scratch (WL: ln g + hist)
-  __host__ __device__ size_t total() const { return (size_t)v_bytes + tab_bytes + (size_t)BRW_WALKER_WARPS * (lat_bytes + extra_bytes); }
+  int fast_delta;              // lane-parallel dE (needs the table); 0: reference association
+  int v_bytes, tab_bytes, ksh_bytes, lat_bytes, extra_bytes;   // ksh = shell index per neighbour; extra = per-warp f64 scratch (WL: ln g + hist)
+  __host__ __device__ size_t total() const { return (size_t)v_bytes + tab_bytes + ksh_bytes + (size_t)BRW_WALKER_WARPS * (lat_bytes + extra_bytes); }
 };
 static inline BrwWalkerLayout brw_walker_layout(const BrwGeom &g, int extra_doubles) {
   BrwWalkerLayout L;
@@ -28,6 +35,8 @@ static inline BrwWalkerLayout brw_walker_layout(const BrwGeom &g, int extra_doub
   L.staged = g.n_sites <= BRW_WALKER_SMEM_SITES;
   L.use_tab = L.staged && (size_t)g.n_sites * g.ztot * 2 <= BRW_WALKER_TAB_BYTES && g.n_sites <= 65535;
   L.tab_bytes = L.use_tab ? ((g.n_sites * g.ztot * 2 + 7) & ~7) : 0;
+  L.ksh_bytes = L.use_tab ? ((g.ztot + 7) & ~7) : 0;
+  L.fast_delta = L.use_tab;
   L.lat_bytes = L.staged ? ((g.n_sites + 7) & ~7) : 0;
   L.extra_bytes = extra_doubles * 8;
   return L;
@@ -38,6 +47,8 @@ struct BrwWalkerCtx {
   uint8_t *G;                  // its home in global memory
   const double *V;             // V_ex in shared memory
   const unsigned short *tab;   // neighbour table or nullptr
+  const unsigned char *ksh;    // shell index of neighbour k (shared memory; with the table)
+  bool fast;                   // lane-parallel dE
   double *extra;               // per-warp f64 scratch
   bool staged;
 };
@@ -56,8 +67,13 @@ __device__ __forceinline__ BrwWalkerCtx brw_walker_begin(const BrwGeom &g, const
       brw_compact_to_grid(g, c, x, y, z);
       tab[i] = (unsigned short)brw_nbr(g, x, y, z, k);
     }
+  unsigned char *ksh = smem + lay.v_bytes + lay.tab_bytes;
+  if (lay.use_tab)
+    for (int k = threadIdx.x; k < g.ztot; k += blockDim.x) ksh[k] = (unsigned char)g.off[k][3];
   BrwWalkerCtx c;
-  unsigned char *mine = smem + lay.v_bytes + lay.tab_bytes + (size_t)warp * (lay.lat_bytes + lay.extra_bytes);
+  unsigned char *mine = smem + lay.v_bytes + lay.tab_bytes + lay.ksh_bytes + (size_t)warp * (lay.lat_bytes + lay.extra_bytes);
+  c.ksh = ksh;
+  c.fast = lay.use_tab && lay.fast_delta;
   c.G = lat_global;
   c.V = Vs;
   c.tab = lay.use_tab ? tab : nullptr;
@@ -78,7 +94,26 @@ __device__ __forceinline__ void brw_walker_end(const BrwGeom &g, const BrwWalker
 __device__ __forceinline__ void brw_walker_pair(const BrwGeom &g, const BrwWalkerCtx &c, int x1, int y1, int z1, int x2,
                                                 int y2, int z2, int c1, int c2, int s1, int s2, BrwWarpScratch *w,
                                                 double &before, double &after) {
-  if (c.tab) {
+  if (c.fast) {
+    // lane-parallel: d = sum_k [V_k(u1k, s2) - V_k(t1k, s1)] + [V_k(u2k, s1) - V_k(t2k, s2)], t = occupant of
+    // neighbour k before the exchange, u = after it (a neighbour that IS one of the two sites shows the exchanged
+    // occupant: src/metropolis.F90:783-792 swaps, then recomputes)
+    const int lane = threadIdx.x & 31, S = g.S, SS = S * S;
+    const unsigned short *t1 = c.tab + c1 * g.ztot, *t2 = c.tab + c2 * g.ztot;
+    double d = 0.0;
+#pragma unroll 2
+    for (int k = lane; k < g.ztot; k += 32) {
+      const double *Vn = c.V + c.ksh[k] * SS;
+      const int n1 = t1[k], n2 = t2[k];
+      const int a = c.L[n1], b = c.L[n2];
+      const int u1 = n1 == c1 ? s2 : (n1 == c2 ? s1 : a);
+      const int u2 = n2 == c1 ? s2 : (n2 == c2 ? s1 : b);
+      d += (Vn[u1 * S + s2] - Vn[a * S + s1]) + (Vn[u2 * S + s1] - Vn[b * S + s2]);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) d += __shfl_xor_sync(0xffffffffu, d, m);
+    before = 0.0; after = d;
+  } else if (c.tab) {
     BrwNbrTable nb{c.tab + c1 * g.ztot, c.tab + c2 * g.ztot};
     brw_warp_pair_energies_t(g, c.V, c.L, nb, c1, c2, s1, s2, w, before, after);
   } else {
@@ -178,6 +213,7 @@ __global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_wl_walker_kernel(
   unsigned long long accepted = 0;
   BrwProposal mine = {};
   double my_logu = 0.0;
+  long hist_left = hist_every > 0 ? hist_every : -1;           // trials until the next histogram sample (i % hist_every == 0)
   for (long i = 1; i <= n_trials; i++) {
     const int slot = (int)((i - 1) & 31);
     if (slot == 0) {
@@ -205,7 +241,7 @@ __global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_wl_walker_kernel(
           c.L[c1] = (uint8_t)s2; c.L[c2] = (uint8_t)s1;
         } else jbin = ibin;
       } else jbin = ibin;
-      if (hist_every > 0 && i % hist_every == 0) my_hist[jbin - lo] += 1.0;              // :605-606
+      if (--hist_left == 0) { my_hist[jbin - lo] += 1.0; hist_left = hist_every; }        // :605-606
       my_lng[jbin - 1] += wl_f;                                                          // :612 / :624
     }
     acc = __shfl_sync(0xffffffffu, acc, 0);
