@@ -51,7 +51,18 @@ struct BrwWalkerCtx {
   bool fast;                   // lane-parallel dE
   double *extra;               // per-warp f64 scratch
   bool staged;
+  uint32_t Ls;                 // shared-memory address of the staged lattice (explicit ld.shared: the generic L
+                               // pointer may also be global, so plain loads through it compile to slower generic LD)
 };
+__device__ __forceinline__ int brw_lds_u8_at(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return (int)v;
+}
+// species at compact site i of the walker's lattice
+__device__ __forceinline__ int brw_walker_site(const BrwWalkerCtx &c, int i) {
+  return c.staged ? brw_lds_u8_at(c.Ls + (uint32_t)i) : (int)c.L[i];
+}
 
 // CTA-wide set-up: V and the neighbour table are built cooperatively, each warp stages its lattice.
 __device__ __forceinline__ BrwWalkerCtx brw_walker_begin(const BrwGeom &g, const BrwWalkerLayout &lay,
@@ -79,6 +90,7 @@ __device__ __forceinline__ BrwWalkerCtx brw_walker_begin(const BrwGeom &g, const
   c.tab = lay.use_tab ? tab : nullptr;
   c.staged = lay.staged;
   c.L = lay.staged ? mine : lat_global;
+  c.Ls = lay.staged ? (uint32_t)__cvta_generic_to_shared(mine) : 0u;
   c.extra = reinterpret_cast<double *>(mine + lay.lat_bytes);
   if (lay.staged && valid)
     for (int i = lane; i < g.n_sites; i += 32) c.L[i] = lat_global[i];
@@ -105,7 +117,7 @@ __device__ __forceinline__ void brw_walker_pair(const BrwGeom &g, const BrwWalke
     for (int k = lane; k < g.ztot; k += 32) {
       const double *Vn = c.V + c.ksh[k] * SS;
       const int n1 = t1[k], n2 = t2[k];
-      const int a = c.L[n1], b = c.L[n2];
+      const int a = brw_lds_u8_at(c.Ls + n1), b = brw_lds_u8_at(c.Ls + n2);      // fast => table => staged
       const int u1 = n1 == c1 ? s2 : (n1 == c2 ? s1 : a);
       const int u2 = n2 == c1 ? s2 : (n2 == c2 ? s1 : b);
       d += (Vn[u1 * S + s2] - Vn[a * S + s1]) + (Vn[u2 * S + s1] - Vn[b * S + s2]);
@@ -172,7 +184,7 @@ __global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_chain_metropolis_ke
     const int x1 = pr.x1, y1 = pr.y1, z1 = pr.z1, x2 = pr.x2, y2 = pr.y2, z2 = pr.z2;
     const uint32_t w = pr.spare;
     const int c1 = brw_grid_to_compact(g, x1, y1, z1), c2 = brw_grid_to_compact(g, x2, y2, z2);
-    const int s1 = c.L[c1], s2 = c.L[c2];
+    const int s1 = brw_walker_site(c, c1), s2 = brw_walker_site(c, c2);
     if (s1 == s2) { acc++; continue; }                        // src/metropolis.F90:774-777
     double before, after;
     brw_walker_pair(g, c, x1, y1, z1, x2, y2, z2, c1, c2, s1, s2, &scratch[warp], before, after);
@@ -214,6 +226,7 @@ __global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_wl_walker_kernel(
   BrwProposal mine = {};
   double my_logu = 0.0;
   long hist_left = hist_every > 0 ? hist_every : -1;           // trials until the next histogram sample (i % hist_every == 0)
+  int ibin = brw_bin_index(e_unswapped, edge0, range, bins);
   for (long i = 1; i <= n_trials; i++) {
     const int slot = (int)((i - 1) & 31);
     if (slot == 0) {
@@ -224,14 +237,17 @@ __global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_wl_walker_kernel(
     const double logu = __shfl_sync(0xffffffffu, my_logu, slot);
     const int x1 = pr.x1, y1 = pr.y1, z1 = pr.z1, x2 = pr.x2, y2 = pr.y2, z2 = pr.z2;
     const int c1 = brw_grid_to_compact(g, x1, y1, z1), c2 = brw_grid_to_compact(g, x2, y2, z2);
-    const int s1 = c.L[c1], s2 = c.L[c2];
+    const int s1 = brw_walker_site(c, c1), s2 = brw_walker_site(c, c2);
     e_swapped = e_unswapped;
     if (s1 != s2) {
       double pair_unswapped, pair_swapped;
       brw_walker_pair(g, c, x1, y1, z1, x2, y2, z2, c1, c2, s1, s2, &scratch[warp], pair_unswapped, pair_swapped);
       e_swapped = __dadd_rn(__dsub_rn(e_unswapped, pair_unswapped), pair_swapped);      // :568
     }
-    int ibin = brw_bin_index(e_unswapped, edge0, range, bins), jbin = brw_bin_index(e_swapped, edge0, range, bins);
+    // bin of the current state is carried from trial to trial (same value as recomputing it: src/wang-landau.F90:571);
+    // a same-species proposal leaves the energy, hence the bin, unchanged
+    const int jbin_new = s1 != s2 ? brw_bin_index(e_swapped, edge0, range, bins) : ibin;
+    int jbin = jbin_new;
     // decision on lane 0 (it owns ln g / hist)
     int acc = 0;
     if (lane == 0) {
@@ -245,7 +261,7 @@ __global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_wl_walker_kernel(
       my_lng[jbin - 1] += wl_f;                                                          // :612 / :624
     }
     acc = __shfl_sync(0xffffffffu, acc, 0);
-    if (acc) { accepted++; e_unswapped = e_swapped; }
+    if (acc) { accepted++; e_unswapped = e_swapped; ibin = jbin_new; }
     __syncwarp();
   }
   for (int i = lane; i < bins; i += 32) g_lng[i] = my_lng[i];
@@ -278,7 +294,7 @@ __global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_wl_enter_window_ker
     const int x1 = pr.x1, y1 = pr.y1, z1 = pr.z1, x2 = pr.x2, y2 = pr.y2, z2 = pr.z2;
     const uint32_t u = pr.spare;
     const int c1 = brw_grid_to_compact(g, x1, y1, z1), c2 = brw_grid_to_compact(g, x2, y2, z2);
-    const int s1 = c.L[c1], s2 = c.L[c2];
+    const int s1 = brw_walker_site(c, c1), s2 = brw_walker_site(c, c2);
     if (s1 != s2) {                                                                       // :710
       double pu, ps;
       brw_walker_pair(g, c, x1, y1, z1, x2, y2, z2, c1, c2, s1, s2, &scratch[warp], pu, ps);
