@@ -133,12 +133,17 @@ __device__ __forceinline__ void brw_walker_pair(const BrwGeom &g, const BrwWalke
     brw_warp_pair_energies_t(g, c.V, c.L, nb, c1, c2, s1, s2, w, before, after);
   }
 }
+struct BrwProposal;
+__device__ __forceinline__ void brw_walker_pair_lane(const BrwGeom &g, const BrwWalkerCtx &c, const BrwProposal &mine, int src,
+                                                     int c1, int c2, int s1, int s2, BrwWarpScratch *w, double &before,
+                                                     double &after);
 // Proposals are counter-based (Philox counter = trial index), so they can be generated 32 trials at a
 // time: lane l computes the proposal of trial (base + l) -- two Philox blocks, the reference's
 // random_site / random_nbr arithmetic -- and each trial then broadcasts its lane's values.  Same
 // counters, same values as a per-trial draw; ~30x fewer RNG instructions per trial.
 struct BrwProposal {
   int x1, y1, z1, x2, y2, z2;
+  int c1, c2;                // compact indices of the two sites (all the table-driven paths need)
   uint32_t spare;            // 4th word of the second block: the uniform of the accept test
 };
 __device__ __forceinline__ BrwProposal brw_propose_philox(const BrwGeom &g, int nbr_swap, long t, uint32_t tag,
@@ -151,6 +156,8 @@ __device__ __forceinline__ BrwProposal brw_propose_philox(const BrwGeom &g, int 
   if (nbr_swap) brw_random_nbr(g, brw_u01(r1.w), p.x1, p.y1, p.z1, p.x2, p.y2, p.z2);
   else brw_random_site(g, brw_u01(r2.x), brw_u01(r2.y), brw_u01(r2.z), p.x2, p.y2, p.z2);
   p.spare = r2.w;
+  p.c1 = brw_grid_to_compact(g, p.x1, p.y1, p.z1);
+  p.c2 = brw_grid_to_compact(g, p.x2, p.y2, p.z2);
   return p;
 }
 __device__ __forceinline__ BrwProposal brw_proposal_from_lane(const BrwProposal &mine, int src) {
@@ -159,7 +166,24 @@ __device__ __forceinline__ BrwProposal brw_proposal_from_lane(const BrwProposal 
   p.z1 = __shfl_sync(0xffffffffu, mine.z1, src); p.x2 = __shfl_sync(0xffffffffu, mine.x2, src);
   p.y2 = __shfl_sync(0xffffffffu, mine.y2, src); p.z2 = __shfl_sync(0xffffffffu, mine.z2, src);
   p.spare = __shfl_sync(0xffffffffu, mine.spare, src);
+  p.c1 = __shfl_sync(0xffffffffu, mine.c1, src); p.c2 = __shfl_sync(0xffffffffu, mine.c2, src);
   return p;
+}
+// the three values every trial needs (compact sites + the spare random word); the grid coordinates are fetched only
+// by the path without a neighbour table (brw_walker_pair_lane)
+__device__ __forceinline__ void brw_proposal_sites_from_lane(const BrwProposal &mine, int src, int &c1, int &c2, uint32_t &spare) {
+  c1 = __shfl_sync(0xffffffffu, mine.c1, src); c2 = __shfl_sync(0xffffffffu, mine.c2, src);
+  spare = __shfl_sync(0xffffffffu, mine.spare, src);
+}
+
+__device__ __forceinline__ void brw_walker_pair_lane(const BrwGeom &g, const BrwWalkerCtx &c, const BrwProposal &mine, int src,
+                                                     int c1, int c2, int s1, int s2, BrwWarpScratch *w, double &before,
+                                                     double &after) {
+  if (c.tab) brw_walker_pair(g, c, 0, 0, 0, 0, 0, 0, c1, c2, s1, s2, w, before, after);      // coordinates unused with the table
+  else {
+    const BrwProposal pr = brw_proposal_from_lane(mine, src);
+    brw_walker_pair(g, c, pr.x1, pr.y1, pr.z1, pr.x2, pr.y2, pr.z2, c1, c2, s1, s2, w, before, after);
+  }
 }
 
 // ---- Metropolis chains -------------------------------------------------------------------------
@@ -180,14 +204,12 @@ __global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_chain_metropolis_ke
   BrwProposal mine = {};
   for (long t = 0; t < n_trials; t++) {
     if ((t & 31) == 0) mine = brw_propose_philox(g, nbr_swap, t + lane, 0u, (uint32_t)r, off_lo, k0, k1 ^ off_hi);
-    const BrwProposal pr = brw_proposal_from_lane(mine, (int)(t & 31));
-    const int x1 = pr.x1, y1 = pr.y1, z1 = pr.z1, x2 = pr.x2, y2 = pr.y2, z2 = pr.z2;
-    const uint32_t w = pr.spare;
-    const int c1 = brw_grid_to_compact(g, x1, y1, z1), c2 = brw_grid_to_compact(g, x2, y2, z2);
+    int c1, c2; uint32_t w;
+    brw_proposal_sites_from_lane(mine, (int)(t & 31), c1, c2, w);
     const int s1 = brw_walker_site(c, c1), s2 = brw_walker_site(c, c2);
     if (s1 == s2) { acc++; continue; }                        // src/metropolis.F90:774-777
     double before, after;
-    brw_walker_pair(g, c, x1, y1, z1, x2, y2, z2, c1, c2, s1, s2, &scratch[warp], before, after);
+    brw_walker_pair_lane(g, c, mine, (int)(t & 31), c1, c2, s1, s2, &scratch[warp], before, after);
     const double dE = __dsub_rn(after, before);
     bool accept = dE < 0.0;
     if (!accept) accept = brw_u01(w) < exp(-b * dE);
@@ -199,6 +221,16 @@ __global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_chain_metropolis_ke
   }
   brw_walker_end(g, c);
   if (lane == 0) { att_out[r] += (unsigned long long)n_trials; acc_out[r] += acc; dE_out[r] += dsum; }
+}
+
+// bin_index (src/wang-landau.F90:515-523) without the f64 division on the common path: t = (e - e0) * (1/range) * bins
+// differs from the reference's ((e - e0) / range) * bins by < 1e-12, so the truncated integer can differ only if t lies
+// within that distance of an integer -- then (|t - rint(t)| < 1e-6) the reference expression is evaluated instead.
+// Same result as brw_bin_index for every input; ~100 cycles less dependent latency per trial.
+__device__ __forceinline__ int brw_bin_index_nodiv(double e, double edge0, double range, double inv_range, int bins) {
+  const double t = ((e - edge0) * inv_range) * (double)bins;
+  if (fabs(t - rint(t)) < 1e-6 || !(fabs(t) < 1e9)) return brw_bin_index(e, edge0, range, bins);
+  return (int)t + 1;
 }
 
 // ---- Wang-Landau sweeps ---------------------------------------------------------------------------
@@ -227,26 +259,26 @@ __global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_wl_walker_kernel(
   double my_logu = 0.0;
   long hist_left = hist_every > 0 ? hist_every : -1;           // trials until the next histogram sample (i % hist_every == 0)
   int ibin = brw_bin_index(e_unswapped, edge0, range, bins);
+  const double inv_range = 1.0 / range;
   for (long i = 1; i <= n_trials; i++) {
     const int slot = (int)((i - 1) & 31);
     if (slot == 0) {
       mine = brw_propose_philox(g, nbr_swap, i + lane, 0x01000000u, (uint32_t)w, off_lo, k0, k1 ^ off_hi);
       my_logu = log(brw_u01(mine.spare));      // u == 0 gives -inf: accepted, as in the reference
     }
-    const BrwProposal pr = brw_proposal_from_lane(mine, slot);
+    int c1, c2; uint32_t spare_unused;
+    brw_proposal_sites_from_lane(mine, slot, c1, c2, spare_unused);
     const double logu = __shfl_sync(0xffffffffu, my_logu, slot);
-    const int x1 = pr.x1, y1 = pr.y1, z1 = pr.z1, x2 = pr.x2, y2 = pr.y2, z2 = pr.z2;
-    const int c1 = brw_grid_to_compact(g, x1, y1, z1), c2 = brw_grid_to_compact(g, x2, y2, z2);
     const int s1 = brw_walker_site(c, c1), s2 = brw_walker_site(c, c2);
     e_swapped = e_unswapped;
     if (s1 != s2) {
       double pair_unswapped, pair_swapped;
-      brw_walker_pair(g, c, x1, y1, z1, x2, y2, z2, c1, c2, s1, s2, &scratch[warp], pair_unswapped, pair_swapped);
+      brw_walker_pair_lane(g, c, mine, slot, c1, c2, s1, s2, &scratch[warp], pair_unswapped, pair_swapped);
       e_swapped = __dadd_rn(__dsub_rn(e_unswapped, pair_unswapped), pair_swapped);      // :568
     }
     // bin of the current state is carried from trial to trial (same value as recomputing it: src/wang-landau.F90:571);
     // a same-species proposal leaves the energy, hence the bin, unchanged
-    const int jbin_new = s1 != s2 ? brw_bin_index(e_swapped, edge0, range, bins) : ibin;
+    const int jbin_new = s1 != s2 ? brw_bin_index_nodiv(e_swapped, edge0, range, inv_range, bins) : ibin;
     int jbin = jbin_new;
     // decision on lane 0 (it owns ln g / hist)
     int acc = 0;
@@ -290,14 +322,12 @@ __global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_wl_enter_window_ker
   BrwProposal mine = {};
   for (long i = 0; i < max_trials && !ok; i++) {
     if ((i & 31) == 0) mine = brw_propose_philox(g, 0, i + lane, 0x02000000u, (uint32_t)w, off_lo, k0, k1 ^ off_hi);
-    const BrwProposal pr = brw_proposal_from_lane(mine, (int)(i & 31));
-    const int x1 = pr.x1, y1 = pr.y1, z1 = pr.z1, x2 = pr.x2, y2 = pr.y2, z2 = pr.z2;
-    const uint32_t u = pr.spare;
-    const int c1 = brw_grid_to_compact(g, x1, y1, z1), c2 = brw_grid_to_compact(g, x2, y2, z2);
+    int c1, c2; uint32_t u;
+    brw_proposal_sites_from_lane(mine, (int)(i & 31), c1, c2, u);
     const int s1 = brw_walker_site(c, c1), s2 = brw_walker_site(c, c2);
     if (s1 != s2) {                                                                       // :710
       double pu, ps;
-      brw_walker_pair(g, c, x1, y1, z1, x2, y2, z2, c1, c2, s1, s2, &scratch[warp], pu, ps);
+      brw_walker_pair_lane(g, c, mine, (int)(i & 31), c1, c2, s1, s2, &scratch[warp], pu, ps);
       const double e_new = __dadd_rn(__dsub_rn(e, pu), ps);                                // :721
       const double delta = ((e_new - tgt) * (e_new - tgt) - (e - tgt) * (e - tgt)) * inv_two_sigma_sq;   // :725-727
       if (log(brw_u01(u)) < -delta) {                                                      // :729
