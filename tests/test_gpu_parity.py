@@ -654,6 +654,50 @@ def test_wl_and_ns_production_kernels(bw, orc, golden):
     assert np.allclose(e2, dev.total_energy(0, W), rtol=0, atol=1e-11)
 
 
+def test_walker_kernels_fast_dE_takes_the_reference_decisions(bw, orc, golden):
+    """The walker kernels' default lane-parallel dE (butterfly sum) against their reference-association instantiation
+    (dE_mode 0) on the same Philox streams: WL sweeps (bcc n=4, 6 shells), NS walks and small-lattice Metropolis chains
+    (fcc n=4) must take the same decisions -- identical ln g, histograms, accept counts and final configurations --
+    and their running energies agree to f64 rounding."""
+    V = golden["t04_V"]
+    sysm = orc.System("bcc", 4, 4, 4, 4, 6, V)
+    W, bins = 24, 512
+    edges = sysm.wl_bin_edges(-96.0, 0.0, bins)
+    gs = np.stack([random_config(orc, sysm, 300 + w) for w in range(W)])
+    for g in gs:
+        sysm.metropolis_trials(g, orc.MT(seed=2), 1.0 / (1500.0 * orc.K_B_IN_RY), 40 * 128)
+    res = []
+    for mode in (2, 0):
+        dev = bw.Device("bcc", 4, 4, 4, 4, 6, V, n_replicas=W)
+        dev.metropolis_set_mode(mode)
+        dev.set_config(gs)
+        lng = np.zeros((W, bins)); hist = np.zeros((W, bins))
+        acc, ef = dev.wl_sweeps(lng, hist, edges, 1, bins, 0.05, 12800, seed=9)
+        e_exact = dev.total_energy(0, W)
+        lim = e_exact + 2e-4
+        e2, nacc = dev.ns_walk(np.arange(W), e_exact, lim, 400, seed=10)
+        res.append((lng, hist, acc, ef, e2, nacc, dev.get_config(0, W)))
+    a, b = res
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.allclose(a[3], b[3], rtol=0, atol=1e-11)
+    assert np.array_equal(a[5], b[5]) and np.allclose(a[4], b[4], rtol=0, atol=1e-11)
+    assert np.array_equal(a[6], b[6])
+    # Metropolis chains on a lattice too small for boxes
+    Vf = golden["ex_FeNi_V"][: 2 * 2 * 4]
+    sf = orc.System("fcc", 4, 4, 4, 2, 4, Vf)
+    g = random_config(orc, sf, 5)
+    out = []
+    for mode in (2, 0):
+        dev = bw.Device("fcc", 4, 4, 4, 2, 4, Vf, n_replicas=16)
+        dev.metropolis_set_mode(mode)
+        assert dev.metropolis_plan()["use_box"] == 0
+        dev.set_config(np.stack([g] * 16))
+        att, acc, dE = dev.metropolis_run(1.0 / (900.0 * bw.K_B_IN_RY), 100 * sf.n_atoms, seed=3)
+        out.append((acc, dE, dev.get_config(0, 16)))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][2], out[1][2])
+    assert np.allclose(out[0][1], out[1][1], rtol=0, atol=1e-11)
+
+
 # ---------------------------------------------------------------------------------------------
 # edge cases and full-size properties
 def test_edge_cases_empty_and_degenerate_inputs(bw, orc, golden):
