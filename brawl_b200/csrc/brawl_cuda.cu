@@ -643,6 +643,15 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
     // whose steps are short enough for the box copies to be 9 % of a four-sweep phase
     int steps = h->tune_steps > 0 ? h->tune_steps : ((we ? 6 : 4) * p.box_sites + Mmax - 1) / Mmax;
     p.steps = std::max(8, std::min(steps, 512));
+    p.steps_a = p.steps;
+    pl->M_a = 0;
+    if (we && we->split) {
+      // group A holds NPA of the NP - 1 working planes (12 of 30 warps for the 64x64x32 box) and was measured to idle
+      // 5.3 % of the phase waiting for group B: give it that many more steps (unless the caller fixed the step count)
+      const int NPA = (p.mode[0].A[2] - 1) / 2;
+      pl->M_a = p.mode[0].A[1] * NPA * 2 * p.mode[0].A[0];
+      if (h->tune_steps <= 0) p.steps_a = p.steps + (p.steps * 53 + 500) / 1000;     // swept 0..17 %: +0.5 % at 5-9 %
+    }
     pl->threads = std::min(1024, ((Mmax + 31) / 32) * 32);
     pl->smem = (size_t)p.v_entries * 16 * 8 + (size_t)2 * g.ztot * 4 + 2 * sizeof(BrwStepParams) + 32 * 8 + p.box_sites;
     // offset tables per x-parity of the centre site
@@ -736,7 +745,7 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       pl->fast_fn = (void *)(h->dE_mode == 0 ? we->fn_exact : we->fn);
       pl->screened = h->dE_mode != 0; pl->word = true; pl->split = we->split;
       pl->fast_smem = blob.size() * sizeof(int) + 32 * 8 + 2 * (size_t)p.mode[0].A[1] * p.mode[0].A[2] * 4 + 16 +
-                      (size_t)(p.steps + 1) * 32 + (size_t)we->plp * p.bzc * 4;
+                      (size_t)(std::max(p.steps, p.steps_a) + 1) * 32 + (size_t)we->plp * p.bzc * 4;
       pl->threads = 32 * std::min(32, p.mode[0].A[1] * (p.mode[0].A[2] - (we->split ? 1 : 0)));
       BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)pl->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
     }
@@ -839,7 +848,7 @@ extern "C" int brawl_cuda_metropolis_enqueue(brawl_cuda_t *h, const double *beta
       BRW_LAUNCH_CHECK("brw_box_metropolis_kernel");
       launches++;
       phases++;
-      done += (int64_t)p.mode[mode].M * p.steps * p.boxes_per_replica;
+      done += ((int64_t)p.mode[mode].M * p.steps + (int64_t)pl->M_a * (p.steps_a - p.steps)) * p.boxes_per_replica;
     }
     if (next_offset) *next_offset = offset + (uint64_t)phases;
   } else {

@@ -40,6 +40,7 @@ struct BrwBoxParams {          // POD kernel parameter
   BrwBoxMode mode[BRW_MAX_MODES];
   int boxes_per_replica;
   int steps;
+  int steps_a;                 // SPLIT word kernels: steps of warp group A (fewer warps, shorter steps: it gets more of them)
   int v_entries;               // S*S*n_shells
   int row_mul;                 // word kernel: row of its fixed-point table = code_a*row_mul + code_b
 };
@@ -54,6 +55,7 @@ struct BrwPlan {
   double *d_Vrep = nullptr;    // [v_entries][16] lane-replicated V (layout [shell][centre][nbr])
   size_t smem = 0;
   int threads = 0, Mmax = 0;
+  int M_a = 0;                 // SPLIT word kernels: trials per step of warp group A (runs p.steps_a steps)
   void *fast_fn = nullptr;     // specialised kernel for this (lattice, shells, pitch), if instantiated
   bool screened = false;
   bool split = false;          // word kernel with two warp groups per CTA and shared z margin planes

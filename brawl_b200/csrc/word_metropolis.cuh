@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
   int *rowoff = reinterpret_cast<int *>(red + 32);                            // [2*NROWS]
   BrwDenseStep *sp = reinterpret_cast<BrwDenseStep *>(                        // [steps], 16-byte aligned
       smem_raw + (((size_t)tab_words * 4 + (size_t)p.v_entries * 8 + 32 * 8 + 2 * G::NROWS * 4 + 15) & ~(size_t)15));
-  uint32_t *wbox = reinterpret_cast<uint32_t *>(sp + p.steps + 1);            // [bzc][PLP]
+  const int sp_steps = SPLIT ? max(p.steps, p.steps_a) : p.steps;
+  uint32_t *wbox = reinterpret_cast<uint32_t *>(sp + sp_steps + 1);           // [bzc][PLP]
   __shared__ unsigned int s_att[32], s_acc[32];
 
   const int tid = threadIdx.x;
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
       rowoff[r] = 2 * PXP * (rr % G::NJ) + 4 * PLP * (rr / G::NJ);
     }
   }
-  for (int st = tid; st <= p.steps; st += blockDim.x)         // one entry past the last step (header prefetch)
+  for (int st = tid; st <= sp_steps; st += blockDim.x)
     brw_make_dense_step<2 * PX, 2 * PY, PZ, MARGIN, PXP, PLP, SPLIT>(k0, k1, (uint32_t)st, box_id, phase_lo, &sp[st]);
   brw_wbox_copy<LAT, PX, PY, PXP, PLP, false, PAIRW>(g, L, wbox, 0, PY * p.bzc, ox, oy, oz);
   __syncthreads();
@@ -441,7 +442,10 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
     }
   };
 
-  for (int step = 0; step < p.steps; step++) {
+  // the groups are independent, and group A (fewer warps) finishes a step sooner: it runs steps_a >= steps steps so
+  // that both groups end the phase together
+  const int my_steps = SPLIT && !grp ? p.steps_a : p.steps;
+  for (int step = 0; step < my_steps; step++) {
     if (SPLIT && warp >= n_work) break;                        // no row pair: not a member of either group barrier
     gather(step);
     decide();
