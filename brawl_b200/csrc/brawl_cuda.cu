@@ -650,7 +650,7 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       // 5.3 % of the phase waiting for group B: give it that many more steps (unless the caller fixed the step count)
       const int NPA = (p.mode[0].A[2] - 1) / 2;
       pl->M_a = p.mode[0].A[1] * NPA * 2 * p.mode[0].A[0];
-      if (h->tune_steps <= 0) p.steps_a = p.steps + (p.steps * 53 + 500) / 1000;     // swept 0..17 %: +0.5 % at 5-9 %
+      if (h->tune_steps <= 0 && !BRW_ANTI) p.steps_a = p.steps + (p.steps * 53 + 500) / 1000;     // swept 0..17 %: +0.5 % at 5-9 %
     }
     pl->threads = std::min(1024, ((Mmax + 31) / 32) * 32);
     pl->smem = (size_t)p.v_entries * 16 * 8 + (size_t)2 * g.ztot * 4 + 2 * sizeof(BrwStepParams) + 32 * 8 + p.box_sites;

@@ -97,6 +97,9 @@ __device__ __forceinline__ uint32_t brw_lo16(const uint32_t *p) { return *reinte
 #ifndef BRW_XP
 #define BRW_XP 0        // timing experiments only (results invalid): 1 skips the dE arithmetic, 2 skips the gathers
 #endif
+#ifndef BRW_ANTI
+#define BRW_ANTI 0      // 1: SPLIT groups in enforced anti-phase (timing experiment)
+#endif
 #ifndef BRW_INTDEC
 #define BRW_INTDEC 0    // 1: acceptance test without conversions / MUFU / fp64 (FMA + ALU pipes only); measured slower
 #endif
@@ -444,7 +447,20 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_word_kernel(
 
   // the groups are independent, and group A (fewer warps) finishes a step sooner: it runs steps_a >= steps steps so
   // that both groups end the phase together
-  const int my_steps = SPLIT && !grp ? p.steps_a : p.steps;
+  const int my_steps = SPLIT && !grp && !BRW_ANTI ? p.steps_a : p.steps;
+  if (SPLIT && BRW_ANTI) {
+    // experiment: the two groups in enforced anti-phase, one CTA barrier per half step (group A: gather s | decide s;
+    // group B: decide s-1 | gather s), so that the shared-memory-pipe half of one group runs beside the ALU half of
+    // the other.  Needs a decide half without MIO-queue instructions (BRW_INTDEC, BRW_TABG) to have a chance.
+    const int halves = 2 * p.steps + 1;
+    for (int hs = 0; hs < halves; hs++) {
+      const int t = hs - grp;
+      if (warp < n_work && t >= 0 && t < 2 * p.steps) {
+        if (t & 1) decide(); else gather(t >> 1);
+      }
+      __syncthreads();
+    }
+  } else
   for (int step = 0; step < my_steps; step++) {
     if (SPLIT && warp >= n_work) break;                        // no row pair: not a member of either group barrier
     gather(step);
