@@ -11,15 +11,21 @@ swaps between adjacent windows on different GPUs, the converged flags (:230) and
 the W x bins ln g table for dos_combine (:1147-1194) -- all through torch.distributed (NCCL on
 GPUs; gloo in the CPU tests of the host logic).
 
-Not mirrored (documented in DESIGN.md): dynamic window resizing (mpi_window_optimise -- i.e. this
-driver behaves like `performance = 2`), rho(E) sampling, merge_configs/load_window_config.
+Dynamic window resizing (mpi_window_optimise, :1211-1328) follows the reference's `performance` switch: 0/1 resize
+after pre-sampling and after every f-stage, 2/3 after pre-sampling only, 4 never (WLParams' default here; the
+reference's file default is 0 and `from_file` keeps that).  After a resize the reference reloads a stored
+configuration of a random bin of the new window (load_window_config, :1541-1554, from the bins x grid store that
+energy_explore/merge_configs fill); here the walkers are steered from their current configurations into the new
+window on the GPU by the enter_energy_window kernel instead -- no bins x grid store, same post-condition (every
+walker inside its window).  compute_mean_energy (:457-477) is evaluated after every stage (`mean_energy`).
+Not mirrored: rho(E) sampling.
 The pure functions below restate the reference's integer/f64 host arithmetic exactly.
 """
 import math
 
 import numpy as np
 
-from .engine import Device, RY_TO_EV, BrawlCudaError
+from .engine import Device, RY_TO_EV, K_B_IN_RY, BrawlCudaError
 
 
 def _f32(v):
@@ -31,7 +37,7 @@ class WLParams:
     e.g. wl_f = 0.05 is really 0.05000000074505806."""
 
     def __init__(self, mc_sweeps=100, bins=512, num_windows=4, bin_overlap=0.25, tolerance=5e-5, flatness=0.9,
-                 wl_f=0.05, energy_min=-96.0, energy_max=0.0, radial_samples=8, performance=2, nbr_swap=False):
+                 wl_f=0.05, energy_min=-96.0, energy_max=0.0, radial_samples=8, performance=4, nbr_swap=False):
         self.mc_sweeps, self.bins, self.num_windows = int(mc_sweeps), int(bins), int(num_windows)
         self.bin_overlap, self.tolerance, self.flatness = _f32(bin_overlap), _f32(tolerance), _f32(flatness)
         self.wl_f, self.energy_min, self.energy_max = _f32(wl_f), _f32(energy_min), _f32(energy_max)
@@ -40,7 +46,7 @@ class WLParams:
     @classmethod
     def from_file(cls, path):
         """read_wl_file (src/io.f90:951-1086): key=value lines, '#' comments, unknown keys ignored."""
-        kw = {}
+        kw = {"performance": 0}                              # io.f90:981
         conv = dict(mc_sweeps=int, bins=int, num_windows=int, bin_overlap=float, tolerance=float, flatness=float,
                     wl_f=float, energy_min=float, energy_max=float, radial_samples=int, performance=int)
         for line in open(path):
@@ -116,6 +122,123 @@ def dos_combine(lng_windows, window_indices):
         for j in range(beta_index, end + 1):         # same association as the reference: (buf + comb(bi)) - buf(bi)
             comb[j - 1] = buf[j - 1] + comb[beta_index - 1] - buf[beta_index - 1]
     return comb - comb.min()
+
+
+def _seq_sum(v):
+    """Fortran SUM of a short f64 array as gfortran evaluates it without -ffast-math: left to right
+    (Python's built-in sum() is compensated since 3.12 and numpy's is pairwise, so neither is used)."""
+    t = 0.0
+    for x in v:
+        t = t + float(x)
+    return t
+
+
+def energy_bin_width(n_atoms, energy_min, energy_max, bins):
+    """bin_width as create_energy_bins leaves it in the module variable (:980)."""
+    return (energy_max - energy_min) / float(np.float32(bins)) * (n_atoms / (RY_TO_EV * 1000))
+
+
+def compute_mean_energy(lng, edges, bins, bin_width):
+    """compute_mean_energy (:457-477): canonical mean energy from ln g at T = 10, 20, ... 3000 K.
+    Returns mean_energy[300][2] = (<E>(T) in Ry per cell, beta)."""
+    lng = np.asarray(lng, dtype=np.float64)
+    buf = lng - lng.max()
+    centre = np.asarray(edges[:bins], dtype=np.float64) + 0.5 * bin_width
+    out = np.zeros((300, 2))
+    for itemp in range(1, 301):
+        beta = 1.0 / (K_B_IN_RY * itemp * 10.0)
+        prob = buf[:bins] - beta * centre
+        prob = np.exp(prob - prob.max())
+        prob = prob / _seq_sum(prob)
+        out[itemp - 1, 0] = _seq_sum(centre * prob)
+        out[itemp - 1, 1] = beta
+    return out
+
+
+def sort_descending(a):
+    """sort_descending (:1686-1701): the reference's exchange sort of an index vector (1-based indices
+    returned); ties keep the order this particular algorithm produces, which decides where the
+    left-over bins go in window_optimise."""
+    n = len(a)
+    idx = list(range(1, n + 1))
+    for i in range(n - 1):
+        for j in range(i + 1, n):
+            if a[idx[i] - 1] < a[idx[j] - 1]:
+                idx[i], idx[j] = idx[j], idx[i]
+    return idx
+
+
+def _nint(x):
+    """Fortran NINT: round half away from zero."""
+    return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+
+def window_optimise(it, window_intervals, wl_mc_steps, diffusion_prev, bins):
+    """The rank-0 arithmetic of mpi_window_optimise (:1211-1311): resize the windows so that windows which
+    needed more trials per bin to become flat get fewer bins.  `it` is the argument the reference passes (0 after
+    pre-sampling, iter-1 in the main loop); wl_mc_steps[W] = trials each window spent before it converged (summed
+    over its walkers); diffusion_prev[W] = the previous blend (1/W initially, :1079).  Returns
+    (new window_intervals [W][2], 1-based inclusive; new diffusion_prev).  The caller then applies create_overlap
+    (mpi_arrays, :1351-1379).  Reference quirks kept: the per-window width used for the weights is
+    ABS(first-last+1) = width-2; the floor w_min = 0.02; weights_log is computed but never used."""
+    W = len(wl_mc_steps)
+    iv = np.array(window_intervals, dtype=np.int64).copy()
+    if W < 2:
+        return iv, np.array(diffusion_prev, dtype=np.float64).copy()
+    alpha = 0.8 * (0.8 ** (it - 1))
+    if it == 0:
+        alpha = 1.0
+    w_min = 0.02
+    prev = [float(x) for x in diffusion_prev]
+    w_mc = []
+    for i in range(W):
+        first, last = int(iv[i, 0]), int(iv[i, 1])
+        with np.errstate(divide="ignore", invalid="ignore"):          # width-2 window: x/0 = Inf, 1/Inf = 0 as in IEEE Fortran
+            w_mc.append(float(np.float64(1.0) / (np.float64(wl_mc_steps[i]) / np.float64(np.float32(abs(first - last + 1))))))
+    s = _seq_sum(w_mc)
+    w_mc = [x / s for x in w_mc]
+    frac = [alpha * a + (1.0 - alpha) * b for a, b in zip(w_mc, prev)]
+    s = _seq_sum(frac)
+    frac = [x / s for x in frac]
+    new_prev = np.array(frac, dtype=np.float64)
+    frac = [max(x, w_min) for x in frac]
+    free = [x > w_min for x in frac]
+    if abs(_seq_sum(frac) - 1.0) > 1.0e-12:
+        rem = 1.0 - _seq_sum(frac)
+        if any(free):
+            sum_free = _seq_sum([x for x, f in zip(frac, free) if f])
+            if sum_free > 0.0:
+                scale = rem / sum_free
+                frac = [x + x * scale if f else x for x, f in zip(frac, free)]
+    s = _seq_sum(frac)
+    frac = [x / s for x in frac]
+    nb = [_nint(float(np.float32(bins)) * x) for x in frac]
+    min_bins = max(int(w_min * bins), 2)
+    nb = [max(b, min_bins) for b in nb]
+    if sum(nb) != bins:
+        idx = sort_descending(nb)
+        diff = bins - sum(nb)
+        i = 1
+        guard = 0
+        while diff != 0:
+            j = idx[(i - 1) % W] - 1
+            if diff > 0:
+                nb[j] += 1
+                diff -= 1
+            elif nb[j] > min_bins:
+                nb[j] -= 1
+                diff += 1
+            i += 1
+            guard += 1
+            if guard > 4 * W * bins:
+                raise BrawlCudaError("window_optimise: %d bins cannot hold %d windows of >= %d bins" % (bins, W, min_bins))
+    iv[0, 1] = nb[0]
+    for i in range(1, W):
+        iv[i, 0] = iv[i - 1, 1] + 1
+        iv[i, 1] = iv[i, 0] + nb[i] - 1
+    iv[W - 1, 0] = iv[W - 2, 1] + 1
+    iv[W - 1, 1] = bins
+    return iv, new_prev
 
 
 def overlap_location(ibin, q, window_indices):
@@ -234,9 +357,27 @@ class WangLandau:
         self.energies = np.zeros(self.n_local)
         self.total_trials = 0
         self.stage_sweeps = []
+        # load balancing (:1016-1019, 1079, 1108): trials each window spent unconverged, previous blend of weights
+        self.wl_mc_steps = np.zeros(W)
+        self.diffusion_prev = np.full(W, 1.0 / float(np.float32(W)))
+        self.bin_width = energy_bin_width(self.n_atoms, params.energy_min, params.energy_max, params.bins)
+        self.mean_energy = np.full((300, 2), 1.0 / (K_B_IN_RY * 10.0))          # :1112
+        self.window_history = [self.window_indices.copy()]
+
+    def _set_windows(self, intervals):
+        """mpi_arrays (:1351-1379): new overlapping index ranges for every walker of this rank."""
+        self.intervals = np.array(intervals, dtype=np.int64)
+        self.window_indices = create_overlap(self.intervals, self.p.bin_overlap)
+        q = np.repeat(np.arange(self.first_window, self.first_window + self.w_local), self.walkers)
+        self.win_lo = self.window_indices[q, 0].astype(np.int32)
+        self.win_hi = self.window_indices[q, 1].astype(np.int32)
+        self.hist[...] = 0.0
+        self.window_history.append(self.window_indices.copy())
 
     # --- window entry (enter_energy_window, :643-741) ------------------------------------------------
-    def enter_energy_windows(self, max_rounds=200):
+    def enter_energy_windows(self, max_rounds=200, fresh=True):
+        """fresh=False: start from the walkers' current configurations (after a window resize); walkers already
+        inside their window leave the kernel at once."""
         p = self.p
         lo = self.edges[self.win_lo - 1]
         hi = self.edges[self.win_hi]
@@ -245,7 +386,7 @@ class WangLandau:
         sigma = _f32(0.0025) * abs(p.energy_max - p.energy_min) * self.n_atoms / (RY_TO_EV * 1000)
         inv = 1.0 / (2.0 * sigma ** 2)
         pending = np.ones(self.n_local, dtype=bool)
-        for w in range(self.n_local):
+        for w in range(self.n_local if fresh else 0):
             self.dev.set_config(random_configuration(self.lattice, *self.n, self.counts, self.rng_local), w, 1)
         for _ in range(max_rounds):
             e, ent = self.dev.wl_enter_window(target, lo + cond, hi - cond, inv, self.n_atoms * 250, self.seed, self.offset)
@@ -320,12 +461,16 @@ class WangLandau:
             ok.append(bool(good))
         return ok
 
-    def _stage(self, wl_f, min_hist=None, max_sweeps=100000, exchange_every=1):
+    def _stage(self, wl_f, min_hist=None, max_sweeps=100000, exchange_every=1, it=0, resize=False):
         converged = [False] * self.w_local
         n = 0
+        per_sweep = float(self.p.mc_sweeps * self.n_atoms * self.walkers)        # every walker adds its trials (:217, :775)
         while True:
             n += 1
             self._sweeps(wl_f)
+            for q in range(self.w_local):
+                if not converged[q]:
+                    self.wl_mc_steps[self.first_window + q] += per_sweep
             if n % exchange_every == 0:
                 self._replica_exchange()
             flat = self._flat_windows(min_hist)
@@ -336,6 +481,16 @@ class WangLandau:
         self.hist[...] = 0.0
         combined = dos_combine(self._window_lng_all(), self.window_indices)      # dos_average + dos_combine
         self.lng[...] = combined[None, :]
+        steps = self.comm.all_gather(self.wl_mc_steps).sum(axis=0)               # MPI_ALLREDUCE(wl_mc_steps) (:244, :814)
+        self.last_mc_steps = steps.copy()
+        if resize and self.p.num_windows > 1:
+            # every rank evaluates the same arithmetic on the same inputs (the reference computes on rank 0 and broadcasts)
+            iv, self.diffusion_prev = window_optimise(it, self.intervals, steps, self.diffusion_prev, self.p.bins)
+            self._set_windows(iv)
+        self.wl_mc_steps[...] = 0.0
+        self.mean_energy = compute_mean_energy(combined, self.edges, self.p.bins, self.bin_width)
+        if resize and self.p.num_windows > 1:
+            self.enter_energy_windows(fresh=False)                               # in place of load_window_config
         return combined
 
     def run(self, max_sweeps_per_stage=100000, callback=None):
@@ -344,9 +499,11 @@ class WangLandau:
         self.enter_energy_windows()
         wl_f = p.wl_f
         combined = self._stage(wl_f, min_hist=1000.0 / float(np.float32(self.walkers)), max_sweeps=max_sweeps_per_stage,
-                               exchange_every=10)
+                               exchange_every=10, it=0, resize=p.performance in (0, 1, 2, 3))
+        it = 1
         while wl_f > p.tolerance:
-            combined = self._stage(wl_f, max_sweeps=max_sweeps_per_stage)
+            combined = self._stage(wl_f, max_sweeps=max_sweeps_per_stage, it=it, resize=p.performance in (0, 1))
+            it += 1
             wl_f = wl_f * 0.5
             if callback:
                 callback(wl_f, combined)

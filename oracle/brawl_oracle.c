@@ -526,3 +526,86 @@ void orc_radial_counts(const orc_sys *s, const int8_t *grid, int wc_range, int64
     }
   }
 }
+
+/* ---- Wang-Landau control plane (host arithmetic; parity UNPINNED: the reference ships no golden for it) ---- */
+
+/* compute_mean_energy, src/wang-landau.F90:457-477. out[300][2] = (<E>, beta). */
+void orc_wl_mean_energy(const double *lng, const double *edges, int bins, double bin_width, double k_b_in_ry,
+                        double *out) {
+  double mx = lng[0];
+  for (int b = 1; b < bins; b++) if (lng[b] > mx) mx = lng[b];
+  double *prob = (double *)malloc(sizeof(double) * (size_t)bins);
+  for (int itemp = 1; itemp <= 300; itemp++) {
+    const double beta = 1.0 / (k_b_in_ry * itemp * 10.0);
+    double pm = 0.0;
+    for (int b = 0; b < bins; b++) {
+      prob[b] = (lng[b] - mx) - beta * (edges[b] + 0.5 * bin_width);
+      if (b == 0 || prob[b] > pm) pm = prob[b];
+    }
+    double s = 0.0;
+    for (int b = 0; b < bins; b++) { prob[b] = exp(prob[b] - pm); s += prob[b]; }
+    double e = 0.0;
+    for (int b = 0; b < bins; b++) e += (edges[b] + 0.5 * bin_width) * (prob[b] / s);
+    out[2 * (itemp - 1)] = e;
+    out[2 * (itemp - 1) + 1] = beta;
+  }
+  free(prob);
+}
+
+/* mpi_window_optimise (rank-0 arithmetic), src/wang-landau.F90:1224-1311; sort_descending :1686-1701.
+   iv[W][2] in/out (1-based inclusive), prev[W] in/out (diffusion_prev). Returns 0, or 1 if W < 2 (nothing done). */
+int orc_wl_window_optimise(int iter, int W, int64_t *iv, const double *mc_steps, double *prev, int bins) {
+  if (W < 2) return 1;
+  double alpha = 0.8 * pow(0.8, (double)(iter - 1));
+  if (iter == 0) alpha = 1.0;
+  const double w_min = 0.02;
+  double *wmc = (double *)malloc(sizeof(double) * (size_t)W), *frac = (double *)malloc(sizeof(double) * (size_t)W);
+  int *nb = (int *)malloc(sizeof(int) * (size_t)W), *idx = (int *)malloc(sizeof(int) * (size_t)W);
+  double s = 0.0;
+  for (int i = 0; i < W; i++) {
+    const long first = (long)iv[2 * i], last = (long)iv[2 * i + 1];
+    wmc[i] = 1.0 / (mc_steps[i] / (double)(float)labs(first - last + 1));
+    s += wmc[i];
+  }
+  double sf = 0.0;
+  for (int i = 0; i < W; i++) { frac[i] = alpha * (wmc[i] / s) + (1.0 - alpha) * prev[i]; sf += frac[i]; }
+  for (int i = 0; i < W; i++) { frac[i] /= sf; prev[i] = frac[i]; }
+  double tot = 0.0, sum_free = 0.0;
+  int any_free = 0;
+  for (int i = 0; i < W; i++) { if (frac[i] < w_min) frac[i] = w_min; tot += frac[i]; }
+  if (fabs(tot - 1.0) > 1.0e-12) {
+    for (int i = 0; i < W; i++) if (frac[i] > w_min) { any_free = 1; sum_free += frac[i]; }
+    if (any_free && sum_free > 0.0) {
+      const double scale = (1.0 - tot) / sum_free;
+      for (int i = 0; i < W; i++) if (frac[i] > w_min) frac[i] = frac[i] + frac[i] * scale;
+    }
+  }
+  tot = 0.0;
+  for (int i = 0; i < W; i++) tot += frac[i];
+  int min_bins = (int)(w_min * bins);
+  if (min_bins < 2) min_bins = 2;
+  long have = 0;
+  for (int i = 0; i < W; i++) {
+    nb[i] = (int)lround((double)(float)bins * (frac[i] / tot));      /* NINT: half away from zero */
+    if (nb[i] < min_bins) nb[i] = min_bins;
+    have += nb[i];
+  }
+  if (have != bins) {
+    for (int i = 0; i < W; i++) idx[i] = i;
+    for (int i = 0; i < W - 1; i++)
+      for (int j = i + 1; j < W; j++)
+        if (nb[idx[i]] < nb[idx[j]]) { int t = idx[i]; idx[i] = idx[j]; idx[j] = t; }
+    long diff = bins - have;
+    for (long i = 0; diff != 0 && i < 8L * W * bins; i++) {
+      const int j = idx[i % W];
+      if (diff > 0) { nb[j]++; diff--; }
+      else if (nb[j] > min_bins) { nb[j]--; diff++; }
+    }
+  }
+  iv[1] = nb[0];
+  for (int i = 1; i < W; i++) { iv[2 * i] = iv[2 * (i - 1) + 1] + 1; iv[2 * i + 1] = iv[2 * i] + nb[i] - 1; }
+  iv[2 * (W - 1)] = iv[2 * (W - 2) + 1] + 1;
+  iv[2 * (W - 1) + 1] = bins;
+  free(wmc); free(frac); free(nb); free(idx);
+  return 0;
+}

@@ -227,3 +227,23 @@ def ref_mt_lib():
     L.f90_init_genrand.restype = C.c_ulong
     L.f90_init_genrand.argtypes = [C.c_int, C.c_int, C.c_ulong]
     return L
+
+
+def wl_mean_energy(lng, edges, bins, bin_width):
+    """compute_mean_energy (src/wang-landau.F90:457-477) -> [300][2]."""
+    lng = np.ascontiguousarray(lng, dtype=np.float64)
+    edges = np.ascontiguousarray(edges, dtype=np.float64)
+    out = np.zeros((300, 2))
+    lib().orc_wl_mean_energy(lng.ctypes.data_as(C.c_void_p), edges.ctypes.data_as(C.c_void_p), C.c_int(bins),
+                             C.c_double(bin_width), C.c_double(K_B_IN_RY), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def wl_window_optimise(it, intervals, mc_steps, diffusion_prev, bins):
+    """mpi_window_optimise rank-0 arithmetic (src/wang-landau.F90:1224-1311) -> (intervals, diffusion_prev)."""
+    iv = np.ascontiguousarray(intervals, dtype=np.int64).copy()
+    mc = np.ascontiguousarray(mc_steps, dtype=np.float64)
+    prev = np.ascontiguousarray(diffusion_prev, dtype=np.float64).copy()
+    lib().orc_wl_window_optimise(C.c_int(it), C.c_int(iv.shape[0]), iv.ctypes.data_as(C.c_void_p),
+                                 mc.ctypes.data_as(C.c_void_p), prev.ctypes.data_as(C.c_void_p), C.c_int(bins))
+    return iv, prev

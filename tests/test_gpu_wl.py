@@ -44,3 +44,31 @@ def test_wang_landau_golden_04(orc, golden):
     print("WL: %.1f s, %d sweeps calls per stage %s, %.3g trials, NRMSE %.4f" % (dt, sum(drv.stage_sweeps), drv.stage_sweeps, drv.total_trials, err))
     assert lng.min() == 0.0 and np.all(np.isfinite(lng))
     assert err < 0.01, err
+
+
+def test_wang_landau_dynamic_windows_golden_04(orc, golden):
+    """The reference's default `performance = 0`: windows resized by mpi_window_optimise (wang-landau.F90:1211-1328)
+    after pre-sampling and after every f-stage, walkers steered into the new windows on the GPU; same golden ln g(E),
+    same 1 % NRMSE criterion (tests/ci_test.py:42-50)."""
+    from brawl_b200 import wang_landau as wl
+    p = wl.WLParams(mc_sweeps=100, bins=512, num_windows=4, bin_overlap=0.25, tolerance=5e-5, flatness=0.90,
+                    wl_f=0.05, energy_min=-96, energy_max=0.0, radial_samples=8, performance=0)
+    drv = wl.WangLandau("bcc", 4, 4, 4, 4, 6, golden["t04_V"], [32, 32, 32, 32], p, walkers=8, seed=2025)
+    t0 = time.time()
+    lng = drv.run()
+    dt = time.time() - t0
+    ref = np.asarray(golden["t04_wl_dos"], dtype=np.float64)
+    err = nrmse(ref, lng)
+    widths = [(h[:, 1] - h[:, 0] + 1).tolist() for h in drv.window_history]
+    print("WL dynamic windows: %.1f s, sweeps per stage %s, NRMSE %.4f, widths %s -> %s" % (dt, drv.stage_sweeps, err, widths[0], widths[-1]))
+    assert len(drv.window_history) == 1 + len(drv.stage_sweeps)
+    for h in drv.window_history:
+        assert h[0, 0] == 1 and h[-1, 1] == 512 and np.all(h[1:, 0] <= h[:-1, 1])
+    e = drv.dev.total_energy(0, drv.n_local)
+    lo = drv.edges[drv.win_lo - 1]; hi = drv.edges[drv.win_hi]
+    assert np.all((e > lo) & (e < hi)) and np.allclose(e, drv.energies, rtol=0, atol=1e-11)
+    assert lng.min() == 0.0 and np.all(np.isfinite(lng))
+    assert err < 0.01, err
+    # <E>(T) from the final ln g (compute_mean_energy, :457-477) against the same sum over the golden ln g
+    me_ref = wl.compute_mean_energy(ref, drv.edges, 512, drv.bin_width)
+    assert np.max(np.abs(drv.mean_energy[29:, 0] - me_ref[29:, 0])) < 0.02 * abs(drv.edges[0])      # T >= 300 K

@@ -106,3 +106,141 @@ def test_collectives_world_size_2_gloo():
     assert res[0][2] == res[1][2]                               # same exchange plan on both ranks
     assert res[0][3] == res[1][3] == 3.0
     assert res[0][4] == [0.0, 0.0, 1.0, 1.0]
+
+
+def test_window_optimise_matches_oracle_and_keeps_invariants(orc):
+    """mpi_window_optimise arithmetic (wang-landau.F90:1224-1311): the host mirror against the oracle's C restatement
+    on seeded inputs, plus the invariants the reference relies on (contiguous cover of 1..bins, minimum width)."""
+    from brawl_b200 import wang_landau as wl
+    rng = np.random.default_rng(11)
+    for case in range(300):
+        W = int(rng.integers(2, 17))
+        bins = int(rng.choice([64, 128, 512, 1000]))
+        if max(int(0.02 * bins), 2) * W > bins:
+            continue
+        iv = wl.divide_range(bins, W)
+        prev = np.full(W, 1.0 / np.float32(W))
+        spread = 10.0 ** rng.uniform(0, 3)
+        for it in range(0, 4):
+            mc = np.floor(rng.uniform(1, spread, W)) * 100 * 128
+            a_iv, a_prev = wl.window_optimise(it, iv, mc, prev, bins)
+            b_iv, b_prev = orc.wl_window_optimise(it, iv, mc, prev, bins)
+            assert np.array_equal(a_iv, b_iv), (case, it)
+            assert np.array_equal(a_prev, b_prev)
+            assert a_iv[0, 0] == 1 and a_iv[-1, 1] == bins
+            assert np.all(a_iv[1:, 0] == a_iv[:-1, 1] + 1)
+            widths = a_iv[:, 1] - a_iv[:, 0] + 1
+            assert widths.sum() == bins and widths.min() >= max(int(0.02 * bins), 2)
+            assert abs(a_prev.sum() - 1.0) < 1e-12
+            iv, prev = a_iv, a_prev
+    # equal effort and equal windows: nothing moves (alpha = 1 after pre-sampling)
+    iv = wl.divide_range(512, 4)
+    out, prev = wl.window_optimise(0, iv, [1e6] * 4, [0.25] * 4, 512)
+    assert out.tolist() == iv.tolist() and np.allclose(prev, 0.25)
+    # a window that needed 3x the trials per bin shrinks, the others grow; later iterations damp the change
+    out, prev = wl.window_optimise(0, iv, [3e6, 1e6, 1e6, 1e6], [0.25] * 4, 512)
+    w = out[:, 1] - out[:, 0] + 1
+    assert w[0] < 128 and np.all(w[1:] > 128) and w.sum() == 512
+    out2, _ = wl.window_optimise(3, iv, [3e6, 1e6, 1e6, 1e6], [0.25] * 4, 512)
+    w2 = out2[:, 1] - out2[:, 0] + 1
+    assert w[0] < w2[0] < 128
+    assert wl.sort_descending([5, 9, 5, 9, 1]) == [2, 4, 3, 1, 5]          # hand-traced exchange sort: not stable
+    assert wl.window_optimise(0, [[1, 512]], [1e6], [1.0], 512)[0].tolist() == [[1, 512]]      # one window: untouched
+
+
+def test_compute_mean_energy_matches_oracle(orc, golden):
+    """compute_mean_energy (wang-landau.F90:457-477) on the reference's own ln g(E) of regression case 04."""
+    from brawl_b200 import wang_landau as wl
+    lng = np.asarray(golden["t04_wl_dos"], dtype=np.float64)
+    edges = wl.create_energy_bins(128, -96.0, 0.0, 512)
+    width = wl.energy_bin_width(128, -96.0, 0.0, 512)
+    me = wl.compute_mean_energy(lng, edges, 512, width)
+    ref = orc.wl_mean_energy(lng, edges, 512, width)
+    assert me.shape == (300, 2) and np.array_equal(me[:, 1], ref[:, 1])
+    assert np.allclose(me[:, 0], ref[:, 0], rtol=1e-13, atol=0)         # libm exp vs numpy exp: last-ulp differences only
+    assert np.all(np.diff(me[:, 0]) > 0)                                 # <E>(T) rises with T
+    assert edges[0] < me[0, 0] < me[-1, 0] < edges[-1]
+    assert me[0, 1] == 1.0 / (wl.K_B_IN_RY * 1 * 10.0)
+
+
+class _OracleDevice:
+    """Stand-in for brawl_b200.Device in the CPU test of the WL driver's control flow: the same host-facing
+    methods, with the trial loops run by the oracle (tests may use the oracle; the product never does)."""
+    orc = None
+
+    def __init__(self, lattice, n_1, n_2, n_3, n_species, n_shells, V_ex, device=0, n_replicas=1):
+        o = self.orc
+        self.sys = o.System(lattice, n_1, n_2, n_3, n_species, n_shells, V_ex)
+        self.n_atoms, self.n_replicas = self.sys.n_atoms, n_replicas
+        self.g = [None] * n_replicas
+        self.mt = [o.MT(seed=1000 + r + 17 * device) for r in range(n_replicas)]
+        self.rng = np.random.default_rng(77 + device)
+
+    def set_config(self, config, first_replica=0, n=None):
+        self.g[first_replica] = np.ascontiguousarray(config, dtype=np.int8).copy()
+
+    def swap_replicas(self, a, b):
+        self.g[a], self.g[b] = self.g[b], self.g[a]
+
+    def wl_sweeps(self, lng, hist, edges, win_lo, win_hi, wl_f, n_trials, seed=0, offset=0, nbr_swap=False):
+        acc, ef = np.zeros(len(self.g), dtype=np.int64), np.zeros(len(self.g))
+        for w in range(len(self.g)):
+            nb = int(win_hi[w] - win_lo[w] + 1)
+            h = np.ascontiguousarray(hist[w, :nb])
+            acc[w], ef[w] = self.sys.wl_sweeps(self.g[w], self.mt[w], lng[w], h, np.asarray(edges), win_lo[w], win_hi[w],
+                                               wl_f, n_trials, nbr_swap)
+            hist[w, :nb] = h
+        return acc, ef
+
+    def wl_enter_window(self, target, lo_e, hi_e, inv_two_sigma_sq, max_trials, seed=0, offset=0):
+        e_out, ent = np.zeros(len(self.g)), np.zeros(len(self.g), dtype=np.int32)
+        for w, g in enumerate(self.g):
+            sites = np.argwhere(g > 0)
+            e = self.sys.total_energy(g)
+            for _ in range(int(max_trials)):
+                if lo_e[w] < e < hi_e[w]:
+                    break
+                a, b = (tuple(s) for s in sites[self.rng.integers(0, len(sites), 2)])
+                if g[a] == g[b]:
+                    continue
+                g[a], g[b] = g[b], g[a]
+                e2 = self.sys.total_energy(g)
+                if np.log(self.rng.random()) < -((e2 - target[w]) ** 2 - (e - target[w]) ** 2) * inv_two_sigma_sq:
+                    e = e2
+                else:
+                    g[a], g[b] = g[b], g[a]
+            e_out[w], ent[w] = e, int(lo_e[w] < e < hi_e[w])
+        return e_out, ent
+
+
+def test_driver_dynamic_windows_control_flow(orc, golden, monkeypatch):
+    """performance = 0: windows are resized after pre-sampling and after every f-stage (wang-landau.F90:284-286, 820),
+    walkers end every stage inside their (new) window, ln g stays a sane stitched curve.  Trial loops by the oracle."""
+    from brawl_b200 import wang_landau as wl
+    _OracleDevice.orc = orc
+    monkeypatch.setattr(wl, "Device", _OracleDevice)
+    p = wl.WLParams(mc_sweeps=20, bins=64, num_windows=3, bin_overlap=0.25, tolerance=0.02, flatness=0.7, wl_f=0.05,
+                    energy_min=-60.0, energy_max=-5.0, performance=0)
+    drv = wl.WangLandau("bcc", 4, 4, 4, 4, 6, golden["t04_V"], [32, 32, 32, 32], p, walkers=2, seed=5)
+    seen = []
+    lng = drv.run(max_sweeps_per_stage=400, callback=lambda f, c: seen.append(drv.window_indices.copy()))
+    assert len(drv.stage_sweeps) == 3 and len(seen) == 2                   # pre-sampling + f = 0.05, 0.025
+    assert len(drv.window_history) == 1 + 3                               # one resize per stage
+    for idx in drv.window_history:
+        assert idx[0, 0] == 1 and idx[-1, 1] == 64
+        assert np.all(idx[1:, 0] <= idx[:-1, 1])                          # neighbours overlap
+    assert any(not np.array_equal(drv.window_history[0], h) for h in drv.window_history[1:])   # and they did move
+    assert np.all(drv.last_mc_steps > 0) and np.all(drv.wl_mc_steps == 0)
+    assert abs(drv.diffusion_prev.sum() - 1.0) < 1e-12
+    lo, hi = drv.edges[drv.win_lo - 1], drv.edges[drv.win_hi]
+    e = np.array([drv.dev.sys.total_energy(g) for g in drv.dev.g])
+    assert np.all((e > lo) & (e < hi))                                    # every walker inside its resized window
+    assert np.array_equal(e, drv.energies)
+    assert lng.min() == 0.0 and np.all(np.isfinite(lng)) and np.all(np.diff(lng[8:40]) > -1.0)
+    assert drv.mean_energy.shape == (300, 2) and np.all(np.diff(drv.mean_energy[:, 0]) >= 0)
+    # performance = 4: static windows
+    p4 = wl.WLParams(mc_sweeps=20, bins=64, num_windows=3, bin_overlap=0.25, tolerance=0.04, flatness=0.7, wl_f=0.05,
+                     energy_min=-60.0, energy_max=-5.0, performance=4)
+    d4 = wl.WangLandau("bcc", 4, 4, 4, 4, 6, golden["t04_V"], [32, 32, 32, 32], p4, walkers=2, seed=5)
+    d4.run(max_sweeps_per_stage=400)
+    assert len(d4.window_history) == 1
