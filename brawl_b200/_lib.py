@@ -26,6 +26,7 @@ _SIGNATURES = {
     "brawl_cuda_set_config": [_vp, _i, _i, _vp],
     "brawl_cuda_get_config": [_vp, _i, _i, _vp],
     "brawl_cuda_copy_replica": [_vp, _i, _i],
+    "brawl_cuda_random_config": [_vp, _i, _i, _vp, _u64, _u64],
     "brawl_cuda_total_energy": [_vp, _i, _i, _i, _vp],
     "brawl_cuda_site_energies": [_vp, _i, _vp],
     "brawl_cuda_pair_dE": [_vp, _i, _i64, _vp, _vp, _vp],

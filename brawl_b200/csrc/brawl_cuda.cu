@@ -8,6 +8,7 @@
 #include <cmath>
 #include <string>
 #include <vector>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/brawl_cuda.h"
 #include "brawl_common.cuh"
@@ -255,6 +256,70 @@ extern "C" int brawl_cuda_get_config(brawl_cuda_t *h, int first, int n, int8_t *
   }
   return 0;
 }
+// ---- start states on the device ---------------------------------------------------------------
+// A uniformly random arrangement of the species multiset on the lattice sites -- the start state initial_setup
+// (src/initialise.F90:434-617) and the WL re-randomisation (src/wang-landau.F90:671-674) produce -- for a batch of
+// replicas at once: every site draws a 44-bit Philox key (counter = site, replica, offset), the (replica, key) pairs
+// are radix-sorted (CUB, a library call: this is one-off set-up, not the hot path) carrying the species template
+// 0..0 1..1 2..2 as values, and the sorted values ARE the compact lattices.  Key collisions (expected 0.5 pairs in
+// 4 M sites) keep template order: a bias of order 1e-7 per site pair.
+struct BrwCum { long long c[BRW_MAX_SPECIES + 1]; };
+__global__ void __launch_bounds__(256) brw_shuffle_keys_kernel(long n_sites, int n_rep, int first, BrwCum cum, int S,
+                                                               uint32_t k0, uint32_t k1, uint32_t off_lo, uint32_t off_hi,
+                                                               unsigned long long *__restrict__ keys, uint8_t *__restrict__ vals) {
+  const long total = n_sites * n_rep;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / n_sites, c = i - r * n_sites;
+    const BrwPhilox4 p = brw_philox((uint32_t)c, (uint32_t)((unsigned long long)c >> 32) ^ 0x0A000000u, (uint32_t)(first + r),
+                                    off_lo, k0, k1 ^ off_hi);
+    keys[i] = ((unsigned long long)r << 44) | ((unsigned long long)p.x << 12) | (p.y >> 20);
+    int sp = 0;
+    while (sp < S - 1 && c >= cum.c[sp + 1]) sp++;
+    vals[i] = (uint8_t)sp;
+  }
+}
+extern "C" int brawl_cuda_random_config(brawl_cuda_t *h, int first, int n, const int64_t *species_count, uint64_t seed,
+                                        uint64_t offset) {
+  BRW_ENTER(h);
+  if (!species_count) return brw_fail("null species_count");
+  if (n < 1 || first < 0 || first + n > h->n_replicas) return brw_fail("replica range [%d,%d) out of [0,%d)", first, first + n, h->n_replicas);
+  const BrwGeom &g = h->g;
+  BrwCum cum;
+  cum.c[0] = 0;
+  for (int s = 0; s < g.S; s++) {
+    if (species_count[s] < 0) return brw_fail("negative count for species %d", s + 1);
+    cum.c[s + 1] = cum.c[s] + species_count[s];
+  }
+  if (cum.c[g.S] != (long long)g.n_sites)
+    return brw_fail("species counts sum to %lld, the lattice has %lld sites", cum.c[g.S], (long long)g.n_sites);
+  // chunks of <= 2^26 elements (and <= 2^19 replicas: the replica id sits above the 44 key bits)
+  int per = (int)std::max<long long>(1, std::min<long long>((1LL << 26) / (long long)g.n_sites, 1LL << 19));
+  for (int r0 = 0; r0 < n; r0 += per) {
+    const int m = std::min(per, n - r0);
+    const size_t ne = (size_t)g.n_sites * m;
+    size_t tmp_bytes = 0;
+    unsigned long long *kin = nullptr, *kout = nullptr;
+    uint8_t *vin = nullptr, *vout = h->d_lat + (size_t)(first + r0) * g.n_sites;
+    int rep_bits = 0;
+    while ((1 << rep_bits) < m) rep_bits++;
+    BRW_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kin, kout, vin, vout, (int)ne, 0, 44 + rep_bits, h->stream));
+    const size_t tmp_al = (tmp_bytes + 255) & ~(size_t)255;
+    if (brw_ensure_scratch(h, 2 * ne * sizeof(unsigned long long))) return 1;
+    if (brw_ensure_stage(h, ne + 256 + tmp_al)) return 1;
+    kin = (unsigned long long *)h->d_scratch;
+    kout = kin + ne;
+    vin = (uint8_t *)h->d_stage;
+    void *tmp = (uint8_t *)h->d_stage + ((ne + 255) & ~(size_t)255);
+    brw_shuffle_keys_kernel<<<grid_for((long)ne, 256), 256, 0, h->stream>>>((long)g.n_sites, m, first + r0, cum, g.S, (uint32_t)seed,
+                                                                           (uint32_t)(seed >> 32), (uint32_t)offset,
+                                                                           (uint32_t)(offset >> 32), kin, vin);
+    BRW_LAUNCH_CHECK("brw_shuffle_keys_kernel");
+    BRW_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kin, kout, vin, vout, (int)ne, 0, 44 + rep_bits, h->stream));
+  }
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 extern "C" int brawl_cuda_copy_replica(brawl_cuda_t *h, int src, int dst) {
   BRW_ENTER(h);
   BRW_REPLICA(h, src); BRW_REPLICA(h, dst);

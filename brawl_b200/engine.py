@@ -85,6 +85,14 @@ class Device:
         check(self.L.brawl_cuda_get_config(self.h, first_replica, n, _p(g)))
         return g[0] if (n == 1 and out is None) else g
 
+    def random_config(self, species_count, first_replica=0, n=1, seed=0x42726157, offset=0):
+        """Independent uniformly random arrangements of the species multiset for replicas [first, first+n), generated
+        on the device (initial_setup / WL re-randomisation for batches, SURVEY 8f#2)."""
+        cnt = np.ascontiguousarray(species_count, dtype=np.int64)
+        if cnt.size != self.S:
+            raise BrawlCudaError("species_count has %d entries, the system has %d species" % (cnt.size, self.S))
+        check(self.L.brawl_cuda_random_config(self.h, first_replica, n, _p(cnt), seed, offset))
+
     def copy_replica(self, src, dst):
         check(self.L.brawl_cuda_copy_replica(self.h, src, dst))
 

@@ -72,6 +72,14 @@ int brawl_cuda_get_config(brawl_cuda_t *h, int first_replica, int n, int8_t *gri
 /* replica dst := replica src on the device (nested_sampling.f90:151 walker cloning;
  * wang-landau.F90:1475-1495 same-GPU replica exchange) */
 int brawl_cuda_copy_replica(brawl_cuda_t *h, int src, int dst);
+/* Start states generated on the device: replicas [first_replica, first_replica+n) each become an independent,
+ * uniformly random arrangement of the species multiset species_count[n_species] (which must sum to the number of
+ * lattice sites).  Stands in for initial_setup (src/initialise.F90:434-617) called once per replica and for the
+ * re-randomisation inside enter_energy_window (src/wang-landau.F90:671-674) when thousands of replicas / walkers are
+ * started at once; the reference's own MT-stream fill stays a host routine (the drivers' initial_setup), this entry
+ * draws from Philox (seed, offset, replica, site).  Deterministic for given (seed, offset, first_replica + i). */
+int brawl_cuda_random_config(brawl_cuda_t *h, int first_replica, int n, const int64_t *species_count, uint64_t seed,
+                             uint64_t offset);
 
 /* ---- Hamiltonian ----------------------------------------------------------------------------
  * total_energy == setup%full_energy (src/bw_hamiltonian.f90:58-81).  exact_order != 0 adds the

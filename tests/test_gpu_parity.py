@@ -785,3 +785,62 @@ def test_full_size_128_cubed_properties(bw, golden):
         assert abs((e1 - e0) - dE[0]) < 1e-9 * abs(e1 - e0) + 1e-9, (e0, e1, dE[0])
         finals.append((g1, att[0], acc[0], e1))
     assert np.array_equal(finals[0][0], finals[1][0]) and finals[0][1:] == finals[1][1:]
+
+
+def test_random_config_on_device(bw, orc, golden):
+    """brawl_cuda_random_config: start states for a batch of replicas generated on the device.  Exact
+    species quotas per replica, sites only where the lattice has them, deterministic per (seed, offset, replica),
+    independent across replicas, uniform over sites (chi-square on per-site species frequencies over 512 replicas),
+    and a random-alloy energy that matches the oracle's host initial_setup ensemble."""
+    V = golden["ex_AlCrFeCoNi_V"][: 5 * 5 * 4]
+    R = 512
+    dev = bw.Device("bcc", 4, 4, 4, 5, 4, V, n_replicas=R)
+    counts = [26, 26, 26, 25, 25]
+    dev.random_config(counts, 0, R, seed=123, offset=7)
+    g = dev.get_config(0, R)
+    osys = orc.System("bcc", 4, 4, 4, 5, 4, V)
+    mask = osys.initial_setup(orc.MT(seed=1), *osys.quotas(conc=[0.2] * 5)) > 0
+    assert np.all((g > 0) == mask[None])
+    for r in range(R):
+        assert np.array_equal(np.bincount(g[r].ravel(), minlength=6), [512 - 128] + counts)
+    flat = g[:, mask]                                                     # [R][128] species 1..5
+    assert len({row.tobytes() for row in flat}) == R                      # all replicas differ
+    dev.random_config(counts, 0, R, seed=123, offset=7)                   # deterministic
+    assert np.array_equal(dev.get_config(0, R), g)
+    dev.random_config(counts, 5, 3, seed=123, offset=7)                   # a sub-range regenerates the same replicas
+    assert np.array_equal(dev.get_config(0, R), g)
+    dev.random_config(counts, 0, R, seed=123, offset=8)
+    g2 = dev.get_config(0, R)
+    assert not np.array_equal(g2, g)
+    # uniformity: species frequency at each site ~ Binomial(R, count/128); chi-square over 128 sites x 5 species
+    both = np.concatenate([flat, g2[:, mask]])                            # 1024 samples per site
+    n = both.shape[0]
+    chi = 0.0
+    for s, c in enumerate(counts, start=1):
+        exp = n * c / 128.0
+        chi += (((both == s).sum(axis=0) - exp) ** 2 / exp).sum()
+    dof = 128 * 4
+    assert abs(chi - dof) < 6 * np.sqrt(2 * dof), chi                     # 6 sigma
+    # pair correlations vanish: mean energy equals the host ensemble's within errors
+    e_dev = dev.total_energy(0, R)
+    mt = orc.MT(seed=99)
+    e_host = []
+    for _ in range(256):
+        conc, cnt = osys.quotas(numbers=counts)
+        e_host.append(osys.total_energy(osys.initial_setup(mt, conc, cnt)))
+    e_host = np.array(e_host)
+    se = np.sqrt(e_dev.var() / R + e_host.var() / e_host.size)
+    assert abs(e_dev.mean() - e_host.mean()) < 5 * se, (e_dev.mean(), e_host.mean(), se)
+    # errors: wrong multiset, bad range
+    with pytest.raises(bw.BrawlCudaError):
+        dev.random_config([26, 26, 26, 25, 24], 0, 1)
+    with pytest.raises(bw.BrawlCudaError):
+        dev.random_config(counts, R - 1, 2)
+    # the 128^3 bench lattice in one call (4 194 304 sites: chunking, 64-bit keys)
+    V4 = golden["ex_AlTiCrMo_V"][: 4 * 4 * 4]
+    big = bw.Device("bcc", 128, 128, 128, 4, 4, V4)
+    big.random_config([1048576] * 4, seed=5)
+    gb = big.get_config()
+    assert np.array_equal(np.bincount(gb.ravel(), minlength=5), [256 ** 3 - 4194304] + [1048576] * 4)
+    sub = gb[gb > 0].astype(np.int64)
+    assert abs((sub[:-1] == sub[1:]).mean() - 0.25) < 2e-3                # neighbours in site order uncorrelated
