@@ -363,6 +363,7 @@ class WangLandau:
         self.bin_width = energy_bin_width(self.n_atoms, params.energy_min, params.energy_max, params.bins)
         self.mean_energy = np.full((300, 2), 1.0 / (K_B_IN_RY * 10.0))          # :1112
         self.window_history = [self.window_indices.copy()]
+        self.rand_calls = 0
 
     def _set_windows(self, intervals):
         """mpi_arrays (:1351-1379): new overlapping index ranges for every walker of this rank."""
@@ -373,6 +374,12 @@ class WangLandau:
         self.win_hi = self.window_indices[q, 1].astype(np.int32)
         self.hist[...] = 0.0
         self.window_history.append(self.window_indices.copy())
+
+    def _rand_offset(self):
+        """Philox offset of the next batch of random start states: distinct per rank and per call (the replica index
+        the device mixes in is local to the handle)."""
+        self.rand_calls += 1
+        return (0x5A << 56) | (self.rank << 32) | self.rand_calls
 
     # --- window entry (enter_energy_window, :643-741) ------------------------------------------------
     def enter_energy_windows(self, max_rounds=200, fresh=True):
@@ -386,8 +393,8 @@ class WangLandau:
         sigma = _f32(0.0025) * abs(p.energy_max - p.energy_min) * self.n_atoms / (RY_TO_EV * 1000)
         inv = 1.0 / (2.0 * sigma ** 2)
         pending = np.ones(self.n_local, dtype=bool)
-        for w in range(self.n_local if fresh else 0):
-            self.dev.set_config(random_configuration(self.lattice, *self.n, self.counts, self.rng_local), w, 1)
+        if fresh:                                              # start states generated on the device, all walkers at once
+            self.dev.random_config(self.counts, 0, self.n_local, seed=self.seed, offset=self._rand_offset())
         for _ in range(max_rounds):
             e, ent = self.dev.wl_enter_window(target, lo + cond, hi - cond, inv, self.n_atoms * 250, self.seed, self.offset)
             self.offset += 1
@@ -395,8 +402,9 @@ class WangLandau:
             if not pending.any():
                 self.energies = e
                 return
+            off = self._rand_offset()
             for w in np.flatnonzero(pending):                 # re-randomise (:671-674)
-                self.dev.set_config(random_configuration(self.lattice, *self.n, self.counts, self.rng_local), int(w), 1)
+                self.dev.random_config(self.counts, int(w), 1, seed=self.seed, offset=off)
         raise BrawlCudaError("walkers failed to enter their energy windows")
 
     # --- one outer iteration: sweeps + window average + replica exchange -------------------------------

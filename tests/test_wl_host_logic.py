@@ -179,6 +179,11 @@ class _OracleDevice:
     def set_config(self, config, first_replica=0, n=None):
         self.g[first_replica] = np.ascontiguousarray(config, dtype=np.int8).copy()
 
+    def random_config(self, species_count, first_replica=0, n=1, seed=0, offset=0):
+        from brawl_b200 import wang_landau as wl
+        for r in range(first_replica, first_replica + n):
+            self.g[r] = wl.random_configuration("bcc", 4, 4, 4, species_count, self.rng)
+
     def swap_replicas(self, a, b):
         self.g[a], self.g[b] = self.g[b], self.g[a]
 
