@@ -18,7 +18,7 @@ configuration of a random bin of the new window (load_window_config, :1541-1554,
 energy_explore/merge_configs fill); here the walkers are steered from their current configurations into the new
 window on the GPU by the enter_energy_window kernel instead -- no bins x grid store, same post-condition (every
 walker inside its window).  compute_mean_energy (:457-477) is evaluated after every stage (`mean_energy`).
-Not mirrored: rho(E) sampling.
+rho(E) (:574-592, save_rho_E :346-381) is sampled with the SRO kernel when `wc_range` > 0 (`_sample_rho`).
 The pure functions below restate the reference's integer/f64 host arithmetic exactly.
 """
 import math
@@ -331,7 +331,7 @@ class WangLandau:
     (windows_per_rank * walkers) replicas."""
 
     def __init__(self, lattice, n_1, n_2, n_3, n_species, n_shells, V_ex, counts, params, walkers=8, device=0,
-                 rank=0, world=1, seed=0x42726157, torch_device=None):
+                 rank=0, world=1, seed=0x42726157, torch_device=None, wc_range=0):
         self.p, self.walkers, self.rank, self.world, self.seed = params, walkers, rank, world, seed
         W = params.num_windows
         if W % world:
@@ -364,6 +364,12 @@ class WangLandau:
         self.mean_energy = np.full((300, 2), 1.0 / (K_B_IN_RY * 10.0))          # :1112
         self.window_history = [self.window_indices.copy()]
         self.rand_calls = 0
+        # rho(E): radial densities per energy bin (:574-592, save_rho_E :346-381); off when wc_range == 0
+        self.wc_range, self.n_species = int(wc_range), n_species
+        self.radial_record = np.zeros((self.n_local, params.bins), dtype=np.int64)
+        self.radial_record_bool = np.zeros(params.bins, dtype=bool)
+        self.rho_sum = np.zeros((params.bins, max(self.wc_range, 1), n_species, n_species))
+        self.rho_saved, self.radial_min, self.rho_of_E = False, 0.0, None
 
     def _set_windows(self, intervals):
         """mpi_arrays (:1351-1379): new overlapping index ranges for every walker of this rank."""
@@ -416,11 +422,47 @@ class WangLandau:
         self.offset += 1
         self.total_trials += n_trials * self.n_local
         self.energies = ef
+        if self.wc_range and not self.rho_saved:
+            self._sample_rho()
         # intra-window average (:628-631): all walkers of a window are on this GPU
         w = self.walkers
         for q in range(self.w_local):
             self.lng[q * w:(q + 1) * w] = self.lng[q * w:(q + 1) * w].sum(axis=0) / float(np.float32(w))
             self.hist[q * w:(q + 1) * w] = self.hist[q * w:(q + 1) * w].sum(axis=0) / float(np.float32(w))
+
+    def _sample_rho(self):
+        """Radial densities of the walkers' configurations, accumulated in the energy bin they sit in (:574-592).  The
+        reference samples inside the trial loop, at most once per n_atoms trials and in the bin of the proposed
+        configuration; here the configuration at the end of each `sweeps` call is sampled (same estimator -- the mean
+        of rho over configurations of a bin -- at a coarser cadence, one SRO kernel launch per sample).  Per walker and
+        bin at most max(radial_samples / num_walkers, 1) samples, as in the reference."""
+        cap = max(self.p.radial_samples // self.walkers, 1)
+        for w in range(self.n_local):
+            jb = bin_index(self.energies[w], self.edges, self.p.bins)
+            if 0 < jb < self.p.bins + 1 and not self.radial_record_bool[jb - 1] and self.radial_record[w, jb - 1] < cap:
+                self.radial_record[w, jb - 1] += 1
+                self.rho_sum[jb - 1] += self.dev.radial_densities(self.wc_range, w)
+
+    def _save_rho_E(self):
+        """save_rho_E (:346-381): a bin is complete once radial_samples samples exist over all ranks; when every bin is,
+        rho_of_E[bin][shell][j][i] = the mean over its samples (what ncdf_radial_density_writer_across_energy stores)
+        and sampling stops.  `rho_of_E_partial()` gives the same means over whatever has been sampled so far."""
+        if not self.wc_range or self.rho_saved:
+            return
+        total = self.comm.all_gather(self.radial_record.sum(axis=0)).sum(axis=0)
+        self.radial_record_bool |= total >= self.p.radial_samples
+        self.radial_min = float(np.count_nonzero(self.radial_record_bool)) / float(self.p.bins)
+        if self.radial_record_bool.all():
+            self.rho_of_E = self.rho_of_E_partial()
+            self.rho_saved = True
+
+    def rho_of_E_partial(self):
+        """(mean rho per bin [bins][wc_range][S][S] over all ranks, samples per bin [bins]); bins without samples are 0."""
+        if self.rho_saved:
+            return self.rho_of_E
+        n = self.comm.all_gather(self.radial_record.sum(axis=0)).sum(axis=0)
+        tot = self.comm.all_gather(self.rho_sum).sum(axis=0)
+        return tot / np.maximum(n, 1)[:, None, None, None], n.astype(np.int64)
 
     def _window_lng_all(self):
         """lng per window for all windows (all-gather over ranks): [W][bins]."""
@@ -487,6 +529,7 @@ class WangLandau:
                 break
         self.stage_sweeps.append(n)
         self.hist[...] = 0.0
+        self._save_rho_E()
         combined = dos_combine(self._window_lng_all(), self.window_indices)      # dos_average + dos_combine
         self.lng[...] = combined[None, :]
         steps = self.comm.all_gather(self.wl_mc_steps).sum(axis=0)               # MPI_ALLREDUCE(wl_mc_steps) (:244, :814)

@@ -72,3 +72,24 @@ def test_wang_landau_dynamic_windows_golden_04(orc, golden):
     # <E>(T) from the final ln g (compute_mean_energy, :457-477) against the same sum over the golden ln g
     me_ref = wl.compute_mean_energy(ref, drv.edges, 512, drv.bin_width)
     assert np.max(np.abs(drv.mean_energy[29:, 0] - me_ref[29:, 0])) < 0.02 * abs(drv.edges[0])      # T >= 300 K
+
+
+def test_wang_landau_rho_of_E_on_gpu(orc, golden):
+    """rho(E) sampled with the SRO kernel during a short WL run (wang-landau.F90:574-592, save_rho_E :346-381): sum
+    rules per bin, agreement of a walker's sample with the oracle's radial_densities of the same configuration, and a
+    first-shell like-pair density that changes between the low- and the high-energy bins."""
+    from brawl_b200 import wang_landau as wl
+    p = wl.WLParams(mc_sweeps=50, bins=64, num_windows=2, bin_overlap=0.25, tolerance=0.02, flatness=0.8, wl_f=0.05,
+                    energy_min=-60.0, energy_max=0.0, radial_samples=8, performance=0)
+    drv = wl.WangLandau("bcc", 4, 4, 4, 4, 6, golden["t04_V"], [32, 32, 32, 32], p, walkers=8, seed=11, wc_range=3)
+    drv.run(max_sweeps_per_stage=2000)
+    rho, n = drv.rho_of_E_partial()
+    assert np.count_nonzero(n) > 40 and drv.radial_record.max() <= 1 and 0.0 < drv.radial_min <= 1.0
+    for b in np.flatnonzero(n):
+        for l, z in enumerate((1, 8, 6)):
+            assert np.allclose(rho[b, l].sum(axis=0), z, atol=1e-9) or np.allclose(rho[b, l].sum(axis=1), z, atol=1e-9)
+    sysm = orc.System("bcc", 4, 4, 4, 4, 6, golden["t04_V"])
+    g = drv.dev.get_config(3)
+    assert np.array_equal(drv.dev.radial_densities(3, 3), sysm.radial_densities(g, 3, sysm.lattice_shells(g, 3)))
+    like = np.array([np.trace(rho[b, 1]) for b in np.flatnonzero(n)])       # like-pair density in the first shell
+    assert np.all(np.isfinite(like)) and abs(like[:5].mean() - like[-5:].mean()) > 1e-3     # SRO changes with E

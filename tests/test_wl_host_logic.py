@@ -184,6 +184,10 @@ class _OracleDevice:
         for r in range(first_replica, first_replica + n):
             self.g[r] = wl.random_configuration("bcc", 4, 4, 4, species_count, self.rng)
 
+    def radial_densities(self, wc_range, replica=0):
+        g = self.g[replica]
+        return self.sys.radial_densities(g, wc_range, self.sys.lattice_shells(g, wc_range))
+
     def swap_replicas(self, a, b):
         self.g[a], self.g[b] = self.g[b], self.g[a]
 
@@ -249,3 +253,33 @@ def test_driver_dynamic_windows_control_flow(orc, golden, monkeypatch):
     d4 = wl.WangLandau("bcc", 4, 4, 4, 4, 6, golden["t04_V"], [32, 32, 32, 32], p4, walkers=2, seed=5)
     d4.run(max_sweeps_per_stage=400)
     assert len(d4.window_history) == 1
+
+
+def test_driver_rho_of_E_sampling(orc, golden, monkeypatch):
+    """rho(E) (wang-landau.F90:574-592, save_rho_E :346-381): per-bin means of the radial densities, capped at
+    max(radial_samples / walkers, 1) samples per walker and bin; a bin completes at radial_samples samples."""
+    from brawl_b200 import wang_landau as wl
+    _OracleDevice.orc = orc
+    monkeypatch.setattr(wl, "Device", _OracleDevice)
+    p = wl.WLParams(mc_sweeps=20, bins=32, num_windows=2, bin_overlap=0.25, tolerance=0.02, flatness=0.7, wl_f=0.05,
+                    energy_min=-50.0, energy_max=-5.0, radial_samples=4, performance=4)
+    drv = wl.WangLandau("bcc", 4, 4, 4, 4, 6, golden["t04_V"], [32, 32, 32, 32], p, walkers=2, seed=5, wc_range=3)
+    drv.run(max_sweeps_per_stage=300)
+    rho, n = drv.rho_of_E_partial()
+    assert rho.shape == (32, 3, 4, 4) and n.shape == (32,)
+    assert drv.radial_record.max() <= 2                                    # cap = max(4 // 2, 1) per walker and bin
+    assert n.max() <= 2 * 2 * 2                                            # <= cap x walkers x 2 overlapping windows
+    assert np.count_nonzero(n) > 16 and 0.0 < drv.radial_min <= 1.0
+    assert np.array_equal(drv.radial_record_bool, n >= 4) or drv.rho_saved
+    z = [1, 8, 6]             # lattice_shells starts at distance 0 (the atom itself, analytics.f90:205-275), then bcc 8, 6
+    for b in np.flatnonzero(n):
+        for l in range(3):
+            # every atom has z_l neighbours in shell l: sum over the neighbour species of rho(i, j, l) = z_l
+            assert np.allclose(rho[b, l].sum(axis=0), z[l]) or np.allclose(rho[b, l].sum(axis=1), z[l])
+    # ordering tendency: the unlike-pair density in shell 1 differs between the lowest and highest sampled bins
+    lo_b, hi_b = np.flatnonzero(n)[0], np.flatnonzero(n)[-1]
+    assert not np.allclose(rho[lo_b, 1], rho[hi_b, 1])
+    # off by default
+    d0 = wl.WangLandau("bcc", 4, 4, 4, 4, 6, golden["t04_V"], [32, 32, 32, 32], p, walkers=2, seed=5)
+    d0.run(max_sweeps_per_stage=50)
+    assert d0.radial_record.sum() == 0 and d0.rho_of_E is None
