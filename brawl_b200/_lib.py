@@ -27,6 +27,8 @@ _SIGNATURES = {
     "brawl_cuda_get_config": [_vp, _i, _i, _vp],
     "brawl_cuda_copy_replica": [_vp, _i, _i],
     "brawl_cuda_random_config": [_vp, _i, _i, _vp, _u64, _u64],
+    "brawl_cuda_store_state": [_vp, _i, _i],
+    "brawl_cuda_get_order": [_vp, _i, _vp, _i],
     "brawl_cuda_total_energy": [_vp, _i, _i, _i, _vp],
     "brawl_cuda_site_energies": [_vp, _i, _vp],
     "brawl_cuda_pair_dE": [_vp, _i, _i64, _vp, _vp, _vp],

@@ -214,6 +214,7 @@ struct brawl_cuda_ctx {
   int dE_mode;                 // 0: reference association for every trial; 1: screened, byte lattice; 2: screened, word lattice (default)
   int word_split;              // 1 (default): the planner may pick the two-warp-group (SPLIT) word kernels
   int byte_layout;             // 1: never use the word-lattice kernels / dense decomposition (test hook, A/B comparisons)
+  uint32_t *d_order;           // [n_replicas][S][n_sites] occupancy counts (store_state), allocated on first use
 };
 
 int brw_fail(const char *fmt, ...);              // sets last error, returns 1

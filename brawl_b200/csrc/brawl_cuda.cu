@@ -166,7 +166,7 @@ extern "C" int brawl_cuda_destroy(brawl_cuda_t *h) {
   cudaSetDevice(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   cudaFree(h->d_lat); cudaFree(h->d_V); cudaFree(h->d_stage); cudaFree(h->d_scratch); cudaFree(h->d_flag);
-  cudaFree(h->d_beta); cudaFree(h->d_small);
+  cudaFree(h->d_beta); cudaFree(h->d_small); cudaFree(h->d_order);
   brw_free_plan((BrwPlan *)h->mc_plan[0]); brw_free_plan((BrwPlan *)h->mc_plan[1]);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete[] h->hV;
@@ -316,6 +316,58 @@ extern "C" int brawl_cuda_random_config(brawl_cuda_t *h, int first, int n, const
     BRW_LAUNCH_CHECK("brw_shuffle_keys_kernel");
     BRW_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kin, kout, vin, vout, (int)ne, 0, 44 + rep_bits, h->stream));
   }
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ---- atomic long-range order: site occupancies (store_state, src/analytics.f90:43-64) ---------------------------
+__global__ void __launch_bounds__(256) brw_store_state_kernel(long n_sites, int S, int n_rep, const uint8_t *__restrict__ lat,
+                                                              uint32_t *__restrict__ order) {
+  const long total = n_sites * n_rep;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / n_sites, c = i - r * n_sites;
+    order[(r * S + lat[i]) * n_sites + c] += 1u;          // one thread per (replica, site): no atomics needed
+  }
+}
+// reference layout of `order`: (species, basis = 1, x, y, z), species fastest; off-site cells 0
+__global__ void __launch_bounds__(256) brw_order_unpack_kernel(BrwGeom g, const uint32_t *__restrict__ order, double *__restrict__ out) {
+  const long cells = (long)g.gx * g.gy * g.gz, total = cells * g.S;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long c = i / g.S;
+    const int s = (int)(i - c * g.S);
+    const int x = (int)(c % g.gx), y = (int)((c / g.gx) % g.gy), z = (int)(c / ((long)g.gx * g.gy));
+    out[i] = brw_is_site(g, x, y, z) ? (double)order[(long)s * g.n_sites + brw_grid_to_compact(g, x, y, z)] : 0.0;
+  }
+}
+extern "C" int brawl_cuda_store_state(brawl_cuda_t *h, int first, int n) {
+  BRW_ENTER(h);
+  if (n < 1 || first < 0 || first + n > h->n_replicas) return brw_fail("replica range [%d,%d) out of [0,%d)", first, first + n, h->n_replicas);
+  const BrwGeom &g = h->g;
+  const size_t per = (size_t)g.S * g.n_sites;
+  if (!h->d_order) {
+    BRW_CUDA(cudaMalloc(&h->d_order, per * h->n_replicas * sizeof(uint32_t)));
+    BRW_CUDA(cudaMemsetAsync(h->d_order, 0, per * h->n_replicas * sizeof(uint32_t), h->stream));
+  }
+  brw_store_state_kernel<<<grid_for((long)g.n_sites * n, 256), 256, 0, h->stream>>>((long)g.n_sites, g.S, n, h->d_lat + (size_t)first * g.n_sites,
+                                                                                  h->d_order + (size_t)first * per);
+  BRW_LAUNCH_CHECK("brw_store_state_kernel");
+  return 0;
+}
+extern "C" int brawl_cuda_get_order(brawl_cuda_t *h, int replica, double *order, int reset) {
+  BRW_ENTER(h);
+  BRW_REPLICA(h, replica);
+  if (!order) return brw_fail("null order pointer");
+  const BrwGeom &g = h->g;
+  const size_t per = (size_t)g.S * g.n_sites, n_out = (size_t)h->grid_cells * g.S;
+  if (!h->d_order) {                                        // nothing stored yet: all zeros
+    memset(order, 0, n_out * sizeof(double));
+    return 0;
+  }
+  if (brw_ensure_scratch(h, n_out * sizeof(double))) return 1;
+  brw_order_unpack_kernel<<<grid_for((long)n_out, 256), 256, 0, h->stream>>>(g, h->d_order + (size_t)replica * per, h->d_scratch);
+  BRW_LAUNCH_CHECK("brw_order_unpack_kernel");
+  BRW_CUDA(cudaMemcpyAsync(order, h->d_scratch, n_out * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (reset) BRW_CUDA(cudaMemsetAsync(h->d_order + (size_t)replica * per, 0, per * sizeof(uint32_t), h->stream));
   BRW_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
 }

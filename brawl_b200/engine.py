@@ -93,6 +93,16 @@ class Device:
             raise BrawlCudaError("species_count has %d entries, the system has %d species" % (cnt.size, self.S))
         check(self.L.brawl_cuda_random_config(self.h, first_replica, n, _p(cnt), seed, offset))
 
+    def store_state(self, first_replica=0, n=1):
+        """store_state (src/analytics.f90:43-64): add the current occupancies to the device-side site counts."""
+        check(self.L.brawl_cuda_store_state(self.h, first_replica, n))
+
+    def get_order(self, replica=0, reset=False):
+        """Occupancy counts as float64 [2n3][2n2][2n1][S] = the reference's order(species, 1, x, y, z)."""
+        out = np.empty(self.shape + (self.S,), dtype=np.float64)
+        check(self.L.brawl_cuda_get_order(self.h, replica, _p(out), int(reset)))
+        return out
+
     def copy_replica(self, src, dst):
         check(self.L.brawl_cuda_copy_replica(self.h, src, dst))
 

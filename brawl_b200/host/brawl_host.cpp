@@ -439,6 +439,29 @@ void ncdf_radial_density_writer(const std::string &f, const std::vector<double> 
   fp.write(out.b.data(), (std::streamsize)out.b.size());
 }
 
+// ncdf_order_writer (netcdf_io.f90:362-480): site occupancies per temperature; the reference names the six dimensions
+// of order(species, basis, x, y, z, T) "b","x","y","z","s","t" in that order (labels shifted by one -- kept).
+void ncdf_order_writer(const std::string &f, const std::vector<double> &order, const std::vector<double> &T, const RunParams &s) {
+  std::vector<std::pair<std::string, uint32_t>> dims = {{"b", (uint32_t)s.n_species}, {"x", (uint32_t)s.n_basis}, {"y", (uint32_t)(2 * s.n_1)},
+                                                        {"z", (uint32_t)(2 * s.n_2)}, {"s", (uint32_t)(2 * s.n_3)}, {"t", (uint32_t)T.size()},
+                                                        {"temp", (uint32_t)T.size()}};
+  std::vector<NcAtt> atts = {{"N_Basis", NC_INT, {s.n_basis}, "", {}}, {"N_1", NC_INT, {s.n_1}, "", {}}, {"N_2", NC_INT, {s.n_2}, "", {}},
+                             {"N_3", NC_INT, {s.n_3}, "", {}}, {"Number of Species", NC_INT, {s.n_species}, "", {}},
+                             {"Lattice Type", NC_CHAR, {}, rtrim(s.lattice), {}},
+                             {"Interaction file", NC_CHAR, {}, rtrim(s.interaction_file), {}},
+                             {"Concentrations", NC_DOUBLE, {}, "", s.species_concentrations},
+                             {"Warren-Cowley Range", NC_INT, {s.wc_range}, "", {}}};
+  std::vector<NcVar> vars = {{"grid data", {5, 4, 3, 2, 1, 0}, NC_DOUBLE, order.size()}, {"temperature data", {6}, NC_DOUBLE, T.size()}};
+  std::vector<uint32_t> begins;
+  NcBuf out;
+  out.b = nc_header(dims, atts, vars, begins);
+  for (double v : order) out.f64(v);
+  for (double v : T) out.f64(v);
+  std::ofstream fp(f, std::ios::binary);
+  if (!fp) throw Stop("cannot open " + f);
+  fp.write(out.b.data(), (std::streamsize)out.b.size());
+}
+
 // Minimal classic reader for files written by ncdf_grid_state_writer (restart, netcdf_io.f90:1368-1429)
 void ncdf_config_reader(const std::string &f, Config &config, const RunParams &s) {
   std::ifstream fp(f, std::ios::binary);
@@ -500,6 +523,7 @@ void metropolis_main(RunParams &setup, MetropolisParams &mp, const DriverOptions
   if (mp.write_final_config_xyz || mp.write_final_config_nc || mp.write_initial_config_nc) mkdir_p("configs");
   if (mp.calculate_energies) mkdir_p("energies");
   if (mp.calculate_asro) mkdir_p("asro");
+  if (mp.calculate_alro) mkdir_p("alro");                                 // :129-131
   if (mp.write_trajectory_energy || mp.write_trajectory_asro) mkdir_p("trajectories");
   std::vector<double> V = read_exchange(setup);
   const size_t nrho = (size_t)S * S * setup.wc_range;
@@ -518,6 +542,11 @@ void metropolis_main(RunParams &setup, MetropolisParams &mp, const DriverOptions
     const int n_save_energy = (int)std::floor((float)mp.n_mc_steps / (float)mp.n_sample_steps);
     const int n_save_asro = (int)std::floor((float)mp.n_mc_steps / (float)mp.n_sample_steps_asro);
     std::vector<double> energies_of_T(T_steps), C_of_T(T_steps), acceptance_of_T(T_steps), rho_of_T(nrho * T_steps, 0.0);
+    // ALRO (:164-165, 185): site occupancies accumulate on the device (brawl_cuda_store_state) and are cleared per
+    // temperature (:196) by the reset flag of brawl_cuda_get_order
+    const size_t norder = (size_t)setup.n_species * setup.n_basis * 8 * setup.n_1 * setup.n_2 * setup.n_3;
+    const int n_save_alro = mp.calculate_alro ? (int)std::floor((float)mp.n_mc_steps / (float)mp.n_sample_steps_alro) : 1;
+    std::vector<double> order_of_T(mp.calculate_alro ? norder * T_steps : 0, 0.0), order(mp.calculate_alro ? norder : 0, 0.0);
     uint32_t st[625];
     auto trials = [&](double beta, int64_t n) -> double {     // n x setup%mc_step; returns the acceptance increment
       if (n <= 0) return 0.0;
@@ -573,6 +602,7 @@ void metropolis_main(RunParams &setup, MetropolisParams &mp, const DriverOptions
           }
           if (mp.write_trajectory_asro && step_n % mp.n_sample_steps_trajectory == 0) asro_trajectory_writer(afile, step_n, asro);
         }
+        if (mp.calculate_alro && step_n % mp.n_sample_steps_alro == 0) Gpu::check(brawl_cuda_store_state(gpu.h, 0, 1));   // :394-399
       }
       acceptance_of_T[j - 1] = acceptance / (double)(float)mp.n_mc_steps;           // :412
       if (mp.calculate_energies) {
@@ -583,6 +613,10 @@ void metropolis_main(RunParams &setup, MetropolisParams &mp, const DriverOptions
         C_of_T[j - 1] = C;
       }
       if (mp.calculate_asro) for (size_t q = 0; q < nrho; q++) rho_of_T[(size_t)(j - 1) * nrho + q] = r_densities[q] / n_save_asro;
+      if (mp.calculate_alro) {                                                      // :444-447
+        Gpu::check(brawl_cuda_get_order(gpu.h, 0, order.data(), 1));
+        for (size_t q = 0; q < norder; q++) order_of_T[(size_t)(j - 1) * norder + q] = order[q] / (double)(float)n_save_alro;
+      }
       if (mp.write_final_config_nc) {
         Gpu::check(brawl_cuda_get_config(gpu.h, 0, 1, config.data()));
         ncdf_grid_state_writer("configs/proc_" + rt + "_final_config_at_T_" + tt + ".nc", config, setup);
@@ -596,6 +630,7 @@ void metropolis_main(RunParams &setup, MetropolisParams &mp, const DriverOptions
     }
     if (mp.calculate_energies) diagnostics_writer("energies/proc_" + rank_tag(my_rank) + "_energy_diagnostics.dat", temperature, energies_of_T, C_of_T, acceptance_of_T);
     if (mp.calculate_asro) ncdf_radial_density_writer("asro/proc_" + rank_tag(my_rank) + "_rho_of_T.nc", rho_of_T, shells, temperature, energies_of_T, setup);
+    if (mp.calculate_alro) ncdf_order_writer("alro/proc_" + rank_tag(my_rank) + "_rho_of_T.nc", order_of_T, temperature, setup);   // :506-510
     for (int j = 0; j < T_steps; j++) { av_E[j] += energies_of_T[j]; av_C[j] += C_of_T[j]; av_acc[j] += acceptance_of_T[j]; }
     for (size_t q = 0; q < av_rho.size(); q++) av_rho[q] += rho_of_T[q];
   }

@@ -83,6 +83,8 @@ void asro_trajectory_writer(const std::string &f, int64_t step, const std::vecto
 void diagnostics_writer(const std::string &f, const std::vector<double> &T, const std::vector<double> &E,
                         const std::vector<double> &C, const std::vector<double> &acc);       // :113-135
 void ncdf_grid_state_writer(const std::string &f, const Config &state, const RunParams &setup);   // netcdf_io.f90:495-583
+void ncdf_order_writer(const std::string &f, const std::vector<double> &order /* (species,basis,x,y,z,T) Fortran order */,
+                       const std::vector<double> &T, const RunParams &s);
 void ncdf_radial_density_writer(const std::string &f, const std::vector<double> &rho /* (i,j,r,T) Fortran order */,
                                 const std::vector<double> &r, const std::vector<double> &T,
                                 const std::vector<double> &U, const RunParams &setup);         // netcdf_io.f90:150-244

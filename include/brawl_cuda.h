@@ -72,6 +72,14 @@ int brawl_cuda_get_config(brawl_cuda_t *h, int first_replica, int n, int8_t *gri
 /* replica dst := replica src on the device (nested_sampling.f90:151 walker cloning;
  * wang-landau.F90:1475-1495 same-GPU replica exchange) */
 int brawl_cuda_copy_replica(brawl_cuda_t *h, int src, int dst);
+/* Atomic long-range order.  store_state == analytics.f90:43-64 (called from metropolis.F90:397 every
+ * n_sample_steps_alro trials): for replicas [first_replica, first_replica+n) add 1 to the occupancy count of the
+ * species sitting on every site.  The counts live on the device (uint32, [replica][species][site], allocated on the
+ * first call).  get_order writes them in the reference's layout order(species, 1, x, y, z) -- species fastest, then the
+ * (2n1, 2n2, 2n3) grid, off-site cells 0 -- as float64 counts (the caller divides by the number of samples,
+ * metropolis.F90:446); reset != 0 zeroes that replica's counts afterwards (one temperature done). */
+int brawl_cuda_store_state(brawl_cuda_t *h, int first_replica, int n);
+int brawl_cuda_get_order(brawl_cuda_t *h, int replica, double *order, int reset);
 /* Start states generated on the device: replicas [first_replica, first_replica+n) each become an independent,
  * uniformly random arrangement of the species multiset species_count[n_species] (which must sum to the number of
  * lattice sites).  Stands in for initial_setup (src/initialise.F90:434-617) called once per replica and for the

@@ -844,3 +844,32 @@ def test_random_config_on_device(bw, orc, golden):
     assert np.array_equal(np.bincount(gb.ravel(), minlength=5), [256 ** 3 - 4194304] + [1048576] * 4)
     sub = gb[gb > 0].astype(np.int64)
     assert abs((sub[:-1] == sub[1:]).mean() - 0.25) < 2e-3                # neighbours in site order uncorrelated
+
+
+def test_store_state_occupancies(bw, orc, golden):
+    """store_state (analytics.f90:43-64) on the device: occupancy counts accumulated over a short Metropolis run equal
+    the counts accumulated from the configurations read back, in the reference's order(species, 1, x, y, z) layout."""
+    V = golden["ex_AlTiCrMo_V"][: 4 * 4 * 4]
+    for lattice, n in (("bcc", (4, 4, 4)), ("fcc", (3, 4, 5))):
+        sysm = orc.System(lattice, *n, 4, 4, V)
+        R = 3
+        dev = bw.Device(lattice, *n, 4, 4, V, n_replicas=R)
+        assert not dev.get_order(1).any()                                      # nothing stored yet
+        na = dev.n_atoms
+        dev.random_config([na // 4] * 4, 0, R, seed=3)
+        want = np.zeros((R,) + dev.shape + (4,))
+        beta = np.full(R, 1.0 / (800.0 * bw.K_B_IN_RY))
+        for k in range(5):
+            dev.metropolis_run(beta, 10 * na, seed=k)
+            dev.store_state(0, R)
+            g = dev.get_config(0, R)
+            for s in range(4):
+                want[..., s] += (g == s + 1)                                   # the reference's loop, vectorised
+        for r in range(R):
+            got = dev.get_order(r)
+            assert got.shape == dev.shape + (4,) and np.array_equal(got, want[r]), (lattice, r)
+            assert np.array_equal(got.sum(axis=-1), 5.0 * (dev.get_config(r) > 0))   # every site counted once per sample
+        assert np.array_equal(dev.get_order(1, reset=True), want[1])
+        assert not dev.get_order(1).any() and np.array_equal(dev.get_order(2), want[2])
+        dev.store_state(1, 1)                                                  # a sub-range only touches its replicas
+        assert dev.get_order(1).sum() == na and np.array_equal(dev.get_order(0), want[0])

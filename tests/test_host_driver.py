@@ -122,3 +122,36 @@ def test_driver_runs_reference_case_03_nested_sampling(driver, golden, orc, tmp_
     culled, _, _ = sysm.nested_sampling(orc.MT(rank=0), conc, cnt, 100, 500, 1000)
     got = np.array([float(l.split()[1]) for l in mine[1:1001]])
     assert np.array_equal(got, culled)
+
+
+@pytest.mark.gpu
+def test_driver_alro_site_occupancies(driver, golden, tmp_path):
+    """calculate_alro = T on reference case 01 (metropolis.F90:394-399, 444-447, 506-510; store_state,
+    analytics.f90:43-64; ncdf_order_writer, netcdf_io.f90:362-480).  With one ALRO sample at the last trial the file
+    must hold the one-hot of the golden final configuration; with a sample every 64 trials the per-site means."""
+    tmp = str(tmp_path)
+    write_case(tmp, golden, "01", ("brawl.inp", "metropolis.inp", "fcc_epi.vij"))
+    inp = str(golden["in_01_metropolis.inp"]).replace("calculate_alro = F", "calculate_alro = T")
+    open(os.path.join(tmp, "metropolis.inp"), "w").write(inp)
+    subprocess.run([driver], cwd=tmp, check=True, capture_output=True)
+    f = netcdf_file(os.path.join(tmp, "alro/proc_0000_rho_of_T.nc"), "r", mmap=False)
+    final = golden["t01_final"]
+    S = int(getattr(f, "Number of Species"))
+    gz, gy, gx = final.shape
+    assert S == int(final.max()) and f.N_Basis == 1 and 2 * f.N_1 == gx
+    assert list(f.dimensions.items()) == [("b", S), ("x", 1), ("y", gx), ("z", gy), ("s", gz), ("t", 1), ("temp", 1)]
+    assert f.variables["grid data"].dimensions == ("t", "s", "z", "y", "x", "b")
+    order = np.array(f.variables["grid data"].data)[0, :, :, :, 0, :]          # [z][y][x][species]
+    assert np.array_equal(order, np.stack([(final == s) for s in range(1, S + 1)], axis=-1).astype(np.float64))
+    assert np.array_equal(np.array(f.variables["temperature data"].data), [300.0])
+    # the other outputs are untouched by the extra sampling
+    assert np.array_equal(nc_var(os.path.join(tmp, "configs/proc_0000_final_config_at_T_0300.0.nc"), "configuration")[..., 0], final)
+    # four samples per temperature, two temperatures: means in [0, 1], one atom per site, accumulator cleared per T
+    inp2 = inp.replace("n_sample_steps_alro = 256", "n_sample_steps_alro = 64").replace("T_steps = 1", "T_steps = 2").replace("delta_T = 0.0", "delta_T = 100.0")
+    open(os.path.join(tmp, "metropolis.inp"), "w").write(inp2)
+    subprocess.run([driver], cwd=tmp, check=True, capture_output=True)
+    o2 = nc_var(os.path.join(tmp, "alro/proc_0000_rho_of_T.nc"), "grid data")[:, :, :, :, 0, :]
+    assert o2.shape == (2, gz, gy, gx, S) and o2.min() >= 0.0 and o2.max() <= 1.0
+    assert np.array_equal(np.unique(o2 * 4), np.unique(np.round(o2 * 4)))       # multiples of 1/4
+    for t in range(2):
+        assert np.array_equal(o2[t].sum(axis=-1), (final > 0).astype(np.float64))
