@@ -7,3 +7,4 @@ from ._lib import BrawlCudaError, EXPORTS, LIB_PATH, load  # noqa: F401
 from .engine import Device, RunParams, K_B_IN_RY, RY_TO_EV, LATTICES  # noqa: F401
 from . import wang_landau  # noqa: F401,E402
 from . import nested_sampling  # noqa: F401,E402
+from . import replica_annealing  # noqa: F401,E402

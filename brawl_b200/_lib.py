@@ -43,6 +43,7 @@ _SIGNATURES = {
     "brawl_cuda_metropolis_set_layout": [_vp, _i],
     "brawl_cuda_metropolis_plan": [_vp, _i, _vp],
     "brawl_cuda_radial_counts": [_vp, _i, _i, _vp, _vp],
+    "brawl_cuda_radial_counts_batch": [_vp, _i, _i, _i, _vp, _vp],
     "brawl_cuda_wl_sweeps_replay": [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _d, _i64, _i, _vp, _vp, _vp],
     "brawl_cuda_wl_sweeps": [_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _d, _i64, _i, _u64, _u64, _vp, _vp],
     "brawl_cuda_wl_enter_window": [_vp, _i, _vp, _vp, _vp, _d, _i64, _u64, _u64, _vp, _vp],

@@ -1087,6 +1087,37 @@ extern "C" int brawl_cuda_radial_counts(brawl_cuda_t *h, int replica, int wc_ran
   return 0;
 }
 
+// replicas [first, first+n) in one launch (blockIdx.y = replica): cnt[n][wc_range][S][S], species_count[n][S]
+extern "C" int brawl_cuda_radial_counts_batch(brawl_cuda_t *h, int first, int n, int wc_range, int64_t *cnt, int64_t *species_count) {
+  BRW_ENTER(h);
+  if (n < 1 || first < 0 || first + n > h->n_replicas) return brw_fail("replica range [%d,%d) out of [0,%d)", first, first + n, h->n_replicas);
+  if (n > 65535) return brw_fail("at most 65535 replicas per radial_counts_batch call");
+  if (wc_range < 1 || wc_range > 64) return brw_fail("wc_range out of range");
+  if (!cnt || !species_count) return brw_fail("null output pointer");
+  const BrwGeom &g = h->g;
+  std::vector<int4> offs; std::vector<double> radii;
+  brw_sro_offsets(g, wc_range, offs, radii);
+  const size_t n_cnt = (size_t)wc_range * g.S * g.S, nh = n_cnt + g.S;
+  const size_t cnt_bytes = ((nh * n * sizeof(unsigned long long)) + 15) & ~(size_t)15;
+  if (brw_small(h, cnt_bytes + offs.size() * sizeof(int4) + 16)) return 1;
+  unsigned long long *d_cnt = (unsigned long long *)h->d_small;
+  int4 *d_off = (int4 *)((char *)h->d_small + cnt_bytes);
+  BRW_CUDA(cudaMemsetAsync(d_cnt, 0, cnt_bytes, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(d_off, offs.data(), offs.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+  const int bx = std::max(1, std::min(grid_for(g.n_sites, 256, 592), (148 * 8 + n - 1) / n));
+  brw_radial_counts_kernel<<<dim3(bx, n), 256, nh * sizeof(unsigned int), h->stream>>>(g, h->d_lat + (size_t)first * g.n_sites, d_off,
+                                                                                    (int)offs.size(), wc_range, d_cnt, d_cnt + n_cnt);
+  BRW_LAUNCH_CHECK("brw_radial_counts_kernel (batch)");
+  std::vector<unsigned long long> hc(nh * n);
+  BRW_CUDA(cudaMemcpyAsync(hc.data(), d_cnt, hc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < n; r++) {
+    for (size_t i = 0; i < n_cnt; i++) cnt[(size_t)r * n_cnt + i] = (int64_t)hc[(size_t)r * nh + i];
+    for (int i = 0; i < g.S; i++) species_count[(size_t)r * g.S + i] = (int64_t)hc[(size_t)r * nh + n_cnt + i];
+  }
+  return 0;
+}
+
 // ---- Wang-Landau -------------------------------------------------------------------------------------------------
 extern "C" int brawl_cuda_wl_sweeps_replay(brawl_cuda_t *h, int replica, double *lng, double *hist, const double *edges,
                                            int bins, int win_lo, int win_hi, double wl_f, int64_t n_trials, int nbr_swap,

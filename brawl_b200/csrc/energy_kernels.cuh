@@ -247,6 +247,10 @@ __global__ void __launch_bounds__(256) brw_radial_counts_kernel(BrwGeom g, const
                                                                 unsigned long long *__restrict__ species_count) {
   extern __shared__ unsigned int hist[];   // [wc_range*S*S] + [S]
   const int nh = wc_range * g.S * g.S + g.S;
+  // batched form: blockIdx.y = replica; its counts follow the previous replica's [wc_range*S*S + S] block
+  lat += (size_t)blockIdx.y * g.n_sites;
+  cnt += (size_t)blockIdx.y * nh;
+  species_count += (size_t)blockIdx.y * nh;
   for (int i = threadIdx.x; i < nh; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   unsigned int *sc = hist + wc_range * g.S * g.S;

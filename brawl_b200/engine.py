@@ -217,6 +217,13 @@ class Device:
         cnt, sc = self.radial_counts(wc_range, replica)
         return cnt / sc[None, None, :].astype(np.float64)
 
+    def radial_densities_batch(self, wc_range, first_replica=0, n=1):
+        """rho[r][l][j][i] for replicas [first, first+n) from one launch."""
+        cnt = np.zeros((n, wc_range, self.S, self.S), dtype=np.int64)
+        sc = np.zeros((n, self.S), dtype=np.int64)
+        check(self.L.brawl_cuda_radial_counts_batch(self.h, first_replica, n, wc_range, _p(cnt), _p(sc)))
+        return cnt / sc[:, None, None, :].astype(np.float64)
+
     # --- Wang-Landau --------------------------------------------------------------------------------
     def wl_sweeps_replay(self, lng, hist, bin_edges, win_lo, win_hi, wl_f, n_trials, mt_state625, nbr_swap=False,
                          replica=0):

@@ -55,10 +55,7 @@ class ReplicaAnnealing:
 
     def _radial_densities(self):
         """r_densities(i,j,l) per replica: [R][wc_range][S][S] (analytics.f90:293-404)."""
-        out = np.empty((self.R, self.wc_range, self.S, self.S))
-        for r in range(self.R):
-            out[r] = self.dev.radial_densities(self.wc_range, r)
-        return out
+        return self.dev.radial_densities_batch(self.wc_range, 0, self.R)      # one launch for all replicas
 
     def run(self, initial_configs=None):
         """Returns (per_replica, averaged): per_replica = dict of arrays [R][T_steps]...; averaged = the reference's

@@ -171,6 +171,10 @@ int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *out10);
  * atoms (l = 0: the site itself), species_count[S].  rho = cnt / species_count[i] in f64 is
  * exactly the reference's r_densities(i,j,l).  wc_range-1 <= n tabulated shells. */
 int brawl_cuda_radial_counts(brawl_cuda_t *h, int replica, int wc_range, int64_t *cnt, int64_t *species_count);
+/* the same for replicas [first_replica, first_replica+n) in one launch: cnt[n][wc_range][S][S], species_count[n][S]
+ * (SRO of every chain of a replica batch per sampling point, metropolis.F90:378-383) */
+int brawl_cuda_radial_counts_batch(brawl_cuda_t *h, int first_replica, int n, int wc_range, int64_t *cnt,
+                                   int64_t *species_count);
 
 /* ---- Wang-Landau ----------------------------------------------------------------------------
  * sweeps() for the walkers held by this handle (src/wang-landau.F90:539-626): walker w owns

@@ -873,3 +873,22 @@ def test_store_state_occupancies(bw, orc, golden):
         assert not dev.get_order(1).any() and np.array_equal(dev.get_order(2), want[2])
         dev.store_state(1, 1)                                                  # a sub-range only touches its replicas
         assert dev.get_order(1).sum() == na and np.array_equal(dev.get_order(0), want[0])
+
+
+def test_radial_counts_batch_matches_single(bw, orc, golden):
+    """brawl_cuda_radial_counts_batch: all replicas in one launch == the per-replica entry == the oracle."""
+    V = golden["ex_AlCrFeCoNi_V"][: 5 * 5 * 4]
+    for lattice, n, R in (("bcc", (6, 5, 7), 7), ("fcc", (4, 4, 4), 33)):
+        sysm = orc.System(lattice, *n, 5, 4, V)
+        dev = bw.Device(lattice, *n, 5, 4, V, n_replicas=R)
+        na = dev.n_atoms
+        dev.random_config([na // 5 + (1 if s < na % 5 else 0) for s in range(5)], 0, R, seed=17)
+        rho = dev.radial_densities_batch(4, 0, R)
+        assert rho.shape == (R, 4, 5, 5)
+        for r in range(R):
+            assert np.array_equal(rho[r], dev.radial_densities(4, r))
+        g = dev.get_config(R - 1)
+        assert np.array_equal(rho[R - 1], sysm.radial_densities(g, 4, sysm.lattice_shells(g, 4)))
+        assert np.array_equal(dev.radial_densities_batch(4, 2, 3), rho[2:5])
+        with pytest.raises(bw.BrawlCudaError):
+            dev.radial_densities_batch(4, R - 1, 2)

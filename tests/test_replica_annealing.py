@@ -35,9 +35,9 @@ class _OracleChains:
     def total_energy(self, first_replica=0, n=1, exact_order=True):
         return np.array([self.sys.total_energy(g) for g in self.g[first_replica:first_replica + n]])
 
-    def radial_densities(self, wc_range, replica=0):
-        g = self.g[replica]
-        return self.sys.radial_densities(g, wc_range, self.sys.lattice_shells(g, wc_range))
+    def radial_densities_batch(self, wc_range, first_replica=0, n=1):
+        return np.stack([self.sys.radial_densities(g, wc_range, self.sys.lattice_shells(g, wc_range))
+                         for g in self.g[first_replica:first_replica + n]])
 
 
 def _run(rank, world, golden, torch_device=None):
