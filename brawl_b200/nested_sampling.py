@@ -13,7 +13,6 @@ import math
 import numpy as np
 
 from .engine import Device, BrawlCudaError
-from .wang_landau import random_configuration
 
 
 class NSParams:
@@ -54,9 +53,8 @@ class NestedSampling:
         """Random initial walkers (:78-97) unless `configs[R*K]` is given; E = full_energy + u*1e-8
         (the 1e-8 is a default-real literal, :95)."""
         n = self.R * self.K
-        if configs is None:
-            for w in range(n):
-                self.dev.set_config(random_configuration(self.lattice, *self.n, self.counts, self.rng), w, 1)
+        if configs is None:                                    # all R*K start states in one device call
+            self.dev.random_config(self.counts, 0, n, seed=self.seed, offset=0x5C << 56)
         else:
             self.dev.set_config(configs, 0, n)
         e = self.dev.total_energy(0, n, exact_order=True)
