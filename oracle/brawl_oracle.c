@@ -11,6 +11,11 @@
  * against fixtures built from those files by tests/golden/make_golden.py.  The MT19937
  * restated here is checked against the reference's own src/mt19937ar.c compiled into
  * oracle/_ref/ (oracle/Makefile) whenever /root/reference is present.
+ * Exception -- parity UNPINNED: the Wang-Landau control-plane arithmetic at the end of this file
+ * (orc_wl_mean_energy, orc_wl_window_optimise).  The reference ships no golden output for its load
+ * balancer; these two are a second, independent restatement against which the host mirror in
+ * brawl_b200/wang_landau.py is compared.  The WL trial loop itself (orc_wl_sweeps) is pinned
+ * statistically by tests/99_ref/04_parallel_wang-landau/wl_dos.nc (1 % NRMSE, the reference's criterion).
  *
  * Each function cites the reference file:line it follows (paths relative to
  * /root/reference).  Conventions: all coordinates are 0-based here (the reference is
