@@ -172,24 +172,31 @@ class _OracleDevice:
         o = self.orc
         self.sys = o.System(lattice, n_1, n_2, n_3, n_species, n_shells, V_ex)
         self.n_atoms, self.n_replicas = self.sys.n_atoms, n_replicas
-        self.g = [None] * n_replicas
+        # one buffer for all replicas; self.g[r] are views, so lattice_tensor() can expose it to torch.distributed
+        self.buf = np.zeros((n_replicas, 2 * n_3, 2 * n_2, 2 * n_1), dtype=np.int8)
+        self.g = [self.buf[r] for r in range(n_replicas)]
         self.mt = [o.MT(seed=1000 + r + 17 * device) for r in range(n_replicas)]
         self.rng = np.random.default_rng(77 + device)
 
     def set_config(self, config, first_replica=0, n=None):
-        self.g[first_replica] = np.ascontiguousarray(config, dtype=np.int8).copy()
+        self.g[first_replica][...] = np.asarray(config, dtype=np.int8).reshape(self.g[first_replica].shape)
+
+    def lattice_tensor(self, torch):
+        return torch.from_numpy(self.buf.reshape(self.n_replicas, -1))
 
     def random_config(self, species_count, first_replica=0, n=1, seed=0, offset=0):
         from brawl_b200 import wang_landau as wl
         for r in range(first_replica, first_replica + n):
-            self.g[r] = wl.random_configuration("bcc", 4, 4, 4, species_count, self.rng)
+            self.g[r][...] = wl.random_configuration("bcc", 4, 4, 4, species_count, self.rng)
 
     def radial_densities(self, wc_range, replica=0):
         g = self.g[replica]
         return self.sys.radial_densities(g, wc_range, self.sys.lattice_shells(g, wc_range))
 
     def swap_replicas(self, a, b):
-        self.g[a], self.g[b] = self.g[b], self.g[a]
+        t = self.g[a].copy()
+        self.g[a][...] = self.g[b]
+        self.g[b][...] = t
 
     def wl_sweeps(self, lng, hist, edges, win_lo, win_hi, wl_f, n_trials, seed=0, offset=0, nbr_swap=False):
         acc, ef = np.zeros(len(self.g), dtype=np.int64), np.zeros(len(self.g))
@@ -283,3 +290,52 @@ def test_driver_rho_of_E_sampling(orc, golden, monkeypatch):
     d0 = wl.WangLandau("bcc", 4, 4, 4, 4, 6, golden["t04_V"], [32, 32, 32, 32], p, walkers=2, seed=5)
     d0.run(max_sweeps_per_stage=50)
     assert d0.radial_record.sum() == 0 and d0.rho_of_E is None
+
+
+def _gloo_driver_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from oracle import oracle
+    from brawl_b200 import wang_landau as wl
+    import test_wl_host_logic as t
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    t._OracleDevice.orc = oracle
+    wl.Device = t._OracleDevice
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "brawl_golden.npz"))
+    p = wl.WLParams(mc_sweeps=20, bins=64, num_windows=4, bin_overlap=0.25, tolerance=0.02, flatness=0.7, wl_f=0.05,
+                    energy_min=-60.0, energy_max=-5.0, performance=0)
+    drv = wl.WangLandau("bcc", 4, 4, 4, 4, 6, golden["t04_V"], [32, 32, 32, 32], p, walkers=2, device=rank, rank=rank,
+                        world=world, seed=5)
+    swaps = []
+    orig = drv._replica_exchange
+    drv._replica_exchange = lambda: swaps.append(orig()) or swaps[-1]
+    lng = drv.run(max_sweeps_per_stage=400)
+    e = np.array([drv.dev.sys.total_energy(g) for g in drv.dev.g])
+    lo, hi = drv.edges[drv.win_lo - 1], drv.edges[drv.win_hi]
+    q.put((rank, [h.tolist() for h in drv.window_history], lng.tolist(), bool(np.array_equal(e, drv.energies)),
+           bool(np.all((e > lo) & (e < hi))), int(sum(swaps)), drv.last_mc_steps.tolist(), drv.stage_sweeps))
+    dist.destroy_process_group()
+
+
+def test_driver_dynamic_windows_world_size_2_gloo():
+    """Four windows sharded over two ranks (two each), performance = 0: both ranks derive the same resized windows from
+    the all-gathered per-window trial counts, stitch the same ln g, exchange configurations across the rank boundary
+    (isend/irecv of the lattice bytes) with consistent energy bookkeeping, and end with every walker in its window."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_gloo_driver_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in ps])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    a, b = res
+    assert a[1] == b[1] and len(a[1]) == 4 and any(h != a[1][0] for h in a[1][1:])       # same windows, and they moved
+    assert a[2] == b[2] and min(a[2]) == 0.0                                              # same stitched ln g
+    assert a[3] and b[3] and a[4] and b[4]                                                # energies == configs; inside windows
+    assert a[5] == b[5] and a[5] > 0                                                      # same exchange plan, some accepted
+    assert a[6] == b[6] and min(a[6]) > 0 and a[7] == b[7]
