@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--overlap", type=float, default=0.25)
     ap.add_argument("--tolerance", type=float, default=5e-5)
     ap.add_argument("--seed", type=int, default=2024)
+    ap.add_argument("--performance", type=int, default=4,
+                    help="the reference's switch: 0/1 resize windows every f-stage, 2/3 after pre-sampling only, 4 static")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -40,7 +42,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     gold = np.load(os.path.join(ROOT, "tests", "golden", "brawl_golden.npz"))
     p = wl.WLParams(mc_sweeps=100, bins=512, num_windows=args.windows, bin_overlap=args.overlap, tolerance=args.tolerance,
-                    flatness=0.90, wl_f=0.05, energy_min=-96, energy_max=0.0)
+                    flatness=0.90, wl_f=0.05, energy_min=-96, energy_max=0.0, performance=args.performance)
     drv = wl.WangLandau("bcc", 4, 4, 4, 4, 6, gold["t04_V"], [32] * 4, p, walkers=args.walkers, device=local, rank=rank,
                         world=world, seed=args.seed, torch_device=torch.device("cuda", local))
     torch.cuda.synchronize()
@@ -57,7 +59,9 @@ def main():
         ref = np.asarray(gold["t04_wl_dos"], dtype=np.float64)
         err = float(np.sqrt(np.mean((ref - lng) ** 2)) / np.mean(np.abs(ref)))
         print(json.dumps({"workload": "WL bcc n=4 4 species 6 shells 512 bins", "n_gpus": world, "windows": args.windows,
-                          "walkers_per_window": args.walkers, "seconds_to_final_lng": dt, "wl_trials": trials,
+                          "walkers_per_window": args.walkers, "performance": args.performance,
+                          "final_window_widths": (drv.window_indices[:, 1] - drv.window_indices[:, 0] + 1).tolist(),
+                          "seconds_to_final_lng": dt, "wl_trials": trials,
                           "wl_trials_per_sec": trials / dt, "sweeps_calls_per_stage": drv.stage_sweeps,
                           "nrmse_vs_reference_golden": err, "pass_reference_criterion": err < 0.01}))
     if world > 1:
