@@ -358,6 +358,8 @@ def main():
                                    2: "word lattice + dense non-interacting-set decomposition: integer-count screening "
                                       "with fixed-point dp4a dE + reference association inside the guard band "
                                       "(accept/reject decisions identical to mode 0)"}[args.dE_mode], "acceptance": float(acc.sum()) / max(1, float(att.sum())),
+                       # same-species attempts count as attempts but touch 2 B and no flops
+                       "distinct_species_fraction": 1.0 - 1.0 / S,
                        "energy_per_atom_start_end_Ry": [e_start / N, e_end / N]},
             "e2e": {"value": e2e_value, "unit": "swaps/s", "h2d_bytes_per_step": int(R * (8 * n ** 3 + 8)),
                     "d2h_bytes_per_step": int(R * (8 * n ** 3 + 8 + 24)),
