@@ -301,6 +301,27 @@ def random_configuration(lattice, n_1, n_2, n_3, counts, rng):
     return g
 
 
+def ncdf_writer_1d(filename, grid_data):
+    """ncdf_writer_1d (src/netcdf_io.f90:731-806): one dimension "x", one NF90_DOUBLE variable "grid data", no
+    attributes, NetCDF-3 classic (CDF-1) -- byte-identical to the file netCDF-Fortran writes for the same data."""
+    import struct
+    data = np.ascontiguousarray(grid_data, dtype=np.float64).ravel()
+
+    def name(t):
+        b = t.encode()
+        return struct.pack(">I", len(b)) + b + b"\0" * (-len(b) % 4)
+
+    NC_DIMENSION, NC_VARIABLE, NC_DOUBLE = 10, 11, 6
+    head = b"CDF\x01" + struct.pack(">I", 0)                                     # magic, numrecs
+    head += struct.pack(">II", NC_DIMENSION, 1) + name("x") + struct.pack(">I", data.size)
+    head += struct.pack(">II", 0, 0)                                              # gatt_list ABSENT
+    var = name("grid data") + struct.pack(">II", 1, 0) + struct.pack(">II", 0, 0) + struct.pack(">II", NC_DOUBLE, 8 * data.size)
+    head += struct.pack(">II", NC_VARIABLE, 1) + var
+    head += struct.pack(">I", len(head) + 4)                                      # begin
+    with open(filename, "wb") as fh:
+        fh.write(head + data.astype(">f8").tobytes())
+
+
 class _Comm:
     """torch.distributed plumbing (world size 1 needs no torch at all)."""
 
@@ -543,6 +564,17 @@ class WangLandau:
         if resize and self.p.num_windows > 1:
             self.enter_energy_windows(fresh=False)                               # in place of load_window_config
         return combined
+
+    def save_wl_data(self, directory, lng, hist=None):
+        """save_wl_data (:409-417), rank 0 only: data/wl_dos_bins.nc (bin edges), data/wl_dos.nc (ln g), data/wl_hist.nc."""
+        if self.rank != 0:
+            return
+        import os
+        d = os.path.join(directory, "data")
+        os.makedirs(d, exist_ok=True)
+        ncdf_writer_1d(os.path.join(d, "wl_dos_bins.nc"), self.edges)
+        ncdf_writer_1d(os.path.join(d, "wl_dos.nc"), lng)
+        ncdf_writer_1d(os.path.join(d, "wl_hist.nc"), np.zeros(self.p.bins) if hist is None else hist)
 
     def run(self, max_sweeps_per_stage=100000, callback=None):
         """pre_sampling (:757-838) then the f-halving loop (:198-292).  Returns ln g(E) [bins]."""

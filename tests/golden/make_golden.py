@@ -88,6 +88,7 @@ def main():
             out["in_%s_%s" % (case[:2], fn)] = text(t + case + "/" + fn)
     out["raw_t02_r0_initial_nc"] = np.frombuffer(open(r + "02_parallel_metropolis/proc_0000_initial_config_at_0300.0.nc", "rb").read(), dtype=np.uint8)
     out["raw_t02_r0_rho_nc"] = np.frombuffer(open(r + "02_parallel_metropolis/proc_0000_rho_of_T.nc", "rb").read(), dtype=np.uint8)
+    out["raw_t04_wl_dos_nc"] = np.frombuffer(open(r + "04_parallel_wang-landau/wl_dos.nc", "rb").read(), dtype=np.uint8)
     out["raw_t02_av_rho_nc"] = np.frombuffer(open(r + "02_parallel_metropolis/av_radial_density.nc", "rb").read(), dtype=np.uint8)
     path = os.path.join(HERE, "brawl_golden.npz")
     np.savez_compressed(path, **out)

@@ -229,7 +229,7 @@ class _OracleDevice:
         return e_out, ent
 
 
-def test_driver_dynamic_windows_control_flow(orc, golden, monkeypatch):
+def test_driver_dynamic_windows_control_flow(orc, golden, monkeypatch, tmp_path):
     """performance = 0: windows are resized after pre-sampling and after every f-stage (wang-landau.F90:284-286, 820),
     walkers end every stage inside their (new) window, ln g stays a sane stitched curve.  Trial loops by the oracle."""
     from brawl_b200 import wang_landau as wl
@@ -254,6 +254,11 @@ def test_driver_dynamic_windows_control_flow(orc, golden, monkeypatch):
     assert np.array_equal(e, drv.energies)
     assert lng.min() == 0.0 and np.all(np.isfinite(lng)) and np.all(np.diff(lng[8:40]) > -1.0)
     assert drv.mean_energy.shape == (300, 2) and np.all(np.diff(drv.mean_energy[:, 0]) >= 0)
+    # output files of save_wl_data (wang-landau.F90:409-417)
+    from scipy.io import netcdf_file
+    drv.save_wl_data(str(tmp_path), lng)
+    rd = lambda f: np.array(netcdf_file(str(tmp_path / "data" / f), "r", mmap=False).variables["grid data"].data)
+    assert np.array_equal(rd("wl_dos.nc"), lng) and np.array_equal(rd("wl_dos_bins.nc"), drv.edges) and rd("wl_hist.nc").shape == (64,)
     # performance = 4: static windows
     p4 = wl.WLParams(mc_sweeps=20, bins=64, num_windows=3, bin_overlap=0.25, tolerance=0.04, flatness=0.7, wl_f=0.05,
                      energy_min=-60.0, energy_max=-5.0, performance=4)
@@ -339,3 +344,17 @@ def test_driver_dynamic_windows_world_size_2_gloo():
     assert a[3] and b[3] and a[4] and b[4]                                                # energies == configs; inside windows
     assert a[5] == b[5] and a[5] > 0                                                      # same exchange plan, some accepted
     assert a[6] == b[6] and min(a[6]) > 0 and a[7] == b[7]
+
+
+def test_ncdf_writer_1d_is_byte_identical_to_the_reference_file(golden, tmp_path):
+    """ncdf_writer_1d (netcdf_io.f90:731-806): the reference's own tests/99_ref/04_parallel_wang-landau/wl_dos.nc,
+    rewritten from its data by the host mirror, byte for byte (header and payload)."""
+    from scipy.io import netcdf_file
+    from brawl_b200 import wang_landau as wl
+    path = str(tmp_path / "wl_dos.nc")
+    wl.ncdf_writer_1d(path, golden["t04_wl_dos"])
+    assert open(path, "rb").read() == golden["raw_t04_wl_dos_nc"].tobytes()
+    f = netcdf_file(path, "r", mmap=False)
+    assert list(f.dimensions.items()) == [("x", 512)] and np.array_equal(f.variables["grid data"].data, golden["t04_wl_dos"])
+    wl.ncdf_writer_1d(path, np.arange(5.0))                              # another length: still a valid classic file
+    assert np.array_equal(netcdf_file(path, "r", mmap=False).variables["grid data"].data, np.arange(5.0))

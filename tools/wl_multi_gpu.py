@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--overlap", type=float, default=0.25)
     ap.add_argument("--tolerance", type=float, default=5e-5)
     ap.add_argument("--seed", type=int, default=2024)
+    ap.add_argument("--out", default=None, help="directory for data/wl_dos.nc, wl_dos_bins.nc, wl_hist.nc (the reference's files)")
     ap.add_argument("--performance", type=int, default=4,
                     help="the reference's switch: 0/1 resize windows every f-stage, 2/3 after pre-sampling only, 4 static")
     args = ap.parse_args()
@@ -55,6 +56,8 @@ def main():
         dist.barrier()
     dt = time.time() - t0
     trials = drv.comm.all_sum(drv.total_trials)
+    if args.out:
+        drv.save_wl_data(args.out, lng)
     if rank == 0:
         ref = np.asarray(gold["t04_wl_dos"], dtype=np.float64)
         err = float(np.sqrt(np.mean((ref - lng) ** 2)) / np.mean(np.abs(ref)))
