@@ -115,6 +115,17 @@ class ReplicaAnnealing:
         return per, av
 
 
+def save_av_radial_density(directory, av, shells, setup):
+    """asro/av_radial_density.nc as metropolis_simulated_annealing writes it after the rank average (metropolis.F90:529;
+    ncdf_radial_density_writer, netcdf_io.f90:150-244): rho(i,j,r,T), shell radii, temperatures, <E>(T) per atom."""
+    import os
+    from .netcdf3 import ncdf_radial_density_writer
+    d = os.path.join(directory, "asro")
+    os.makedirs(d, exist_ok=True)
+    ncdf_radial_density_writer(os.path.join(d, "av_radial_density.nc"), av["rho_of_T"], shells, av["temperature"],
+                               av["energies_of_T"], setup)
+
+
 def warren_cowley(rho, concentrations, coordination):
     """alpha^{ij}_n = 1 - rho^{ij}_n / (Z_n c_j) (examples/01_metropolis_FeNi/02_simulated_annealing/01_plot_results.py:35-36);
     rho[..., shell, j, i], coordination[shell] (use 1 for the r = 0 shell)."""

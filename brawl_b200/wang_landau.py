@@ -301,25 +301,7 @@ def random_configuration(lattice, n_1, n_2, n_3, counts, rng):
     return g
 
 
-def ncdf_writer_1d(filename, grid_data):
-    """ncdf_writer_1d (src/netcdf_io.f90:731-806): one dimension "x", one NF90_DOUBLE variable "grid data", no
-    attributes, NetCDF-3 classic (CDF-1) -- byte-identical to the file netCDF-Fortran writes for the same data."""
-    import struct
-    data = np.ascontiguousarray(grid_data, dtype=np.float64).ravel()
-
-    def name(t):
-        b = t.encode()
-        return struct.pack(">I", len(b)) + b + b"\0" * (-len(b) % 4)
-
-    NC_DIMENSION, NC_VARIABLE, NC_DOUBLE = 10, 11, 6
-    head = b"CDF\x01" + struct.pack(">I", 0)                                     # magic, numrecs
-    head += struct.pack(">II", NC_DIMENSION, 1) + name("x") + struct.pack(">I", data.size)
-    head += struct.pack(">II", 0, 0)                                              # gatt_list ABSENT
-    var = name("grid data") + struct.pack(">II", 1, 0) + struct.pack(">II", 0, 0) + struct.pack(">II", NC_DOUBLE, 8 * data.size)
-    head += struct.pack(">II", NC_VARIABLE, 1) + var
-    head += struct.pack(">I", len(head) + 4)                                      # begin
-    with open(filename, "wb") as fh:
-        fh.write(head + data.astype(">f8").tobytes())
+from .netcdf3 import ncdf_writer_1d, ncdf_radial_density_writer_across_energy  # noqa: E402
 
 
 class _Comm:
@@ -575,6 +557,20 @@ class WangLandau:
         ncdf_writer_1d(os.path.join(d, "wl_dos_bins.nc"), self.edges)
         ncdf_writer_1d(os.path.join(d, "wl_dos.nc"), lng)
         ncdf_writer_1d(os.path.join(d, "wl_hist.nc"), np.zeros(self.p.bins) if hist is None else hist)
+
+    def save_rho_of_E(self, directory, shells, setup):
+        """The file save_rho_E writes once every bin is complete (:374-391): asro/rho_of_E.nc with rho(i,j,r,bin), the
+        shell radii (lattice_shells) and bin_energy(i) = E_min + (i - 0.5) * bin_width (:985).  `setup`: the attribute
+        fields of netcdf3._setup_atts.  Writes the partial means if sampling has not completed; rank 0 only."""
+        rho, _ = self.rho_of_E_partial()
+        if self.rank != 0:
+            return
+        import os
+        d = os.path.join(directory, "asro")
+        os.makedirs(d, exist_ok=True)
+        e_min = self.p.energy_min * (self.n_atoms / (RY_TO_EV * 1000))
+        bin_energy = np.array([e_min + (i - 0.5) * self.bin_width for i in range(1, self.p.bins + 1)])
+        ncdf_radial_density_writer_across_energy(os.path.join(d, "rho_of_E.nc"), rho, shells, bin_energy, setup)
 
     def run(self, max_sweeps_per_stage=100000, callback=None):
         """pre_sampling (:757-838) then the f-halving loop (:198-292).  Returns ln g(E) [bins]."""

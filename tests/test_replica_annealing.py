@@ -49,8 +49,16 @@ def _run(rank, world, golden, torch_device=None):
     return drv, drv.run()
 
 
-def test_annealing_control_flow_single_rank(golden):
+def test_annealing_control_flow_single_rank(golden, tmp_path):
     drv, (per, av) = _run(0, 1, golden)
+    from scipy.io import netcdf_file
+    from brawl_b200.replica_annealing import save_av_radial_density
+    shells = drv.dev.sys.lattice_shells(drv.dev.g[0], 3)
+    save_av_radial_density(str(tmp_path), av, shells, dict(n_1=4, n_2=4, n_3=4, n_species=4, lattice="bcc", interaction_file="bcc_epi.vij",
+                                                           species_concentrations=[0.0, 0.25, 0.25, 0.25, 0.25], wc_range=3))
+    f = netcdf_file(str(tmp_path / "asro" / "av_radial_density.nc"), "r", mmap=False)
+    assert f.variables["rho data"].dimensions == ("T", "r", "j", "i") and np.array_equal(f.variables["rho data"].data, av["rho_of_T"])
+    assert np.array_equal(f.variables["T data"].data, av["temperature"]) and np.array_equal(f.variables["U data"].data, av["energies_of_T"])
     assert per["energies_of_T"].shape == (3, 3) and per["rho_of_T"].shape == (3, 3, 3, 4, 4)
     assert np.array_equal(av["temperature"], [1500.0, 1000.0, 500.0]) and av["n_chains"] == 3
     for k in ("energies_of_T", "C_of_T", "acceptance_of_T", "rho_of_T"):

@@ -267,7 +267,7 @@ def test_driver_dynamic_windows_control_flow(orc, golden, monkeypatch, tmp_path)
     assert len(d4.window_history) == 1
 
 
-def test_driver_rho_of_E_sampling(orc, golden, monkeypatch):
+def test_driver_rho_of_E_sampling(orc, golden, monkeypatch, tmp_path):
     """rho(E) (wang-landau.F90:574-592, save_rho_E :346-381): per-bin means of the radial densities, capped at
     max(radial_samples / walkers, 1) samples per walker and bin; a bin completes at radial_samples samples."""
     from brawl_b200 import wang_landau as wl
@@ -291,6 +291,17 @@ def test_driver_rho_of_E_sampling(orc, golden, monkeypatch):
     # ordering tendency: the unlike-pair density in shell 1 differs between the lowest and highest sampled bins
     lo_b, hi_b = np.flatnonzero(n)[0], np.flatnonzero(n)[-1]
     assert not np.allclose(rho[lo_b, 1], rho[hi_b, 1])
+    # asro/rho_of_E.nc (ncdf_radial_density_writer_across_energy, netcdf_io.f90:260-346)
+    from scipy.io import netcdf_file
+    setup = dict(n_1=4, n_2=4, n_3=4, n_species=4, lattice="bcc", interaction_file="bcc_epi.vij",
+                 species_concentrations=[0.0, 0.25, 0.25, 0.25, 0.25], wc_range=3)
+    shells = drv.dev.sys.lattice_shells(drv.dev.g[0], 3)
+    drv.save_rho_of_E(str(tmp_path), shells, setup)
+    f = netcdf_file(str(tmp_path / "asro" / "rho_of_E.nc"), "r", mmap=False)
+    assert f.variables["rho data"].dimensions == ("U", "r", "j", "i") and np.array_equal(f.variables["rho data"].data, rho)
+    assert np.array_equal(f.variables["r data"].data, shells)
+    u = np.array(f.variables["U data"].data)
+    assert u.shape == (32,) and np.allclose(u, 0.5 * (drv.edges[:-1] + drv.edges[1:]), rtol=1e-13)
     # off by default
     d0 = wl.WangLandau("bcc", 4, 4, 4, 4, 6, golden["t04_V"], [32, 32, 32, 32], p, walkers=2, seed=5)
     d0.run(max_sweeps_per_stage=50)
