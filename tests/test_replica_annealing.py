@@ -135,3 +135,12 @@ def test_annealing_on_gpu(golden):
         assert np.array_equal(np.bincount(gi.ravel(), minlength=6)[1:], counts)
     for l, z in enumerate((1, 8, 6)):
         assert np.allclose(per["rho_of_T"][:, :, l].sum(axis=-2), z) or np.allclose(per["rho_of_T"][:, :, l].sum(axis=-1), z)
+
+
+def test_av_energy_diagnostics_text_matches_golden(golden, tmp_path):
+    """The reference's own av_energy_diagnostics.dat (case 02) rewritten from the numbers it holds."""
+    from brawl_b200.replica_annealing import save_av_energy_diagnostics
+    ref = str(golden["t02_av_diag_txt"])
+    T, E, C, a = (float(x) for x in ref.split("\n")[1].split())
+    save_av_energy_diagnostics(str(tmp_path), dict(temperature=[T], energies_of_T=[E], C_of_T=[C], acceptance_of_T=[a]))
+    assert open(tmp_path / "energies" / "av_energy_diagnostics.dat").read() == ref
