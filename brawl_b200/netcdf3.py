@@ -92,3 +92,59 @@ def ncdf_radial_density_writer_across_energy(filename, rho, r, U, setup):
     nU, nr, S, _ = rho.shape
     write_classic(filename, [("i", S), ("j", S), ("r", nr), ("U", nU), ("r_i", len(r)), ("U_i", len(U))], _setup_atts(setup),
                   [("rho data", [3, 2, 1, 0], NC_DOUBLE, rho), ("r data", [4], NC_DOUBLE, r), ("U data", [5], NC_DOUBLE, U)])
+
+
+def ncdf_grid_state_writer(filename, config, setup):
+    """ncdf_grid_state_writer (netcdf_io.f90:495-583): one configuration, int8 grid [2n3][2n2][2n1] (the layout of
+    Device.get_config) stored as NF90_SHORT "configuration"(z, y, x, b) -- the restart file ncdf_config_reader reads."""
+    g = np.asarray(config)
+    gz, gy, gx = g.shape
+    atts = [("N_basis", int(setup.get("n_basis", 1))), ("N_1", int(setup["n_1"])), ("N_2", int(setup["n_2"])), ("N_3", int(setup["n_3"])),
+            ("Number of Species", int(setup["n_species"])), ("Lattice Type", str(setup["lattice"]).rstrip()),
+            ("Concentrations", np.asarray(setup["species_concentrations"], dtype=np.float64))]
+    write_classic(filename, [("b", int(setup.get("n_basis", 1))), ("x", gx), ("y", gy), ("z", gz)], atts,
+                  [("configuration", [3, 2, 1, 0], NC_SHORT, g.astype(np.int16))])
+
+
+def ncdf_config_reader(filename):
+    """ncdf_config_reader (netcdf_io.f90:1368-1429): the "configuration" variable of a classic file written by
+    ncdf_grid_state_writer, returned as int8 [2n3][2n2][2n1] (ready for Device.set_config)."""
+    d = open(filename, "rb").read()
+    if d[:4] != b"CDF\x01":
+        raise ValueError("%s is not a NetCDF classic file" % filename)
+    rd = lambda o: struct.unpack(">I", d[o:o + 4])[0]
+    o = 8
+    dims = []
+    if rd(o) == _NC_DIMENSION:
+        n = rd(o + 4); o += 8
+        for _ in range(n):
+            ln = rd(o); o += 4 + ln + (-ln % 4)
+            dims.append(rd(o)); o += 4
+    else:
+        o += 8
+    if rd(o) == _NC_ATTRIBUTE:
+        n = rd(o + 4); o += 8
+        for _ in range(n):
+            ln = rd(o); o += 4 + ln + (-ln % 4)
+            typ, ne = rd(o), rd(o + 4); o += 8
+            nb = ne * {NC_CHAR: 1, NC_SHORT: 2, NC_INT: 4, NC_DOUBLE: 8, 1: 1, 5: 4}[typ]
+            o += nb + (-nb % 4)
+    else:
+        o += 8
+    if rd(o) != _NC_VARIABLE:
+        raise ValueError("%s holds no variables" % filename)
+    n = rd(o + 4); o += 8
+    for _ in range(n):
+        ln = rd(o); name = d[o + 4:o + 4 + ln].decode(); o += 4 + ln + (-ln % 4)
+        nd = rd(o); dimids = [rd(o + 4 + 4 * k) for k in range(nd)]; o += 4 + 4 * nd
+        if rd(o) != 0 or rd(o + 4) != 0:
+            raise ValueError("variable attributes are not expected in a configuration file")
+        o += 8
+        typ, _, begin = rd(o), rd(o + 4), rd(o + 8); o += 12
+        if name == "configuration":
+            if typ != NC_SHORT:
+                raise ValueError("configuration is not NF90_SHORT")
+            shape = [dims[k] for k in dimids]
+            a = np.frombuffer(d, dtype=">i2", count=int(np.prod(shape)), offset=begin).reshape(shape)
+            return a[..., 0].astype(np.int8)
+    raise ValueError("%s holds no 'configuration' variable" % filename)

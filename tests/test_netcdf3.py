@@ -38,3 +38,24 @@ def test_writer_1d_and_across_energy(golden, tmp_path):
     assert f.variables["rho data"].dimensions == ("U", "r", "j", "i") and np.array_equal(f.variables["rho data"].data, rho)
     assert np.array_equal(f.variables["U data"].data, np.linspace(-1, 0, 7)) and getattr(f, "Interaction file") == b"bcc_epi.vij"
     assert getattr(f, "Warren-Cowley Range") == 3 and np.array_equal(f.Concentrations, [0.0, 0.25, 0.25, 0.25, 0.25])
+
+
+def test_grid_state_writer_and_reader_against_golden(golden, tmp_path):
+    """The reference's golden proc_0000_initial_config_at_0300.0.nc (case 02): read by the restart reader, rewritten
+    byte for byte by the writer."""
+    from brawl_b200 import netcdf3
+    raw = golden["raw_t02_r0_initial_nc"].tobytes()
+    src = str(tmp_path / "ref.nc")
+    open(src, "wb").write(raw)
+    cfg = netcdf3.ncdf_config_reader(src)
+    assert cfg.dtype == np.int8 and np.array_equal(cfg, golden["t02_r0_initial"])
+    f = netcdf_file(src, "r", mmap=False)
+    setup = dict(n_basis=f.N_basis, n_1=f.N_1, n_2=f.N_2, n_3=f.N_3, n_species=getattr(f, "Number of Species"),
+                 lattice=getattr(f, "Lattice Type").decode(), species_concentrations=np.array(f.Concentrations))
+    out = str(tmp_path / "mine.nc")
+    netcdf3.ncdf_grid_state_writer(out, cfg, setup)
+    assert open(out, "rb").read() == raw
+    import pytest
+    open(out, "wb").write(b"HDF5....")
+    with pytest.raises(ValueError):
+        netcdf3.ncdf_config_reader(out)
