@@ -127,15 +127,13 @@ def save_av_radial_density(directory, av, shells, setup):
 
 
 def save_av_energy_diagnostics(directory, av):
-    """energies/av_energy_diagnostics.dat (diagnostics_writer, src/metropolis_output.f90:113-135, format
-    '(F8.1,2X,F24.15,2X,F24.15,2X,F6.4)' under the header line ' # T E C acceptance_rate')."""
+    """energies/av_energy_diagnostics.dat (diagnostics_writer, src/metropolis_output.f90:113-135)."""
     import os
+    from .text_io import diagnostics_writer
     d = os.path.join(directory, "energies")
     os.makedirs(d, exist_ok=True)
-    with open(os.path.join(d, "av_energy_diagnostics.dat"), "w") as fh:
-        fh.write(" # T E C acceptance_rate\n")
-        for T, E, C, a in zip(av["temperature"], av["energies_of_T"], av["C_of_T"], av["acceptance_of_T"]):
-            fh.write("%8.1f  %24.15f  %24.15f  %6.4f\n" % (T, E, C, a))
+    diagnostics_writer(os.path.join(d, "av_energy_diagnostics.dat"), av["temperature"], av["energies_of_T"], av["C_of_T"],
+                       av["acceptance_of_T"])
 
 
 def warren_cowley(rho, concentrations, coordination):
