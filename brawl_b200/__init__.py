@@ -8,3 +8,4 @@ from .engine import Device, RunParams, K_B_IN_RY, RY_TO_EV, LATTICES  # noqa: F4
 from . import wang_landau  # noqa: F401,E402
 from . import nested_sampling  # noqa: F401,E402
 from . import replica_annealing  # noqa: F401,E402
+from . import inputs, netcdf3, text_io  # noqa: F401,E402

@@ -83,7 +83,8 @@ def main():
     # --- the reference's own input files for its regression cases (text) + two raw NetCDF goldens
     for case, files in (("01_serial_metropolis", ("brawl.inp", "metropolis.inp", "fcc_epi.vij")),
                         ("02_parallel_metropolis", ("brawl.inp", "metropolis.inp", "bcc_epi.vij")),
-                        ("03_serial_nested_sampling", ("brawl.inp", "ns_input.inp", "fcc_al_1.00_crfeconi.vij"))):
+                        ("03_serial_nested_sampling", ("brawl.inp", "ns_input.inp", "fcc_al_1.00_crfeconi.vij")),
+                        ("04_parallel_wang-landau", ("brawl.inp", "wl_input.inp", "bcc_epi.vij"))):
         for fn in files:
             out["in_%s_%s" % (case[:2], fn)] = text(t + case + "/" + fn)
     out["raw_t02_r0_initial_nc"] = np.frombuffer(open(r + "02_parallel_metropolis/proc_0000_initial_config_at_0300.0.nc", "rb").read(), dtype=np.uint8)
