@@ -120,3 +120,70 @@ def wang_landau_from_files(directory, walkers=8, **kw):
     _, counts = species_quotas(p)
     return wl.WangLandau(p["lattice"], p["n_1"], p["n_2"], p["n_3"], p["n_species"], p["interaction_range"], V, counts, wp,
                          walkers=walkers, **kw), p
+
+
+def read_metropolis_file(path):
+    """metropolis.inp -> dict (read_metropolis_file, src/io.f90:500-690): defaults, the n_sample_steps_* fall-backs
+    (including the reference's asro/alro typo, io.f90:654-662) and `burn_in` implying `burn_in_start` (:681-684)."""
+    if not os.path.exists(path):
+        raise BrawlCudaError("Could not find Metropolis control file: " + path)
+    m = dict(n_burn_in_steps=0, burn_in_start=False, burn_in=False, calculate_energies=True, calculate_asro=True,
+             calculate_alro=False, n_sample_steps_asro=0, n_sample_steps_alro=0, n_sample_steps_trajectory=0,
+             write_trajectory_xyz=False, write_trajectory_energy=False, write_trajectory_asro=False,
+             write_initial_config_xyz=False, write_initial_config_nc=False, write_final_config_xyz=False,
+             write_final_config_nc=False, read_start_config_nc=False, start_config_file="", T_steps=1, delta_T=1.0,
+             nbr_swap=False)
+    ints = ("n_mc_steps", "n_burn_in_steps", "n_sample_steps", "n_sample_steps_asro", "n_sample_steps_alro",
+            "n_sample_steps_trajectory", "T_steps")
+    for line in open(path):
+        if line.lstrip().startswith("#") or "=" not in line:
+            continue
+        k, v = line.split("=", 1)
+        k = k.rstrip(" \t")
+        if k in ints:
+            m[k] = int(v.split("#")[0])
+        elif k in ("T", "delta_T"):
+            m[k] = float(v.split("#")[0])
+        elif k in ("mode", "start_config_file"):
+            m[k] = _string(v)
+        elif k in m and isinstance(m[k], bool):
+            m[k] = _logical(v)
+    for k in ("mode", "n_mc_steps", "n_sample_steps", "T"):
+        if k not in m:
+            raise BrawlCudaError("Missing '%s' in Metropolis input file" % k)
+    if m["n_sample_steps_alro"] == 0:
+        m["n_sample_steps_asro"] = m["n_sample_steps"]
+        m["n_sample_steps_alro"] = m["n_sample_steps"]
+    if m["n_sample_steps_trajectory"] == 0:
+        m["n_sample_steps_trajectory"] = m["n_sample_steps"]
+    if m["burn_in"]:
+        m["burn_in_start"] = True
+    return m
+
+
+def replica_annealing_from_files(directory, n_replicas, **kw):
+    """metropolis_simulated_annealing's set-up from brawl.inp + metropolis.inp + the interaction file, with
+    `n_replicas` chains per GPU in place of one chain per MPI rank."""
+    from . import replica_annealing as ra
+    p = read_control_file(os.path.join(directory, "brawl.inp"))
+    m = read_metropolis_file(os.path.join(directory, "metropolis.inp"))
+    V = read_exchange(os.path.join(directory, p["interaction_file"]), p["n_species"], p["interaction_range"])
+    _, counts = species_quotas(p)
+    drv = ra.ReplicaAnnealing(p["lattice"], p["n_1"], p["n_2"], p["n_3"], p["n_species"], p["interaction_range"], V, counts,
+                              n_replicas=n_replicas, T=m["T"], T_steps=m["T_steps"], delta_T=m["delta_T"],
+                              n_mc_steps=m["n_mc_steps"], n_sample_steps=m["n_sample_steps"],
+                              n_burn_in_steps=m["n_burn_in_steps"], burn_in_start=m["burn_in_start"], burn_in=m["burn_in"],
+                              n_sample_steps_asro=m["n_sample_steps_asro"],
+                              wc_range=p["wc_range"] if m["calculate_asro"] else 0, nbr_swap=m["nbr_swap"], **kw)
+    return drv, p, m
+
+
+def nested_sampling_from_files(directory, n_runs=1, **kw):
+    """nested_sampling_main's set-up from brawl.inp + ns_input.inp + the interaction file."""
+    from . import nested_sampling as ns
+    p = read_control_file(os.path.join(directory, "brawl.inp"))
+    sp = ns.NSParams.from_file(os.path.join(directory, "ns_input.inp"))
+    V = read_exchange(os.path.join(directory, p["interaction_file"]), p["n_species"], p["interaction_range"])
+    _, counts = species_quotas(p)
+    return ns.NestedSampling(p["lattice"], p["n_1"], p["n_2"], p["n_3"], p["n_species"], p["interaction_range"], V, counts, sp,
+                             n_runs=n_runs, **kw), p

@@ -77,3 +77,22 @@ def test_wang_landau_from_the_reference_case_04_files(golden, orc, tmp_path, mon
     assert drv.counts == [32, 32, 32, 32] and drv.n_atoms == 128 and p["wc_range"] == 3
     assert drv.window_indices.tolist() == [[1, 128], [97, 256], [217, 384], [343, 512]]
     assert np.array_equal(drv.edges, wl.create_energy_bins(128, -96.0, 0.0, 512))
+
+
+def test_metropolis_file_and_annealing_from_the_reference_case_02_files(golden, tmp_path, monkeypatch):
+    import test_replica_annealing as t
+    from brawl_b200 import inputs, replica_annealing as ra
+    d = str(tmp_path)
+    _write(d, golden, "02", ("brawl.inp", "metropolis.inp", "bcc_epi.vij"))
+    m = inputs.read_metropolis_file(os.path.join(d, "metropolis.inp"))
+    # what brawl_driver's dryrun prints for the same file (tests/test_host_driver.py): asro=128 alro=128 traj=1
+    assert (m["mode"], m["n_mc_steps"], m["n_sample_steps"], m["n_sample_steps_asro"], m["n_sample_steps_alro"],
+            m["n_sample_steps_trajectory"], m["T"], m["T_steps"]) == ("simulated_annealing", 128, 1, 128, 128, 1, 300.0, 1)
+    monkeypatch.setattr(ra, "Device", t._OracleChains)
+    drv, p, m2 = inputs.replica_annealing_from_files(d, n_replicas=2)
+    per, av = drv.run()
+    assert per["energies_of_T"].shape == (2, 1) and av["temperature"].tolist() == [300.0] and drv.counts == [32, 32, 32, 32]
+    assert av["rho_of_T"].shape == (1, p["wc_range"], 4, 4) and drv.attempted == 2 * 128
+    with pytest.raises(inputs.BrawlCudaError, match="Missing 'T' in Metropolis input file"):
+        open(tmp_path / "m2.inp", "w").write("mode = simulated_annealing\nn_mc_steps = 10\nn_sample_steps = 1\n")
+        inputs.read_metropolis_file(str(tmp_path / "m2.inp"))
