@@ -180,8 +180,9 @@ def main():
     ap.add_argument("--box", default="", help="override box extents, e.g. 64,64,32")
     ap.add_argument("--steps-per-phase", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--layout", type=int, default=0, choices=[0, 1, 2],
-                    help="0 automatic, 1 byte-lattice kernels only, 2 word kernels without the warp-group split (A/B runs)")
+    ap.add_argument("--layout", type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
+                    help="0 automatic (epoch kernel), 1 byte-lattice kernels only, 2 / 3 the one-gather-per-step word kernels "
+                         "without / with the warp-group split (3 = the round-1 default), 4 / 5 other epoch lengths (A/B runs)")
     ap.add_argument("--n-cells", type=int, default=N_CELLS)
     ap.add_argument("--workload", default="chain", choices=["chain", "replicas"],
                     help="chain: BASELINE configs[1] (headline); replicas: configs[4], R x 32^3 bcc AlCrFeCoNi per GPU")

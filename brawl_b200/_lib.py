@@ -47,6 +47,7 @@ _SIGNATURES = {
     "brawl_cuda_wl_sweeps_replay": [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _d, _i64, _i, _vp, _vp, _vp],
     "brawl_cuda_wl_sweeps": [_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _d, _i64, _i, _u64, _u64, _vp, _vp],
     "brawl_cuda_wl_enter_window": [_vp, _i, _vp, _vp, _vp, _d, _i64, _u64, _u64, _vp, _vp],
+    "brawl_cuda_wl_enter_window_replay": [_vp, _i, _d, _d, _d, _d, _d, _i64, _vp, _i64, _i, _vp, _vp, _vp, _vp],
     "brawl_cuda_lattice_ptr": [_vp, _vp, _vp],
     "brawl_cuda_swap_replicas": [_vp, _i, _i],
     "brawl_cuda_wl_window_average": [_vp, _vp, _i, _i, _i, _d],

@@ -18,6 +18,7 @@
 #include "replay_kernels.cuh"
 #include "tile_metropolis.cuh"
 #include "word_metropolis.cuh"
+#include "epoch_metropolis.cuh"
 #include "walker_kernels.cuh"
 
 // ---- error state ---------------------------------------------------------------------------------
@@ -138,6 +139,7 @@ extern "C" int brawl_cuda_create(int lattice, int n1, int n2, int n3, int S, int
   h->tune_box[0] = h->tune_box[1] = h->tune_box[2] = 0; h->tune_steps = 0;
   h->dE_mode = 2;
   h->word_split = 1;
+  h->word_epoch = 8;
 #define BRW_CREATE_CUDA(x) do { if (brw_cuda_check((x), #x)) { brawl_cuda_destroy(h); return 1; } } while (0)
   BRW_CREATE_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
@@ -530,7 +532,8 @@ static const BrwFastEntry brw_fast_table[] = {
 #endif
 // pitchz < bzc: consecutive z layers share their frozen margin planes (box extent bzc, layer pitch pitchz = bzc - margin);
 // split: two independent warp groups per CTA on disjoint z zones (word_metropolis.cuh, SPLIT)
-struct BrwWordEntry { int lat, nsh, bxc, byc, bzc, margin, pxp, plp, nlimb; BrwFastKernel fn, fn_exact; int pitchz; bool split; };
+// epoch > 0: counts cached over epochs of that many steps (epoch_metropolis.cuh); pitchxc < bxc: x margins shared as well
+struct BrwWordEntry { int lat, nsh, bxc, byc, bzc, margin, pxp, plp, nlimb; BrwFastKernel fn, fn_exact; int pitchz; bool split; int epoch = 0; int pitchxc = 0; };
 static const BrwWordEntry brw_word_table[] = {
     // bcc, 4 shells, box 64x64x32 (doubled-grid units): 32 warps x 28 = 896 trials per step
     {1, 4, 32, 32, 32, 4, 32, 1024, BRW_NLIMB, brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, BRW_NLIMB, false, BRW_PAIRW>,
@@ -542,6 +545,14 @@ static const BrwWordEntry brw_word_table[] = {
     // 840 trials per step like the 64x64x28 box, but the groups' gather and arithmetic phases overlap
     {1, 4, 32, 32, 32, 4, 32, 1024, BRW_NLIMB, brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, BRW_NLIMB, false, BRW_PAIRW, true>,
      brw_box_metropolis_word_kernel<1, 4, 32, 32, 32, 4, 32, 1024, BRW_NLIMB, true, BRW_PAIRW, true>, 28, true},
+    // box 68x64x32 at a pitch of 64x64x28 (margins shared in x and z: 15 sites per class row), 32 warps x 30 lanes = 960
+    // trials per step, neighbour counts cached over epochs of 8 / 4 steps
+    {1, 4, 34, 32, 32, 4, 34, 1088, BRW_NLIMB, brw_box_metropolis_epoch_kernel<4, 34, 32, 32, 4, 34, 1088, BRW_NLIMB, false, 8>,
+     brw_box_metropolis_epoch_kernel<4, 34, 32, 32, 4, 34, 1088, BRW_NLIMB, true, 8>, 28, false, 8, 32},
+    {1, 4, 34, 32, 32, 4, 34, 1088, BRW_NLIMB, brw_box_metropolis_epoch_kernel<4, 34, 32, 32, 4, 34, 1088, BRW_NLIMB, false, 4>,
+     brw_box_metropolis_epoch_kernel<4, 34, 32, 32, 4, 34, 1088, BRW_NLIMB, true, 4>, 28, false, 4, 32},
+    {1, 4, 34, 32, 32, 4, 34, 1088, BRW_NLIMB, brw_box_metropolis_epoch_kernel<4, 34, 32, 32, 4, 34, 1088, BRW_NLIMB, false, 2>,
+     brw_box_metropolis_epoch_kernel<4, 34, 32, 32, 4, 34, 1088, BRW_NLIMB, true, 2>, 28, false, 2, 32},
 };
 
 // launch helper for the warp-per-walker kernels: layout + opt-in shared memory
@@ -660,10 +671,11 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
         if ((a == 0 && b == 0 && c == 0) || (a == 2 && b == 2 && c == 2)) independent = false;
       }
       if (!independent) continue;
-      const int Be[3] = {e.bxc << g.xs, e.byc << g.ys, e.bzc};
-      if (h->tune_box[0] > 0) {          // user box: must be exactly this entry's box (tune_box z = layer pitch)
+      const int Be[3] = {(e.pitchxc ? e.pitchxc : e.bxc) << g.xs, e.byc << g.ys, e.bzc};    // x, y: box pitch
+      if (e.epoch != h->word_epoch) continue;
+      if (h->tune_box[0] > 0) {          // user box: must be exactly this entry's box (tune_box x, z = pitch)
         if (h->tune_box[0] != Be[0] || h->tune_box[1] != Be[1] || h->tune_box[2] != e.pitchz) continue;
-        if (e.split != (h->word_split != 0)) continue;
+        if (!e.epoch && e.split != (h->word_split != 0)) continue;
       } else if (e.split && h->word_split == 0) continue;
       // boxes tile x and y; along z they need not (the slab left over is visited in later phases: the origin is random)
       if (g.gx % Be[0] || g.gy % Be[1] || Be[2] > g.gz) continue;
@@ -671,7 +683,7 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       const long n_boxes = (long)(g.gx / Be[0]) * (g.gy / Be[1]) * nbz * h->n_replicas;
       const int planes = (Be[2] - 2 * e.margin) / 4 - (e.split ? 1 : 0);
       const int rows = std::min(32, ((((Be[1] - 3 * e.margin) / 2) & ~3) / 4) * planes);
-      const long trials_box = (long)rows * 2 * ((Be[0] - 2 * e.margin) / 4);
+      const long trials_box = (long)rows * 2 * (((e.bxc << g.xs) - 2 * e.margin) / 4);
       // one CTA per SM; a step costs ~rows warp-gathers on the shared-memory pipe (overlapped with the arithmetic of
       // the other group's in the split kernels: measured +5 %)
       const long waves = (n_boxes + n_sm - 1) / n_sm;
@@ -680,7 +692,7 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       if (rate > best_rate) { best_rate = rate; we = &e; }
     }
     if (we) {
-      B[0] = we->bxc << g.xs; B[1] = we->byc << g.ys; B[2] = we->pitchz;     // B = box pitch (origin stride)
+      B[0] = (we->pitchxc ? we->pitchxc : we->bxc) << g.xs; B[1] = we->byc << g.ys; B[2] = we->pitchz;     // B = box pitch (origin stride)
       m = we->margin;
     }
   }
@@ -746,7 +758,7 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       p.n_modes = 1;
       BrwBoxMode &md = p.mode[0];
       md.P[0] = md.P[1] = md.P[2] = 4;
-      md.A[0] = (B[0] - 2 * m) / 4;                               // sites per x-row of one sub-class
+      md.A[0] = ((we->bxc << g.xs) - 2 * m) / 4;                  // sites per x-row of one sub-class
       md.A[1] = (((B[1] - 3 * m) / 2) & ~3) / 4;                  // rows per plane in one y half
       md.A[2] = (we->bzc - 2 * m) / 4;                            // planes per sub-class
       md.M = std::min(32, md.A[1] * (md.A[2] - (we->split ? 1 : 0))) * 2 * md.A[0];
@@ -760,6 +772,7 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
     // whose steps are short enough for the box copies to be 9 % of a four-sweep phase
     int steps = h->tune_steps > 0 ? h->tune_steps : ((we ? 6 : 4) * p.box_sites + Mmax - 1) / Mmax;
     p.steps = std::max(8, std::min(steps, 512));
+    if (we && we->epoch) p.steps = ((p.steps + we->epoch - 1) / we->epoch) * we->epoch;      // whole epochs
     p.steps_a = p.steps;
     pl->M_a = 0;
     if (we && we->split) {
@@ -855,6 +868,41 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
           int dxc = (par + dx) >> 1, dyc = g.ys ? ((par + dy) >> 1) : dy;
           blob[urow_words + par * g.ztot + k] = dz * we->plp + dyc * we->pxp + dxc;
         }
+      if (we->epoch) {
+        // site-energy table of the epoch kernels: X_n[c][s] = V_n(a, s) - V_n(a, 4) - (V_n(4, s) - V_n(4, 4)) for the species a
+        // of cache row a + 1 (S = 5; plain V_n(a, s) for S <= 4), rounded to 2^-k units and split into three signed 8-bit digits.
+        // |h - real| <= Z/2 units per cached value, four values per dE  =>  guard = 2 Z units (+ the f64 rounding slack)
+        // S <= 4: all four counts are explicit, energies relative to species 3 (its row is identically zero and not computed)
+        p.h_rows = S == 5 ? 4 : 3;
+        auto X = [&](int n, int a, int s2) {
+          double x = Vn(n, a, s2);
+          if (S == 5) x -= Vn(n, a, 4) + Vn(n, 4, s2) - Vn(n, 4, 4);
+          else if (S == 4) x -= Vn(n, 3, s2);
+          return x;
+        };
+        double xmax = 0.0;
+        for (int n = 0; n < NSH; n++) for (int a = 0; a < std::min(S, 4); a++) for (int s2 = 0; s2 < std::min(S, 4); s2++)
+          xmax = std::max(xmax, std::fabs(X(n, a, s2)));
+        int kx = 0;
+        if (xmax > 0.0) kx = (int)std::floor(std::log2(std::ldexp(1.0, 22) / xmax));
+        p.fix_scale = std::ldexp(1.0, -kx);
+        p.guard = 2.0 * g.ztot * p.fix_scale + 1e-9 * g.ztot * umax;
+        p.gfix = (int)std::ceil(p.guard / p.fix_scale) + 1;
+        std::memset(p.xdig, 0, sizeof p.xdig);
+        for (int c = 0; c < 4; c++) {
+          const int a = c;                                  // cache row = species + 1
+          if (a >= S || c >= p.h_rows) continue;
+          for (int n = 0; n < NSH; n++)
+            for (int s2 = 0; s2 < std::min(S, 4); s2++) {
+              long long v = std::llrint(std::ldexp(X(n, a, s2), kx));
+              for (int k = 0; k < 3; k++) {
+                long long dgt = k == 2 ? v : ((v + 128) & 255) - 128;
+                v = (v - dgt) >> 8;
+                p.xdig[(n * 3 + k) * 4 + c] |= (int)((uint32_t)(uint8_t)(int8_t)dgt << (8 * s2));
+              }
+            }
+        }
+      }
       std::memcpy(blob.data() + tab_words, h->hV, sizeof(double) * p.v_entries);
       cudaFree(pl->d_Vrep); pl->d_Vrep = nullptr;
       BRW_PLAN_CUDA(cudaMalloc(&pl->d_Vrep, blob.size() * sizeof(int)));
@@ -863,6 +911,9 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       pl->screened = h->dE_mode != 0; pl->word = true; pl->split = we->split;
       pl->fast_smem = blob.size() * sizeof(int) + 32 * 8 + 2 * (size_t)p.mode[0].A[1] * p.mode[0].A[2] * 4 + 16 +
                       (size_t)(std::max(p.steps, p.steps_a) + 1) * 32 + (size_t)we->plp * p.bzc * 4;
+      if (we->epoch)      // epoch table + per-warp count cache instead of the step table
+        pl->fast_smem = blob.size() * sizeof(int) + 32 * 8 + 2 * (size_t)p.mode[0].A[1] * p.mode[0].A[2] * 4 + 16 +
+                        (size_t)(p.steps / we->epoch) * 32 + 32 * 320 * 4 + (size_t)we->plp * p.bzc * 4;
       pl->threads = 32 * std::min(32, p.mode[0].A[1] * (p.mode[0].A[2] - (we->split ? 1 : 0)));
       BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)pl->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
     }
@@ -910,6 +961,8 @@ extern "C" int brawl_cuda_metropolis_set_layout(brawl_cuda_t *h, int byte_layout
   BRW_CUDA(cudaStreamSynchronize(h->stream));
   h->byte_layout = byte_layout_only == 1;
   h->word_split = byte_layout_only == 2 ? 0 : 1;      // 2: word kernels without the two-warp-group split
+  // 2, 3: the one-gather-per-step word kernels (3: with the two-warp-group split, the round-1 default); 4: epochs of 4
+  h->word_epoch = byte_layout_only == 2 || byte_layout_only == 3 ? 0 : byte_layout_only == 4 ? 4 : byte_layout_only == 5 ? 2 : 8;
   for (int i = 0; i < 2; i++) { brw_free_plan((BrwPlan *)h->mc_plan[i]); h->mc_plan[i] = nullptr; }
   return 0;
 }
@@ -1166,6 +1219,33 @@ extern "C" int brawl_cuda_wl_sweeps_replay(brawl_cuda_t *h, int replica, double 
   BRW_CUDA(cudaStreamSynchronize(h->stream));
   if (n_accept) *n_accept = (int64_t)acc;
   if (e_final) *e_final = ef;
+  return 0;
+}
+
+extern "C" int brawl_cuda_wl_enter_window_replay(brawl_cuda_t *h, int replica, double e_start, double target, double lo_e,
+                                                 double hi_e, double two_sigma_sq, int64_t period, int64_t *i_steps_io,
+                                                 int64_t max_iters, int resume, uint32_t *mt, double *e_out, int *status,
+                                                 int64_t *iters_begun) {
+  BRW_ENTER(h);
+  BRW_REPLICA(h, replica);
+  if (!mt || !i_steps_io || !e_out || !status || !iters_begun) return brw_fail("null argument");
+  if (period < 1 || max_iters < 0 || !(two_sigma_sq > 0.0)) return brw_fail("bad window-entry parameters");
+  const BrwGeom &g = h->g;
+  if (brw_small(h, 625 * 4 + 64)) return 1;
+  double *d_e = (double *)h->d_small;
+  long *d_out = (long *)(d_e + 1);
+  uint32_t *d_mt = (uint32_t *)(d_out + 3);
+  BRW_CUDA(cudaMemcpyAsync(d_mt, mt, 625 * 4, cudaMemcpyHostToDevice, h->stream));
+  brw_wl_enter_replay_kernel<<<1, 32, 0, h->stream>>>(g, h->d_V, h->d_lat + (size_t)replica * g.n_sites, e_start, target, lo_e, hi_e,
+                                                      two_sigma_sq, (long)period, (long)*i_steps_io, (long)max_iters, resume, d_mt,
+                                                      d_e, d_out);
+  BRW_LAUNCH_CHECK("brw_wl_enter_replay_kernel");
+  long o3[3] = {0, 0, 0};
+  BRW_CUDA(cudaMemcpyAsync(mt, d_mt, 625 * 4, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(e_out, d_e, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaMemcpyAsync(o3, d_out, sizeof(o3), cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  *status = (int)o3[0]; *iters_begun = (int64_t)o3[1]; *i_steps_io = (int64_t)o3[2];
   return 0;
 }
 

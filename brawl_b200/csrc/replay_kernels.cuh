@@ -225,6 +225,59 @@ __global__ void __launch_bounds__(32) brw_wl_replay_kernel(BrwGeom g, const doub
   brw_mt_store(&sm.mt, state625);
 }
 
+// ---- enter_energy_window, one walker, MT stream (src/wang-landau.F90:643-741) --------------------
+// Runs iterations of the reference's `do while(.True.)` body until
+//   status 1: the RUNNING energy passes the window test (:691) -- the caller recomputes the exact total energy (:692)
+//             and either stops or resumes with it (`cycle`, resume = 0);
+//   status 2: i_steps reached a multiple of `period` = n_atoms*250 (:677-680) -- the caller re-randomises the lattice with
+//             initial_setup on the same MT stream WITHOUT touching the running energy and resumes the SAME iteration
+//             (resume = 1: the window test comes next);
+//   status 0: max_iters iterations begun.
+// delta_e is formed with the reference's division by 2 sigma^2 (`denom`), not a multiplication by its inverse.
+__global__ void __launch_bounds__(32) brw_wl_enter_replay_kernel(BrwGeom g, const double *__restrict__ V, uint8_t *lat,
+                                                                 double e_start, double target, double lo, double hi,
+                                                                 double denom, long period, long i_steps, long max_iters,
+                                                                 int resume, uint32_t *state625, double *e_out,
+                                                                 long *out3 /* status, iterations begun, i_steps */) {
+  __shared__ BrwReplaySmem sm;
+  brw_mt_load(&sm.mt, state625);
+  const int lane = threadIdx.x;
+  double e_unswapped = e_start;
+  long it = 0;
+  int status = 0;
+  while (true) {
+    if (!resume) {
+      if (it >= max_iters) break;
+      it++;
+      i_steps++;
+      if (i_steps % period == 0) { i_steps = 0; status = 2; break; }
+    }
+    resume = 0;
+    if (e_unswapped < hi && e_unswapped > lo) { status = 1; break; }
+    int x1 = 0, y1 = 0, z1 = 0, x2 = 0, y2 = 0, z2 = 0;
+    brw_warp_propose(g, &sm.mt, 0, x1, y1, z1, x2, y2, z2);
+    const int c1 = brw_grid_to_compact(g, x1, y1, z1), c2 = brw_grid_to_compact(g, x2, y2, z2);
+    const int s1 = lat[c1], s2 = lat[c2];
+    if (s1 != s2) {                                                                          // :718
+      double pair_unswapped, pair_swapped;
+      brw_warp_pair_energies(g, V, lat, x1, y1, z1, x2, y2, z2, s1, s2, true, &sm.w, pair_unswapped, pair_swapped);
+      const double e_swapped = __dadd_rn(__dsub_rn(e_unswapped, pair_unswapped), pair_swapped);   // :724
+      const double d1 = __dsub_rn(e_swapped, target), d0 = __dsub_rn(e_unswapped, target);
+      const double delta_e = __ddiv_rn(__dsub_rn(__dmul_rn(d1, d1), __dmul_rn(d0, d0)), denom);   // :727-729
+      if (lane == 0) {
+        if (log(brw_mt_genrand(&sm.mt)) < -delta_e) {                                        // :731
+          e_unswapped = e_swapped;
+          lat[c1] = (uint8_t)s2; lat[c2] = (uint8_t)s1;
+        }
+      }
+      e_unswapped = __shfl_sync(0xffffffffu, e_unswapped, 0);
+      __syncwarp();
+    }
+  }
+  if (lane == 0) { *e_out = e_unswapped; out3[0] = status; out3[1] = it; out3[2] = i_steps; }
+  brw_mt_store(&sm.mt, state625);
+}
+
 // ---- nested-sampling walk, one walker, MT stream (src/nested_sampling.f90:157-192) -------------
 __global__ void __launch_bounds__(32) brw_ns_replay_kernel(BrwGeom g, const double *__restrict__ V, uint8_t *lat,
                                                            double *energy_io, double e_limit, long n_steps,

@@ -43,6 +43,11 @@ struct BrwBoxParams {          // POD kernel parameter
   int steps_a;                 // SPLIT word kernels: steps of warp group A (fewer warps, shorter steps: it gets more of them)
   int v_entries;               // S*S*n_shells
   int row_mul;                 // word kernel: row of its fixed-point table = code_a*row_mul + code_b
+  // epoch kernels (epoch_metropolis.cuh): signed 8-bit digits of the fixed-point site-energy table, packed over the four
+  // count fields, index (shell*3 + digit)*4 + species; guard band in fixed-point units
+  int xdig[48];
+  int gfix;
+  int h_rows;                  // cached rows per site: 4 (five species, relative to species 4) or 3 (relative to species 3)
 };
 
 struct BrwPlan {

@@ -257,6 +257,17 @@ class Device:
                                                 offset, _p(e), _p(ent)))
         return e, ent
 
+    def wl_enter_window_replay(self, e_start, target, lo_e, hi_e, two_sigma_sq, period, i_steps, max_iters, resume,
+                               mt_state625, replica=0):
+        """One stretch of enter_energy_window (wang-landau.F90:643-741) on the reference's MT stream; returns
+        (status, e_running, i_steps, iterations begun).  status 1: window test passed on the running energy, 2: the
+        lattice is due for re-randomisation, 0: max_iters reached (see include/brawl_cuda.h)."""
+        isteps, e, st, it = C.c_int64(int(i_steps)), C.c_double(), C.c_int(), C.c_int64()
+        check(self.L.brawl_cuda_wl_enter_window_replay(self.h, replica, e_start, target, lo_e, hi_e, two_sigma_sq,
+                                                       int(period), C.byref(isteps), int(max_iters), int(resume),
+                                                       _p(mt_state625), C.byref(e), C.byref(st), C.byref(it)))
+        return st.value, e.value, isteps.value, it.value
+
     def swap_replicas(self, a, b):
         check(self.L.brawl_cuda_swap_replicas(self.h, a, b))
 

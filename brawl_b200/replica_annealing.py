@@ -21,6 +21,17 @@ import numpy as np
 from .engine import Device, K_B_IN_RY, BrawlCudaError
 
 
+def rank_seed(seed, rank):
+    """64-bit Philox key of a rank's Monte-Carlo kernels: the common seed for rank 0, a splitmix64 scramble of
+    (seed, rank) otherwise -- distinct streams per rank (replica ids in the counters are handle-local)."""
+    if rank == 0:
+        return int(seed) & 0xFFFFFFFFFFFFFFFF
+    z = (int(seed) + 0x9E3779B97F4A7C15 * int(rank)) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
 def reduce_results(results, comm_all_gather, world):
     """comms_reduce_metropolis_results (src/comms.F90:122-160): sum over ranks, divide by the number of chains.
     `results`: dict of per-rank arrays already summed over the rank's replicas + "n_chains"."""
@@ -38,10 +49,11 @@ class ReplicaAnnealing:
     def __init__(self, lattice, n_1, n_2, n_3, n_species, n_shells, V_ex, counts, n_replicas, T, T_steps, delta_T,
                  n_mc_steps, n_sample_steps, n_burn_in_steps=0, burn_in_start=False, burn_in=False,
                  n_sample_steps_asro=None, wc_range=2, nbr_swap=False, device=0, rank=0, world=1, seed=0x42726157,
-                 torch_device=None):
+                 torch_device=None, device_cls=None):
         if n_mc_steps < 1 or n_sample_steps < 1 or n_mc_steps < n_sample_steps:
             raise BrawlCudaError("need n_mc_steps >= n_sample_steps >= 1")
-        self.dev = Device(lattice, n_1, n_2, n_3, n_species, n_shells, V_ex, device=device, n_replicas=n_replicas)
+        # device_cls: test hook (the CPU tests stand the oracle in for the CUDA handle); never set by the product
+        self.dev = (device_cls or Device)(lattice, n_1, n_2, n_3, n_species, n_shells, V_ex, device=device, n_replicas=n_replicas)
         self.R, self.S, self.counts = n_replicas, n_species, list(counts)
         self.T, self.T_steps, self.delta_T = float(T), int(T_steps), float(delta_T)
         self.n_mc_steps, self.n_sample_steps = int(n_mc_steps), int(n_sample_steps)
@@ -49,6 +61,9 @@ class ReplicaAnnealing:
         self.n_sample_steps_asro = int(n_sample_steps_asro or n_sample_steps)          # io.f90:654-662
         self.wc_range, self.nbr_swap = int(wc_range), bool(nbr_swap)
         self.rank, self.world, self.seed = rank, world, seed
+        # the Philox counters of the Monte-Carlo kernels hold (trial, tag, handle-local replica / box, phase): the rank
+        # goes into the key, or replica j of every rank would draw the same proposals and uniforms
+        self.mc_seed = rank_seed(seed, rank)
         from .wang_landau import _Comm
         self.comm = _Comm(rank, world, torch_device)
         self.n_atoms = self.dev.n_atoms
@@ -79,7 +94,7 @@ class ReplicaAnnealing:
             beta = 1.0 / sim_temp if sim_temp != 0.0 else math.inf
             temperature[j - 1] = temp
             if (j == 1 and self.burn_in_start) or (j > 1 and self.burn_in):                               # :214-238
-                att, _, _ = dev.metropolis_run(beta, self.n_burn_in_steps, seed=self.seed, nbr_swap=self.nbr_swap)
+                att, _, _ = dev.metropolis_run(beta, self.n_burn_in_steps, seed=self.mc_seed, nbr_swap=self.nbr_swap)
                 self.attempted += int(att.sum())
             n_sweeps = self.n_mc_steps // self.n_sample_steps                                             # :343-344
             n_sweep_steps = self.n_mc_steps // n_sweeps
@@ -87,7 +102,7 @@ class ReplicaAnnealing:
             accepted, attempted = np.zeros(R), np.zeros(R)
             r_dens = np.zeros((R, self.wc_range, self.S, self.S))
             for i in range(1, n_sweeps + 1):
-                att, acc, _ = dev.metropolis_run(beta, n_sweep_steps, seed=self.seed, nbr_swap=self.nbr_swap)   # :350-354
+                att, acc, _ = dev.metropolis_run(beta, n_sweep_steps, seed=self.mc_seed, nbr_swap=self.nbr_swap)   # :350-354
                 accepted += acc
                 attempted += att
                 step_n = i * n_sweep_steps

@@ -197,6 +197,21 @@ int brawl_cuda_wl_sweeps(brawl_cuda_t *h, int n_walkers, double *lng_dev_or_host
 int brawl_cuda_wl_enter_window(brawl_cuda_t *h, int n_walkers, const double *target, const double *lo_e,
                                const double *hi_e, double inv_two_sigma_sq, int64_t max_trials, uint64_t seed,
                                uint64_t offset, double *energies, int32_t *entered);
+/* Deterministic form for ONE walker, consuming the reference's MT19937 stream in the reference's order (two
+ * rdm_site draws = 6 uniforms per iteration, + log(genrand()) when the species differ, :710-731): bit-exact with the
+ * Fortran loop.  Runs iterations of its `do while` body from running energy e_start until
+ *   *status = 1  the running energy satisfies lo_e < E < hi_e (:691): the caller recomputes the exact energy
+ *                (brawl_cuda_total_energy, exact_order = 1) and stops, or resumes with it (resume = 0) -- the `cycle`;
+ *   *status = 2  i_steps reached a multiple of `period` (= n_atoms*250, :677): the caller re-randomises the
+ *                configuration (initial_setup on the same MT stream, set_config), leaves the running energy alone as the
+ *                reference does, and resumes the same iteration with resume = 1;
+ *   *status = 0  max_iters iterations were begun.
+ * two_sigma_sq = 2*(0.0025*|energy_max - energy_min|*n_atoms/(Ry_to_eV*1000))**2, the divisor at :727-729.
+ * *i_steps_io carries the reference's i_steps across calls; *iters_begun returns the iterations started by this call. */
+int brawl_cuda_wl_enter_window_replay(brawl_cuda_t *h, int replica, double e_start, double target, double lo_e,
+                                      double hi_e, double two_sigma_sq, int64_t period, int64_t *i_steps_io,
+                                      int64_t max_iters, int resume, uint32_t *mt_state625, double *e_out, int *status,
+                                      int64_t *iters_begun);
 /* Device storage of the compact lattices ([n_replicas][bytes_per_replica] uint8, species 0..S-1),
  * for device-side exchange between GPUs (replica_exchange, src/wang-landau.F90:1475-1495) */
 int brawl_cuda_lattice_ptr(brawl_cuda_t *h, void **dev_ptr, int64_t *bytes_per_replica);

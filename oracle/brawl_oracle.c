@@ -614,3 +614,164 @@ int orc_wl_window_optimise(int iter, int W, int64_t *iv, const double *mc_steps,
   free(wmc); free(frac); free(nb); free(idx);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Wang-Landau: window entry, stitching, replica exchange (src/wang-landau.F90:643-741, 1147-1194,
+ * 1392-1519).  Parity: the reference ships no golden for these (its own run is not reproducible:
+ * MPI_ANY_SOURCE timing decides who enters a window first), so they are pinned by construction --
+ * line-by-line restatements, compared with the GPU replay kernel / the host implementations.
+ * ---------------------------------------------------------------------------------------- */
+
+/* enter_energy_window (:643-741) for ONE walker (no other rank of the window ever reports in, i.e.
+ * `flag` stays false).  min_e / max_e = MINVAL / MAXVAL(mpi_bin_edges) in Ry per cell; energy_min /
+ * energy_max are the single-precision inputs of wl_input.inp (meV/atom).  One loop iteration = one
+ * pass of the `do while(.True.)` body; the walk stops when it leaves through :685-703 (returns 1) or
+ * after max_iters iterations (returns 0).  Reference behaviours kept: i_steps restarts at 0 and the
+ * lattice is re-randomised with initial_setup every n_atoms*250 iterations WITHOUT refreshing the
+ * running energy (:669-674); the window test uses the running energy first and only then the exact
+ * one (:685-690), an iteration that fails the second test makes no trial (`cycle`).
+ * Outputs: *e_final = e_unswapped on exit, *n_iters = loop iterations executed. */
+int orc_wl_enter_energy_window(const orc_sys *s, int8_t *grid, orc_mt *g, const double *conc,
+                               const int64_t *count, double min_e, double max_e, float energy_min,
+                               float energy_max, int64_t max_iters, double *e_final, int64_t *n_iters) {
+  const double target_energy = (min_e + max_e) / 2.0;                       /* :663 */
+  const double condition = fabs(max_e - min_e) * 0.1;                       /* :664 */
+  /* 0.0025*ABS(energy_max - energy_min)*n_atoms: default-real (single) arithmetic, then / (Ry_to_eV*1000) in double (:726-727) */
+  float sf = 0.0025f * fabsf(energy_max - energy_min);
+  sf = sf * (float)s->n_atoms;
+  const double sigma = (double)sf / (13.605693122 * 1000.0);
+  const double denom = 2.0 * (sigma * sigma);
+  double e_unswapped = orc_total_energy(s, grid);                           /* :669 */
+  int64_t i_steps = 0, it = 0;
+  const int64_t period = (int64_t)s->n_atoms * 50 * 5;
+  int entered = 0;
+  while (it < max_iters) {
+    it++;
+    i_steps++;
+    if (i_steps % period == 0) {                                            /* :677-680 */
+      i_steps = 0;
+      orc_initial_setup(s, conc, count, g, grid);
+    }
+    if (e_unswapped < max_e - condition && e_unswapped > min_e + condition) {   /* :691 */
+      e_unswapped = orc_total_energy(s, grid);
+      if (e_unswapped < max_e - condition && e_unswapped > min_e + condition) { entered = 1; break; }
+      continue;                                                             /* cycle */
+    }
+    int a[3], b[3];
+    orc_random_site(s, g, a);                                               /* :710-711 */
+    orc_random_site(s, g, b);
+    int8_t s1 = grid[gidx(s, a[0], a[1], a[2])], s2 = grid[gidx(s, b[0], b[1], b[2])];
+    if (s1 != s2) {                                                         /* :718 */
+      double pair_unswapped = orc_pair_energy(s, grid, a, b);
+      pair_swap(s, grid, a, b);
+      double pair_swapped = orc_pair_energy(s, grid, a, b);
+      double e_swapped = e_unswapped - pair_unswapped + pair_swapped;       /* :724 */
+      double d1 = e_swapped - target_energy, d0 = e_unswapped - target_energy;
+      double delta_e = (d1 * d1 - d0 * d0) / denom;                         /* :727-729 */
+      if (log(orc_mt_genrand(g)) < -delta_e) e_unswapped = e_swapped;       /* :731 */
+      else pair_swap(s, grid, a, b);
+    }
+  }
+  if (e_final) *e_final = e_unswapped;
+  if (n_iters) *n_iters = it;
+  return entered;
+}
+
+/* dos_combine (:1147-1194) as rank 0 evaluates it.  lng[W][bins]: the window-averaged ln g of every
+ * window (what window_rank_index(i,1) sends); win[W][2]: window_indices (1-based, inclusive).
+ * out[bins].  Kept: beta_index is NOT reset between windows (an empty overlap loop re-uses the last
+ * one); the stitch loop starts AT beta_index, so comb(beta_index) is first rewritten to
+ * (buf + comb) - buf and the rewritten value is what the later bins see. */
+void orc_wl_dos_combine(const double *lng, const int64_t *win, int W, int bins, double *out) {
+  int beta_index = 0;
+  memcpy(out, lng, sizeof(double) * (size_t)bins);                          /* :1159 */
+  for (int i = 2; i <= W; i++) {
+    const double *buf = lng + (size_t)(i - 1) * bins;
+    const int start = (int)win[2 * (i - 1)], end = (int)win[2 * (i - 1) + 1];
+    double beta_diff = 1.7976931348623157e308;                              /* HUGE(1.0_real64) */
+    const int jmax = (int)(win[2 * (i - 2) + 1] - win[2 * (i - 1)] - 1);
+    for (int j = 0; j <= jmax; j++) {                                       /* :1174-1181 */
+      double beta_original = out[start + j + 1 - 1] - out[start + j - 1];
+      double beta_merge = buf[start + j + 1 - 1] - buf[start + j - 1];
+      if (fabs(beta_original - beta_merge) < beta_diff) {
+        beta_diff = fabs(beta_original - beta_merge);
+        beta_index = start + j + 1;
+      }
+    }
+    for (int j = beta_index; j <= end; j++)                                 /* :1183-1185 */
+      out[j - 1] = buf[j - 1] + out[beta_index - 1] - buf[beta_index - 1];
+  }
+  double mn = out[0];
+  for (int b = 1; b < bins; b++) if (out[b] < mn) mn = out[b];
+  for (int b = 0; b < bins; b++) out[b] = out[b] - mn;                      /* :1190 */
+}
+
+/* shuffle_rows (:1512-1519), rank 0's MT stream: rows = walker ranks with their overlap location */
+static void shuffle_rows(int *rows /* [n][2] */, int n, orc_mt *g) {
+  for (int i = n; i >= 2; i--) {
+    int r = 1 + (int)(orc_mt_genrand(g) * (double)i);
+    if (r > n) r = n;
+    int t0 = rows[2 * (i - 1)], t1 = rows[2 * (i - 1) + 1];
+    rows[2 * (i - 1)] = rows[2 * (r - 1)]; rows[2 * (i - 1) + 1] = rows[2 * (r - 1) + 1];
+    rows[2 * (r - 1)] = t0; rows[2 * (r - 1) + 1] = t1;
+  }
+}
+
+/* replica_exchange (:1392-1501) for P = W*num_walkers ranks (rank r = walker r%num_walkers of window
+ * r/num_walkers + 1), given every rank's total energy.  lng[P][bins] is each rank's wl_logdos (window-averaged in the
+ * caller), win[W][2] the window_indices, mts[P] the ranks' MT streams (rank 0 shuffles, :1441-1442; the LOWER walker of
+ * a matched pair draws the acceptance uniform, :1482).  Bins are computed once from the energies at entry and not
+ * refreshed after an exchange (:1399, 1405-1431); `accept` is never reset to .False. once it is .True. on a rank
+ * (declared at :1404, set :1483), so a later rejected pair on the same rank still reports the stale .True. to its partner
+ * -- with one overlap region per walker this cannot happen (a walker is matched at most once per call), kept anyway.
+ * Output: pairs[n][2] = (lower rank, upper rank) of the exchanges carried out, in order; returns n (<= P). */
+int orc_wl_replica_exchange(const double *energies, const double *lng, const int64_t *win, int W, int num_walkers,
+                            const double *edges, int bins, orc_mt *mts, int *pairs) {
+  const int P = W * num_walkers;
+  int *ibin = (int *)malloc(sizeof(int) * (size_t)P), *loc = (int *)malloc(sizeof(int) * (size_t)P);
+  int *lower = (int *)malloc(sizeof(int) * 2 * (size_t)num_walkers), *upper = (int *)malloc(sizeof(int) * 2 * (size_t)num_walkers);
+  int *exch = (int *)malloc(sizeof(int) * 2 * (size_t)num_walkers);
+  char *accept = (char *)calloc((size_t)P, 1);
+  for (int r = 0; r < P; r++) {
+    const int q = r / num_walkers + 1;                                      /* mpi_index */
+    const int ib = bin_index(energies[r], edges, bins);
+    ibin[r] = ib;
+    int lo = 0, up = 0;
+    if (q > 1) lo = (ib < win[2 * (q - 2) + 1] + 1) && (ib > win[2 * (q - 1)] - 1);          /* :1409-1413 */
+    if (q < W) up = (ib > win[2 * q] - 1) && (ib < win[2 * (q - 1) + 1] + 1);                /* :1415-1419 */
+    loc[r] = up ? q : (lo ? q - 1 : 0);                                     /* :1421-1427 */
+  }
+  int n = 0;
+  for (int i = 1; i <= W - 1; i++) {
+    for (int k = 0; k < num_walkers; k++) {
+      lower[2 * k] = (i - 1) * num_walkers + k; lower[2 * k + 1] = loc[(i - 1) * num_walkers + k];
+      upper[2 * k] = i * num_walkers + k; upper[2 * k + 1] = loc[i * num_walkers + k];
+      exch[2 * k] = exch[2 * k + 1] = -1;
+    }
+    shuffle_rows(lower, num_walkers, &mts[0]);
+    shuffle_rows(upper, num_walkers, &mts[0]);
+    int ei = 0;
+    for (int j = 0; j < num_walkers; j++) {                                 /* :1444-1462 */
+      if (lower[2 * j + 1] == 0) continue;
+      for (int k = 0; k < num_walkers; k++) {
+        if (upper[2 * k + 1] == 0) continue;
+        /* after a match lower(j,:) = 0, so the comparison below fails for the remaining k (upper rows with 0 are skipped) */
+        if (lower[2 * j + 1] == upper[2 * k + 1]) {
+          exch[2 * ei] = lower[2 * j]; exch[2 * ei + 1] = upper[2 * k]; ei++;
+          lower[2 * j] = lower[2 * j + 1] = 0; upper[2 * k] = upper[2 * k + 1] = 0;
+        }
+      }
+    }
+    int cnt = 0;
+    for (int j = 0; j < num_walkers; j++) if (exch[2 * j] > -1) cnt++;      /* COUNT(overlap_exchange(:,1) > -1) */
+    for (int j = 0; j < cnt; j++) {                                         /* :1470-1497 */
+      const int a = exch[2 * j], b = exch[2 * j + 1];
+      const int jb = bin_index(energies[b], edges, bins);
+      const double *la = lng + (size_t)a * bins;
+      if (orc_mt_genrand(&mts[a]) < exp(la[ibin[a] - 1] - la[jb - 1])) accept[a] = 1;        /* :1482-1483 */
+      if (accept[a]) { pairs[2 * n] = a; pairs[2 * n + 1] = b; n++; }
+    }
+  }
+  free(ibin); free(loc); free(lower); free(upper); free(exch); free(accept);
+  return n;
+}

@@ -177,6 +177,16 @@ class System:
                                   int(nbr_swap), C.byref(ef))
         return acc, ef.value
 
+    def wl_enter_energy_window(self, g, mt, conc, count, min_e, max_e, energy_min, energy_max, max_iters):
+        """enter_energy_window (src/wang-landau.F90:643-741), one walker -> (entered, e_final, loop iterations)."""
+        c = np.ascontiguousarray(conc, dtype=np.float64)
+        cnt = np.ascontiguousarray(count, dtype=np.int64)
+        ef, it = C.c_double(0.0), C.c_int64(0)
+        ok = lib().orc_wl_enter_energy_window(self.hp, _p(g), C.byref(mt), _p(c), _p(cnt), C.c_double(min_e), C.c_double(max_e),
+                                              C.c_float(energy_min), C.c_float(energy_max), C.c_int64(max_iters),
+                                              C.byref(ef), C.byref(it))
+        return bool(ok), ef.value, it.value
+
     def wl_bin_edges(self, energy_min, energy_max, bins):
         """create_energy_bins (src/wang-landau.F90:969-986); energies in meV/atom -> Ry/cell."""
         energy_to_ry = self.n_atoms / (RY_TO_EV * 1000)
@@ -247,3 +257,28 @@ def wl_window_optimise(it, intervals, mc_steps, diffusion_prev, bins):
     lib().orc_wl_window_optimise(C.c_int(it), C.c_int(iv.shape[0]), iv.ctypes.data_as(C.c_void_p),
                                  mc.ctypes.data_as(C.c_void_p), prev.ctypes.data_as(C.c_void_p), C.c_int(bins))
     return iv, prev
+
+
+def wl_dos_combine(lng_windows, window_indices):
+    """dos_combine (src/wang-landau.F90:1147-1194) -> combined ln g [bins]."""
+    lng = np.ascontiguousarray(lng_windows, dtype=np.float64)
+    win = np.ascontiguousarray(window_indices, dtype=np.int64)
+    out = np.zeros(lng.shape[1])
+    lib().orc_wl_dos_combine(lng.ctypes.data_as(C.c_void_p), win.ctypes.data_as(C.c_void_p), C.c_int(lng.shape[0]),
+                             C.c_int(lng.shape[1]), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def wl_replica_exchange(energies, lng_ranks, window_indices, num_walkers, edges, mts):
+    """replica_exchange (src/wang-landau.F90:1392-1519) for W*num_walkers ranks with their own MT streams
+    (`mts`: ctypes array of MT, advanced in place) -> [(lower rank, upper rank), ...] of the exchanges made."""
+    e = np.ascontiguousarray(energies, dtype=np.float64)
+    lng = np.ascontiguousarray(lng_ranks, dtype=np.float64)
+    win = np.ascontiguousarray(window_indices, dtype=np.int64)
+    ed = np.ascontiguousarray(edges, dtype=np.float64)
+    pairs = np.zeros((e.size, 2), dtype=np.int32)
+    lib().orc_wl_replica_exchange.restype = C.c_int
+    n = lib().orc_wl_replica_exchange(e.ctypes.data_as(C.c_void_p), lng.ctypes.data_as(C.c_void_p), win.ctypes.data_as(C.c_void_p),
+                                      C.c_int(win.shape[0]), C.c_int(num_walkers), ed.ctypes.data_as(C.c_void_p),
+                                      C.c_int(ed.size - 1), C.byref(mts), pairs.ctypes.data_as(C.c_void_p))
+    return [tuple(int(v) for v in row) for row in pairs[:n]]

@@ -93,3 +93,60 @@ def test_wang_landau_rho_of_E_on_gpu(orc, golden):
     assert np.array_equal(drv.dev.radial_densities(3, 3), sysm.radial_densities(g, 3, sysm.lattice_shells(g, 3)))
     like = np.array([np.trace(rho[b, 1]) for b in np.flatnonzero(n)])       # like-pair density in the first shell
     assert np.all(np.isfinite(like)) and abs(like[:5].mean() - like[-5:].mean()) > 1e-3     # SRO changes with E
+
+
+@pytest.mark.parametrize("n,lo_bin,hi_bin,max_iters", [(4, 200, 260, 60000), (4, 30, 60, 40000), (2, 1, 6, 12000)])
+def test_enter_energy_window_replay_matches_oracle(orc, golden, n, lo_bin, hi_bin, max_iters):
+    """enter_energy_window (wang-landau.F90:643-741) on the reference's MT19937 stream: the GPU replay kernel driven by the
+    host loop the header prescribes (exact-energy re-check on status 1, initial_setup on status 2) against the oracle's
+    restatement -- same exit, same iteration count, bit-identical running energy, configuration and MT state.  The
+    n = 2 case (16 atoms: re-randomisation every 4000 iterations, window below the reachable energies) crosses the
+    initial_setup branch with its stale running energy three times and stops at max_iters without entering."""
+    import brawl_b200
+    from brawl_b200 import wang_landau as wl
+    V = golden["t04_V"]
+    sysm = orc.System("bcc", n, n, n, 4, 6, V)
+    N = sysm.n_atoms
+    conc, cnt = sysm.quotas(conc=[0.25] * 4)
+    edges = wl.create_energy_bins(N, -96.0, 0.0, 512)
+    min_e, max_e = float(edges[lo_bin - 1]), float(edges[hi_bin])
+    # oracle
+    mt_o = orc.MT(rank=3)
+    g_o = sysm.initial_setup(mt_o, conc, cnt)
+    g0 = g_o.copy()
+    st0 = mt_o.state625().copy()
+    ok_o, e_o, it_o = sysm.wl_enter_energy_window(g_o, mt_o, conc, cnt, min_e, max_e, -96.0, 0.0, max_iters)
+    # GPU replay + the host loop
+    dev = brawl_b200.Device("bcc", n, n, n, 4, 6, V)
+    dev.set_config(g0)
+    mt_h = orc.MT(seed=1); mt_h.load625(st0)            # host copy of the stream for initial_setup (status 2)
+    st = st0.copy()
+    target, cond = (min_e + max_e) / 2.0, abs(max_e - min_e) * 0.1
+    sf = np.float32(0.0025) * np.float32(abs(np.float32(0.0) - np.float32(-96.0)))
+    sf = np.float32(sf * np.float32(N))
+    sigma = float(sf) / (13.605693122 * 1000.0)
+    e = float(dev.total_energy(exact_order=True)[0])
+    i_steps, it, resume, entered, n_rerand = 0, 0, 0, False, 0
+    while it < max_iters or resume:
+        status, e, i_steps, done = dev.wl_enter_window_replay(e, target, min_e + cond, max_e - cond, 2.0 * (sigma * sigma),
+                                                              N * 250, i_steps, max_iters - it, resume, st)
+        it += done
+        resume = 0
+        if status == 1:
+            e = float(dev.total_energy(exact_order=True)[0])                 # :692
+            if max_e - cond > e > min_e + cond:
+                entered = True
+                break
+        elif status == 2:                                                    # :677-680
+            mt_h.load625(st)
+            dev.set_config(sysm.initial_setup(mt_h, conc, cnt))
+            st = mt_h.state625().copy()
+            resume, n_rerand = 1, n_rerand + 1
+        else:
+            break
+    assert (entered, it) == (ok_o, it_o), (entered, it, ok_o, it_o)
+    assert e == e_o
+    assert np.array_equal(dev.get_config(), g_o)
+    assert np.array_equal(st, mt_o.state625())
+    if n == 2:
+        assert n_rerand >= 2 and not entered

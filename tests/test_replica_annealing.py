@@ -42,10 +42,10 @@ class _OracleChains:
 
 def _run(rank, world, golden, torch_device=None):
     from brawl_b200 import replica_annealing as ra
-    ra.Device = _OracleChains
     drv = ra.ReplicaAnnealing("bcc", 4, 4, 4, 4, 6, golden["t04_V"], [32] * 4, n_replicas=3, T=1500.0, T_steps=3, delta_T=-500.0,
                               n_mc_steps=2560, n_sample_steps=128, n_burn_in_steps=1280, burn_in_start=True, burn_in=True,
-                              n_sample_steps_asro=640, wc_range=3, device=rank, rank=rank, world=world, torch_device=torch_device)
+                              n_sample_steps_asro=640, wc_range=3, device=rank, rank=rank, world=world, torch_device=torch_device,
+                              device_cls=_OracleChains)
     return drv, drv.run()
 
 
