@@ -216,6 +216,8 @@ struct brawl_cuda_ctx {
   int word_epoch;              // steps per epoch of the count-caching kernels (epoch_metropolis.cuh): 8 (default), 4, or 0 = off
   int byte_layout;             // 1: never use the word-lattice kernels / dense decomposition (test hook, A/B comparisons)
   uint32_t *d_order;           // [n_replicas][S][n_sites] occupancy counts (store_state), allocated on first use
+  void *wl;                    // BrwWlState*: device-resident Wang-Landau ln g / histograms (wl_resident.inc)
+  void *comm;                  // BrwComm*: NCCL communicator of the multi-GPU drivers (wl_resident.inc)
 };
 
 int brw_fail(const char *fmt, ...);              // sets last error, returns 1

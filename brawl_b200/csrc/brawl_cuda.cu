@@ -139,6 +139,7 @@ extern "C" int brawl_cuda_create(int lattice, int n1, int n2, int n3, int S, int
   h->tune_box[0] = h->tune_box[1] = h->tune_box[2] = 0; h->tune_steps = 0;
   h->dE_mode = 2;
   h->word_split = 1;
+  h->wl = nullptr; h->comm = nullptr;
   h->word_epoch = 8;
 #define BRW_CREATE_CUDA(x) do { if (brw_cuda_check((x), #x)) { brawl_cuda_destroy(h); return 1; } } while (0)
   BRW_CREATE_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -163,10 +164,13 @@ static void brw_free_plan(BrwPlan *pl) {
   delete pl;
 }
 
+static void brw_wl_free(brawl_cuda_ctx *h);
+static void brw_comm_free(brawl_cuda_ctx *h);
 extern "C" int brawl_cuda_destroy(brawl_cuda_t *h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  brw_wl_free(h); brw_comm_free(h);
   cudaFree(h->d_lat); cudaFree(h->d_V); cudaFree(h->d_stage); cudaFree(h->d_scratch); cudaFree(h->d_flag);
   cudaFree(h->d_beta); cudaFree(h->d_small); cudaFree(h->d_order);
   brw_free_plan((BrwPlan *)h->mc_plan[0]); brw_free_plan((BrwPlan *)h->mc_plan[1]);
@@ -1418,3 +1422,5 @@ extern "C" int brawl_cuda_ns_walk(brawl_cuda_t *h, int n_walkers, const int32_t 
   if (n_accept) for (int w = 0; w < n_walkers; w++) n_accept[w] = (int64_t)acc[w];
   return 0;
 }
+
+#include "wl_resident.inc"

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_wl_walker_kernel(
     BrwGeom g, BrwWalkerLayout lay, const double *__restrict__ V, uint8_t *lat, double *lng, double *hist, double edge0,
     double range, int bins, const int *__restrict__ win_lo, const int *__restrict__ win_hi, int hist_stride, double wl_f,
     long n_trials, int hist_every, int nbr_swap, uint32_t k0, uint32_t k1, uint32_t off_lo, uint32_t off_hi,
-    int n_walkers, double *e_io, unsigned long long *n_accept) {
+    int n_walkers, double *e_io, unsigned long long *n_accept, int *bad_walker = nullptr) {
   __shared__ BrwWarpScratch scratch[BRW_WALKER_WARPS];
   extern __shared__ __align__(16) unsigned char dsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -249,6 +249,16 @@ __global__ void __launch_bounds__(32 * BRW_WALKER_WARPS) brw_wl_walker_kernel(
   if (!valid) return;
   double *g_lng = lng + (long)w * bins, *g_hist = hist + (long)w * hist_stride;
   const int lo = win_lo[w], hi = win_hi[w], nh = hi - lo + 1;
+  if (bad_walker) {
+    // device-resident callers cannot check the start energies on the host: a walker outside its window (the reference
+    // would index wl_logdos out of bounds) is reported through the flag and left untouched
+    const double e0 = e_io[w];
+    const int ib = brw_bin_index(e0, edge0, range, bins);
+    if (!(e0 == e0) || ib < lo || ib > hi) {
+      if (lane == 0) { atomicCAS(bad_walker, 0, w + 1); n_accept[w] = 0; }
+      return;
+    }
+  }
   double *my_lng = c.extra, *my_hist = c.extra + bins;
   for (int i = lane; i < bins; i += 32) my_lng[i] = g_lng[i];
   for (int i = lane; i < nh; i += 32) my_hist[i] = g_hist[i];

@@ -151,7 +151,8 @@ int brawl_cuda_metropolis_tune(brawl_cuda_t *h, int box_x, int box_y, int box_z,
  * instantiated it behaves like mode 1.  Where a word kernel exists, mode 0 runs its EXACT instantiation (same
  * decomposition, reference association for every trial), so modes 0 and 2 give identical trajectories; mode 1
  * keeps the byte-lattice decomposition.  The returned sum of accepted dE is exact to f64 rounding in modes 0/1
- * and to the fixed-point unit (~1e-11 Ry per accepted swap) in mode 2. */
+ * and to the fixed-point unit in mode 2 (epoch kernels: 22-bit table entries, < 2e-10 Ry per accepted swap; the
+ * decisions themselves are exact in every mode). */
 int brawl_cuda_metropolis_set_mode(brawl_cuda_t *h, int dE_mode);
 /* byte_layout_only: 0 (default) automatic; 1 never use the word-lattice kernels and their dense decomposition; 2 word
  * kernels, but without the two-warp-group split and the shared z margins (A/B comparisons, tests). */

@@ -372,15 +372,15 @@ def test_production_planner_variants(bw, orc, golden):
         e0 = dev.total_energy()[0]
         att, acc, dE = dev.metropolis_run(1.0 / (700.0 * bw.K_B_IN_RY), 6 * sysm.n_atoms)
         e1 = dev.total_energy()[0]
-        # the word kernel sums fixed-point dE (2^-k units, k ~ 37): bookkeeping to ~1e-8 instead of rounding
-        tol = 1e-7 if plan["use_box"] == 4 else 1e-10 * abs(e0) + 1e-12
+        # the word kernels sum fixed-point dE (epoch kernel: 22-bit table entries, < 2e-10 Ry per accepted swap)
+        tol = 2e-10 * float(acc[0]) if plan["use_box"] == 4 else 1e-10 * abs(e0) + 1e-12
         assert abs((e1 - e0) - dE[0]) < tol
         g1 = dev.get_config()
         assert dev.total_energy()[0] == sysm.total_energy(g1)
         assert np.array_equal(np.bincount(g1.ravel(), minlength=5), np.bincount(g.ravel(), minlength=5))
     assert plans[0]["use_box"] == 4 and plans[0]["P"] == (4, 4, 4) and plans[0]["n_orientations"] == 1
-    # default: 64x64x32 boxes at z pitch 28 (shared margin planes), two warp groups, 840 trials per step
-    assert (plans[0]["box_x"], plans[0]["box_y"], plans[0]["box_z"], plans[0]["trials_per_step"]) in ((64, 64, 28, 840), (64, 64, 32, 896))
+    # default: epoch kernel, 68x64x32 boxes at a pitch of 64x64x28 (shared margin planes in x and z), 32 warps x 30 lanes
+    assert (plans[0]["box_x"], plans[0]["box_y"], plans[0]["box_z"], plans[0]["trials_per_step"]) == (64, 64, 28, 960)
     assert plans[2]["P"] == (6, 6, 6) and plans[2]["n_orientations"] == 1
     assert plans[1]["P"][0] * plans[1]["P"][1] * plans[1]["P"][2] < 216 and plans[1]["n_orientations"] == 3
     assert plans[1]["trials_per_step"] > plans[2]["trials_per_step"]
@@ -520,13 +520,13 @@ def test_screened_kernel_trajectory_identical(bw, orc, golden, lattice, n, S, sh
         dev.set_config(g)
         out = dev.metropolis_run(1.0 / (T * bw.K_B_IN_RY), 12 * int(mask.sum()), seed=99)
         res[(byte_layout, mode)] = (dev.get_config().copy(), out, dev.total_energy()[0])
-    pairs = [((True, 0), (True, 1), 1e-9)] + ([((False, 0), (False, 2), 1e-6)] if word else [((True, 1), (False, 2), 1e-9)])
+    pairs = [((True, 0), (True, 1), 1e-9)] + ([((False, 0), (False, 2), 1e-4)] if word else [((True, 1), (False, 2), 1e-9)])
     for ka, kb, tol in pairs:
         a, b = res[ka], res[kb]
         assert np.array_equal(a[0], b[0])
         assert np.array_equal(a[1][0], b[1][0]) and np.array_equal(a[1][1], b[1][1])
         assert a[2] == b[2]
-        # sum of accepted dE: same to rounding (word kernel: fixed-point dE, ~1e-11 per accepted swap)
+        # sum of accepted dE: same to rounding (epoch kernel: fixed-point dE from a 22-bit table, < 2e-10 Ry per accepted swap)
         assert abs(a[1][2][0] - b[1][2][0]) < tol
 
 
@@ -782,7 +782,9 @@ def test_full_size_128_cubed_properties(bw, golden):
         assert att[0] >= 4 * N and 0 < acc[0] < att[0]
         assert np.array_equal(np.bincount(g1.ravel(), minlength=S + 1), np.bincount(g.ravel(), minlength=S + 1))
         assert np.array_equal(g1 == 0, g == 0)
-        assert abs((e1 - e0) - dE[0]) < 1e-9 * abs(e1 - e0) + 1e-9, (e0, e1, dE[0])
+        # sum of accepted dE of the screened epoch kernel: fixed-point from a 22-bit table, < 2e-10 Ry per accepted swap
+        # (the DECISIONS are exact; dE_mode 0 returns the sum to f64 rounding)
+        assert abs((e1 - e0) - dE[0]) < 2e-10 * float(acc[0]), (e0, e1, dE[0])
         finals.append((g1, att[0], acc[0], e1))
     assert np.array_equal(finals[0][0], finals[1][0]) and finals[0][1:] == finals[1][1:]
 
