@@ -168,6 +168,58 @@ def run_reference(args, rank, world):
         "gpu_launches": 0}))
 
 
+def wl_time_to_flatness(rank, world, local_rank, windows_per_gpu=8, walkers=16, tolerance=5e-5, seed=2024):
+    """BASELINE.json metric, second half: Wang-Landau time to the final ln g(E) on the reference's regression / example
+    shape (tests/04_parallel_wang-landau, examples/02: bcc n=4, 128 atoms, AlTiCrMo 6 shells, 512 bins in [-96, 0]
+    meV/atom, overlap 0.25, flatness 0.9, f 0.05 -> tolerance), energy windows sharded over the GPUs (8 per GPU), every
+    collective through the C ABI's NCCL communicator.  Checked against the reference's golden wl_dos.nc with its own
+    criterion (NRMSE < 1 %, tests/ci_test.py:42-50).  Returns a dict (rank 0) -- the `extra.wl` block."""
+    import torch
+    import torch.distributed as dist
+    from brawl_b200 import wang_landau as wl
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "brawl_golden.npz"))
+    p = wl.WLParams(mc_sweeps=100, bins=512, num_windows=windows_per_gpu * world, bin_overlap=0.25, tolerance=tolerance,
+                    flatness=0.90, wl_f=0.05, energy_min=-96, energy_max=0.0, performance=4)
+    uid = None
+    if world > 1:
+        import brawl_b200
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            probe = brawl_b200.Device("bcc", 4, 4, 4, 4, 6, gold["t04_V"], device=local_rank)
+            t.copy_(torch.from_numpy(probe.comm_unique_id()))
+        dist.broadcast(t, 0)
+        uid = t.cpu().numpy()
+    drv = wl.WangLandau("bcc", 4, 4, 4, 4, 6, gold["t04_V"], [32] * 4, p, walkers=walkers, device=local_rank, rank=rank,
+                        world=world, seed=seed, comm="abi" if world > 1 else "torch", unique_id=uid)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    lng = drv.run()
+    drv.dev.synchronize()
+    dt = time.perf_counter() - t0
+    trials = float(drv.total_trials)
+    timing = [dict(drv.timing)]
+    if world > 1:
+        tv = torch.tensor([drv.timing[k] for k in sorted(drv.timing)], dtype=torch.float64, device="cuda")
+        tl = [torch.empty_like(tv) for _ in range(world)]
+        dist.all_gather(tl, tv)
+        timing = [dict(zip(sorted(drv.timing), (round(float(x), 4) for x in t))) for t in tl]
+        v = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        c = torch.tensor([trials], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        dt, trials = float(v[0]), float(c[0])
+    ref = np.asarray(gold["t04_wl_dos"], dtype=np.float64)
+    err = float(np.sqrt(np.mean((ref - lng) ** 2)) / np.mean(np.abs(ref)))
+    return {"metric": "wl_seconds_to_final_lng", "value": dt, "unit": "s", "higher_is_better": False, "n_gpus": world,
+            "workload": "Wang-Landau bcc n=4 (128 atoms) AlTiCrMo 6 shells, 512 bins, f 0.05 -> %g, flatness 0.9, overlap 0.25" % tolerance,
+            "windows": p.num_windows, "walkers_per_window": walkers, "wl_trials": trials, "wl_trials_per_sec": trials / dt,
+            "sweeps_calls_per_stage": drv.stage_sweeps, "nrmse_vs_reference_golden": err, "pass_reference_criterion": err < 0.01,
+            "collectives": "C ABI NCCL (brawl_cuda_comm_*)" if world > 1 else "none (one GPU)",
+            "host_seconds_per_rank": timing}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,8 +236,12 @@ def main():
                     help="0 automatic (epoch kernel), 1 byte-lattice kernels only, 2 / 3 the one-gather-per-step word kernels "
                          "without / with the warp-group split (3 = the round-1 default), 4 / 5 other epoch lengths (A/B runs)")
     ap.add_argument("--n-cells", type=int, default=N_CELLS)
-    ap.add_argument("--workload", default="chain", choices=["chain", "replicas"],
-                    help="chain: BASELINE configs[1] (headline); replicas: configs[4], R x 32^3 bcc AlCrFeCoNi per GPU")
+    ap.add_argument("--workload", default="chain", choices=["chain", "replicas", "wl"],
+                    help="chain: BASELINE configs[1] (headline); replicas: configs[4], R x 32^3 bcc AlCrFeCoNi per GPU; "
+                         "wl: configs[2], Wang-Landau time to the final ln g only")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra.* blocks (WL time-to-flatness etc.)")
+    ap.add_argument("--wl-walkers", type=int, default=16)
+    ap.add_argument("--wl-windows-per-gpu", type=int, default=8)
     ap.add_argument("--replicas", type=int, default=1024)
     ap.add_argument("--dE-mode", type=int, default=2, choices=[0, 1, 2],
                     help="2 (library default): word-lattice kernel, integer-count screening with fixed-point dp4a dE, "
@@ -214,6 +270,14 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version line to stdout: keep stdout = one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if args.workload == "wl":
+        blk = wl_time_to_flatness(rank, world, local_rank, args.wl_windows_per_gpu, args.wl_walkers)
+        if rank == 0:
+            print(json.dumps(blk))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     n = args.n_cells
     R = 1

@@ -51,6 +51,21 @@ _SIGNATURES = {
     "brawl_cuda_lattice_ptr": [_vp, _vp, _vp],
     "brawl_cuda_swap_replicas": [_vp, _i, _i],
     "brawl_cuda_wl_window_average": [_vp, _vp, _i, _i, _i, _d],
+    "brawl_cuda_wl_init": [_vp, _i, _vp, _i],
+    "brawl_cuda_wl_set_windows": [_vp, _vp, _vp, _i],
+    "brawl_cuda_wl_zero_hist": [_vp],
+    "brawl_cuda_wl_set_lng": [_vp, _vp],
+    "brawl_cuda_wl_get": [_vp, _i, _vp],
+    "brawl_cuda_wl_iterate": [_vp, _d, _i64, _i, _u64, _u64, _vp, _vp, _vp, _vp],
+    "brawl_cuda_comm_unique_id": [_vp],
+    "brawl_cuda_comm_create": [_vp, _i, _i, _vp],
+    "brawl_cuda_comm_destroy": [_vp],
+    "brawl_cuda_comm_allgather": [_vp, _vp, _i, _vp],
+    "brawl_cuda_wl_allreduce": [_vp, _vp, _i],
+    "brawl_cuda_wl_allgather_lng": [_vp, _vp],
+    "brawl_cuda_exchange_replica": [_vp, _i, _i],
+    "brawl_cuda_exchange_replicas": [_vp, _i, _vp, _vp],
+    "brawl_cuda_swap_replicas_batch": [_vp, _i, _vp, _vp],
     "brawl_cuda_ns_walk_replay": [_vp, _i, _vp, _d, _i64, _vp, _vp],
     "brawl_cuda_ns_walk": [_vp, _i, _vp, _vp, _vp, _i64, _u64, _u64, _vp],
 }

@@ -31,6 +31,17 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def rank_seed(seed, rank):
+    """64-bit Philox key of a rank's Monte-Carlo kernels: the common seed for rank 0, a splitmix64 scramble of
+    (seed, rank) otherwise -- distinct streams per rank (replica ids in the counters are handle-local)."""
+    if rank == 0:
+        return int(seed) & 0xFFFFFFFFFFFFFFFF
+    z = (int(seed) + 0x9E3779B97F4A7C15 * int(rank)) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
 class Device:
     """One handle = `n_replicas` lattices resident in HBM on one GPU (C ABI object)."""
 
@@ -267,6 +278,82 @@ class Device:
                                                        int(period), C.byref(isteps), int(max_iters), int(resume),
                                                        _p(mt_state625), C.byref(e), C.byref(st), C.byref(it)))
         return st.value, e.value, isteps.value, it.value
+
+    # device-resident Wang-Landau state and the collectives of the multi-GPU drivers (include/brawl_cuda.h)
+    def wl_init(self, bins, bin_edges, walkers_per_window):
+        edges = np.ascontiguousarray(bin_edges, dtype=np.float64)
+        check(self.L.brawl_cuda_wl_init(self.h, int(bins), _p(edges), int(walkers_per_window)))
+        self._wl_bins, self._wl_windows = int(bins), self.n_replicas // int(walkers_per_window)
+
+    def wl_set_windows(self, win_lo, win_hi, zero_hist=True):
+        lo = np.ascontiguousarray(np.broadcast_to(win_lo, (self.n_replicas,)), dtype=np.int32)
+        hi = np.ascontiguousarray(np.broadcast_to(win_hi, (self.n_replicas,)), dtype=np.int32)
+        check(self.L.brawl_cuda_wl_set_windows(self.h, _p(lo), _p(hi), int(zero_hist)))
+
+    def wl_zero_hist(self):
+        check(self.L.brawl_cuda_wl_zero_hist(self.h))
+
+    def wl_set_lng(self, lng):
+        a = np.ascontiguousarray(lng, dtype=np.float64)
+        if a.size != self._wl_bins:
+            raise BrawlCudaError("ln g has %d entries, the state has %d bins" % (a.size, self._wl_bins))
+        check(self.L.brawl_cuda_wl_set_lng(self.h, _p(a)))
+
+    def wl_get(self, what=0):
+        """what = 0: ln g, 1: hist (entry i = bin win_lo + i) of every local window -> [n_windows][bins]"""
+        out = np.zeros((self._wl_windows, self._wl_bins))
+        check(self.L.brawl_cuda_wl_get(self.h, int(what), _p(out)))
+        return out
+
+    def wl_iterate(self, wl_f, n_trials, seed=0x42726157, offset=0, nbr_swap=False, want_accept=False):
+        """sweeps + window average + flatness inputs on the device -> (energies[W], hist_min[windows], hist_mean[windows])"""
+        e, mn, mean = np.zeros(self.n_replicas), np.zeros(self._wl_windows), np.zeros(self._wl_windows)
+        acc = np.zeros(self.n_replicas, dtype=np.int64) if want_accept else None
+        check(self.L.brawl_cuda_wl_iterate(self.h, wl_f, int(n_trials), int(nbr_swap), seed, offset, _p(e), _p(mn), _p(mean),
+                                           _p(acc) if want_accept else None))
+        return (e, mn, mean, acc) if want_accept else (e, mn, mean)
+
+    def comm_unique_id(self):
+        uid = np.zeros(128, dtype=np.uint8)
+        check(self.L.brawl_cuda_comm_unique_id(_p(uid)))
+        return uid
+
+    def comm_create(self, n_ranks, rank, unique_id):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        check(self.L.brawl_cuda_comm_create(self.h, int(n_ranks), int(rank), _p(uid)))
+        self._comm_ranks = int(n_ranks)
+
+    def comm_destroy(self):
+        check(self.L.brawl_cuda_comm_destroy(self.h))
+
+    def comm_allgather(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        out = np.zeros((self._comm_ranks, a.size))
+        check(self.L.brawl_cuda_comm_allgather(self.h, _p(a), a.size, _p(out)))
+        return out
+
+    def comm_allreduce(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64).copy()
+        check(self.L.brawl_cuda_wl_allreduce(self.h, _p(a), a.size))
+        return a
+
+    def wl_allgather_lng(self, n_ranks):
+        out = np.zeros((n_ranks * self._wl_windows, self._wl_bins))
+        check(self.L.brawl_cuda_wl_allgather_lng(self.h, _p(out)))
+        return out
+
+    def exchange_replica(self, replica, peer):
+        check(self.L.brawl_cuda_exchange_replica(self.h, int(replica), int(peer)))
+
+    def exchange_replicas(self, replicas, peers):
+        r = np.ascontiguousarray(replicas, dtype=np.int32)
+        q = np.ascontiguousarray(peers, dtype=np.int32)
+        check(self.L.brawl_cuda_exchange_replicas(self.h, r.size, _p(r), _p(q)))
+
+    def swap_replicas_batch(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        b = np.ascontiguousarray(b, dtype=np.int32)
+        check(self.L.brawl_cuda_swap_replicas_batch(self.h, a.size, _p(a), _p(b)))
 
     def swap_replicas(self, a, b):
         check(self.L.brawl_cuda_swap_replicas(self.h, a, b))

@@ -18,18 +18,7 @@ import math
 
 import numpy as np
 
-from .engine import Device, K_B_IN_RY, BrawlCudaError
-
-
-def rank_seed(seed, rank):
-    """64-bit Philox key of a rank's Monte-Carlo kernels: the common seed for rank 0, a splitmix64 scramble of
-    (seed, rank) otherwise -- distinct streams per rank (replica ids in the counters are handle-local)."""
-    if rank == 0:
-        return int(seed) & 0xFFFFFFFFFFFFFFFF
-    z = (int(seed) + 0x9E3779B97F4A7C15 * int(rank)) & 0xFFFFFFFFFFFFFFFF
-    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
-    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
-    return z ^ (z >> 31)
+from .engine import Device, K_B_IN_RY, BrawlCudaError, rank_seed
 
 
 def reduce_results(results, comm_all_gather, world):

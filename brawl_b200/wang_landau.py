@@ -25,7 +25,7 @@ import math
 
 import numpy as np
 
-from .engine import Device, RY_TO_EV, K_B_IN_RY, BrawlCudaError
+from .engine import Device, RY_TO_EV, K_B_IN_RY, BrawlCudaError, rank_seed
 
 
 def _f32(v):
@@ -305,7 +305,7 @@ from .netcdf3 import ncdf_writer_1d, ncdf_radial_density_writer_across_energy  #
 
 
 class _Comm:
-    """torch.distributed plumbing (world size 1 needs no torch at all)."""
+    """torch.distributed plumbing (world size 1 needs no torch at all): gloo in the CPU tests, NCCL on GPUs."""
 
     def __init__(self, rank=0, world=1, device=None):
         self.rank, self.world, self.device = rank, world, device
@@ -329,12 +329,37 @@ class _Comm:
         return float(self.all_gather(np.array([float(v)])).sum())
 
 
+class _AbiComm:
+    """The same collectives through the C ABI's own NCCL communicator (brawl_cuda_comm_*, include/brawl_cuda.h) -- the
+    calls a Fortran wl_main binds in place of its MPI ones.  `unique_id`: the 128 bytes rank 0 got from
+    Device.comm_unique_id(), already distributed by the caller."""
+    abi = True
+
+    def __init__(self, dev, rank, world, unique_id):
+        self.dev, self.rank, self.world = dev, rank, world
+        if world > 1:
+            dev.comm_create(world, rank, unique_id)
+
+    def all_gather(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if self.world == 1:
+            return a[None]
+        return self.dev.comm_allgather(a.ravel()).reshape((self.world,) + a.shape)
+
+    def all_sum(self, v):
+        if self.world == 1:
+            return float(v)
+        return float(self.dev.comm_allreduce(np.array([float(v)]))[0])
+
+
 class WangLandau:
-    """wl_main for the windows owned by this rank.  `dev` is created here: one handle with
-    (windows_per_rank * walkers) replicas."""
+    """wl_main for the windows owned by this rank.  `dev` is created here: one handle with (windows_per_rank * walkers)
+    replicas; ln g and the histograms of its walkers stay on the device (brawl_cuda_wl_init / wl_iterate), the host sees
+    8 bytes per walker and 16 per window per `sweeps` call.  comm = "torch" (torch.distributed: NCCL on GPUs, gloo in
+    the CPU tests) or "abi" (the C ABI's NCCL communicator; needs `unique_id`)."""
 
     def __init__(self, lattice, n_1, n_2, n_3, n_species, n_shells, V_ex, counts, params, walkers=8, device=0,
-                 rank=0, world=1, seed=0x42726157, torch_device=None, wc_range=0):
+                 rank=0, world=1, seed=0x42726157, torch_device=None, wc_range=0, comm="torch", unique_id=None):
         self.p, self.walkers, self.rank, self.world, self.seed = params, walkers, rank, world, seed
         W = params.num_windows
         if W % world:
@@ -348,18 +373,24 @@ class WangLandau:
         self.intervals = divide_range(params.bins, W)
         self.window_indices = create_overlap(self.intervals, params.bin_overlap)
         self.edges = create_energy_bins(self.n_atoms, params.energy_min, params.energy_max, params.bins)
-        self.comm = _Comm(rank, world, torch_device)
+        self.comm = _AbiComm(self.dev, rank, world, unique_id) if comm == "abi" else _Comm(rank, world, torch_device)
         self.rng_local = np.random.default_rng([seed, rank])
         self.rng_shared = np.random.default_rng([seed, 0xEC])   # identical on all ranks
+        # Philox key of this rank's Monte-Carlo kernels: the counters hold handle-local walker ids, so the rank goes into
+        # the key (start states take it in the offset, _rand_offset)
+        self.mc_seed = rank_seed(seed, rank)
         self.offset = 0
-        self.lng = np.zeros((self.n_local, params.bins))
-        self.hist = np.zeros((self.n_local, params.bins))
         q = np.repeat(np.arange(self.first_window, self.first_window + self.w_local), walkers)
         self.win_lo = self.window_indices[q, 0].astype(np.int32)
         self.win_hi = self.window_indices[q, 1].astype(np.int32)
+        self.dev.wl_init(params.bins, self.edges, walkers)
+        self.dev.wl_set_windows(self.win_lo, self.win_hi, zero_hist=True)
         self.energies = np.zeros(self.n_local)
+        self.hist_min, self.hist_mean = np.zeros(self.w_local), np.zeros(self.w_local)
         self.total_trials = 0
         self.stage_sweeps = []
+        self.timing = {"enter": 0.0, "sweeps": 0.0, "collectives": 0.0, "exchange": 0.0, "stitch": 0.0,
+                       "x_lng": 0.0, "x_plan": 0.0, "x_swap": 0.0}                                       # host seconds per part
         # load balancing (:1016-1019, 1079, 1108): trials each window spent unconverged, previous blend of weights
         self.wl_mc_steps = np.zeros(W)
         self.diffusion_prev = np.full(W, 1.0 / float(np.float32(W)))
@@ -374,6 +405,15 @@ class WangLandau:
         self.rho_sum = np.zeros((params.bins, max(self.wc_range, 1), n_species, n_species))
         self.rho_saved, self.radial_min, self.rho_of_E = False, 0.0, None
 
+    @property
+    def lng(self):
+        """ln g of every local walker [n_local][bins] (host copy; equal within a window after a `sweeps` call)."""
+        return np.repeat(self.dev.wl_get(0), self.walkers, axis=0)
+
+    @property
+    def hist(self):
+        return np.repeat(self.dev.wl_get(1), self.walkers, axis=0)
+
     def _set_windows(self, intervals):
         """mpi_arrays (:1351-1379): new overlapping index ranges for every walker of this rank."""
         self.intervals = np.array(intervals, dtype=np.int64)
@@ -381,7 +421,7 @@ class WangLandau:
         q = np.repeat(np.arange(self.first_window, self.first_window + self.w_local), self.walkers)
         self.win_lo = self.window_indices[q, 0].astype(np.int32)
         self.win_hi = self.window_indices[q, 1].astype(np.int32)
-        self.hist[...] = 0.0
+        self.dev.wl_set_windows(self.win_lo, self.win_hi, zero_hist=True)
         self.window_history.append(self.window_indices.copy())
 
     def _rand_offset(self):
@@ -394,18 +434,27 @@ class WangLandau:
     def enter_energy_windows(self, max_rounds=200, fresh=True):
         """fresh=False: start from the walkers' current configurations (after a window resize); walkers already
         inside their window leave the kernel at once."""
+        import time
+        t0 = time.perf_counter()
+        try:
+            return self._enter_energy_windows(max_rounds, fresh)
+        finally:
+            self.timing["enter"] += time.perf_counter() - t0
+
+    def _enter_energy_windows(self, max_rounds, fresh):
         p = self.p
         lo = self.edges[self.win_lo - 1]
         hi = self.edges[self.win_hi]
         target = (lo + hi) / 2.0
         cond = np.abs(hi - lo) * 0.1
-        sigma = _f32(0.0025) * abs(p.energy_max - p.energy_min) * self.n_atoms / (RY_TO_EV * 1000)
+        sigma = float(np.float32(np.float32(0.0025) * np.float32(abs(p.energy_max - p.energy_min))) * np.float32(self.n_atoms)) \
+            / (RY_TO_EV * 1000)                                # single-precision product, double division (:726-727)
         inv = 1.0 / (2.0 * sigma ** 2)
         pending = np.ones(self.n_local, dtype=bool)
         if fresh:                                              # start states generated on the device, all walkers at once
             self.dev.random_config(self.counts, 0, self.n_local, seed=self.seed, offset=self._rand_offset())
         for _ in range(max_rounds):
-            e, ent = self.dev.wl_enter_window(target, lo + cond, hi - cond, inv, self.n_atoms * 250, self.seed, self.offset)
+            e, ent = self.dev.wl_enter_window(target, lo + cond, hi - cond, inv, self.n_atoms * 250, self.mc_seed, self.offset)
             self.offset += 1
             pending = ent == 0
             if not pending.any():
@@ -418,33 +467,35 @@ class WangLandau:
 
     # --- one outer iteration: sweeps + window average + replica exchange -------------------------------
     def _sweeps(self, wl_f):
+        """sweeps (:539-626) for every local walker + the intra-window average (:628-631) + the flatness inputs, all on the
+        device; the host receives the walkers' energies and (min, mean) of each window's histogram."""
         p = self.p
         n_trials = p.mc_sweeps * self.n_atoms
-        acc, ef = self.dev.wl_sweeps(self.lng, self.hist, self.edges, self.win_lo, self.win_hi, wl_f, n_trials,
-                                     seed=self.seed, offset=self.offset, nbr_swap=p.nbr_swap)
+        self.energies, self.hist_min, self.hist_mean = self.dev.wl_iterate(wl_f, n_trials, seed=self.mc_seed, offset=self.offset,
+                                                                           nbr_swap=p.nbr_swap)
         self.offset += 1
         self.total_trials += n_trials * self.n_local
-        self.energies = ef
         if self.wc_range and not self.rho_saved:
             self._sample_rho()
-        # intra-window average (:628-631): all walkers of a window are on this GPU
-        w = self.walkers
-        for q in range(self.w_local):
-            self.lng[q * w:(q + 1) * w] = self.lng[q * w:(q + 1) * w].sum(axis=0) / float(np.float32(w))
-            self.hist[q * w:(q + 1) * w] = self.hist[q * w:(q + 1) * w].sum(axis=0) / float(np.float32(w))
 
     def _sample_rho(self):
         """Radial densities of the walkers' configurations, accumulated in the energy bin they sit in (:574-592).  The
         reference samples inside the trial loop, at most once per n_atoms trials and in the bin of the proposed
         configuration; here the configuration at the end of each `sweeps` call is sampled (same estimator -- the mean
-        of rho over configurations of a bin -- at a coarser cadence, one SRO kernel launch per sample).  Per walker and
+        of rho over configurations of a bin -- at a coarser cadence, ONE batched SRO launch per call).  Per walker and
         bin at most max(radial_samples / num_walkers, 1) samples, as in the reference."""
         cap = max(self.p.radial_samples // self.walkers, 1)
+        want = []
         for w in range(self.n_local):
             jb = bin_index(self.energies[w], self.edges, self.p.bins)
             if 0 < jb < self.p.bins + 1 and not self.radial_record_bool[jb - 1] and self.radial_record[w, jb - 1] < cap:
-                self.radial_record[w, jb - 1] += 1
-                self.rho_sum[jb - 1] += self.dev.radial_densities(self.wc_range, w)
+                want.append((w, jb))
+        if not want:
+            return
+        rho = self.dev.radial_densities_batch(self.wc_range, 0, self.n_local) if hasattr(self.dev, "radial_densities_batch") else None
+        for w, jb in want:
+            self.radial_record[w, jb - 1] += 1
+            self.rho_sum[jb - 1] += rho[w] if rho is not None else self.dev.radial_densities(self.wc_range, w)
 
     def _save_rho_E(self):
         """save_rho_E (:346-381): a bin is complete once radial_samples samples exist over all ranks; when every bin is,
@@ -468,49 +519,81 @@ class WangLandau:
         return tot / np.maximum(n, 1)[:, None, None, None], n.astype(np.int64)
 
     def _window_lng_all(self):
-        """lng per window for all windows (all-gather over ranks): [W][bins]."""
-        loc = self.lng[::self.walkers]
-        return self.comm.all_gather(loc).reshape(self.p.num_windows, self.p.bins)
+        """Window-averaged ln g of all windows of all ranks: [W][bins] (dos_combine's gather, :1161-1192)."""
+        if self.world > 1 and getattr(self.comm, "abi", False):
+            return self.dev.wl_allgather_lng(self.world).reshape(self.p.num_windows, self.p.bins)
+        return self.comm.all_gather(self.dev.wl_get(0)).reshape(self.p.num_windows, self.p.bins)
 
-    def _replica_exchange(self):
+    def _replica_exchange(self, e_all=None):
         if self.p.num_windows < 2 or self.p.performance not in (0, 2, 4):
             return 0
-        e_all = self.comm.all_gather(self.energies).reshape(-1)
+        import time
+        if e_all is None:
+            e_all = self.comm.all_gather(self.energies).reshape(-1)
+        t0 = time.perf_counter()
         lng_all = self._window_lng_all()
+        t1 = time.perf_counter()
         swaps = plan_replica_exchange(list(e_all), lng_all, self.window_indices, self.walkers, self.edges, self.rng_shared)
+        t2 = time.perf_counter()
+        try:
+            return self._do_swaps(swaps, e_all)
+        finally:
+            self.timing["x_lng"] += t1 - t0; self.timing["x_plan"] += t2 - t1; self.timing["x_swap"] += time.perf_counter() - t2
+
+    def _do_swaps(self, swaps, e_all):
+        """Carry out the accepted exchanges: same-GPU pairs in one launch, cross-GPU pairs in one NCCL group (a walker is
+        matched at most once per call, so the pairs are disjoint)."""
+        loc_a, loc_b, rem_r, rem_p = [], [], [], []
         for a, b in swaps:
             ra, rb = a // self.n_local, b // self.n_local
             la, lb = a % self.n_local, b % self.n_local
             if ra == rb == self.rank:
-                self.dev.swap_replicas(la, lb)
+                loc_a.append(la); loc_b.append(lb)
                 self.energies[la], self.energies[lb] = self.energies[lb], self.energies[la]
             elif self.rank in (ra, rb):
                 mine, peer = (la, rb) if self.rank == ra else (lb, ra)
-                self._exchange_remote(mine, peer)
+                rem_r.append(mine); rem_p.append(peer)
                 self.energies[mine] = e_all[b if self.rank == ra else a]
+        if loc_a:
+            if hasattr(self.dev, "swap_replicas_batch"):
+                self.dev.swap_replicas_batch(loc_a, loc_b)
+            else:
+                for la, lb in zip(loc_a, loc_b):
+                    self.dev.swap_replicas(la, lb)
+        if rem_r:
+            if getattr(self.comm, "abi", False):
+                self.dev.exchange_replicas(rem_r, rem_p)
+            else:
+                for mine, peer in zip(rem_r, rem_p):
+                    self._exchange_remote(mine, peer)
         return len(swaps)
 
     def _exchange_remote(self, local_replica, peer_rank):
         """Swap one configuration with a walker on another GPU: device-to-device over NCCL."""
+        if getattr(self.comm, "abi", False):
+            self.dev.exchange_replica(local_replica, peer_rank)          # grouped ncclSend/ncclRecv on the handle's stream
+            return
         torch, dist = self.comm.torch, self.comm.dist
+        # the library's kernels run on the handle's own stream, torch's copies on torch's: order the two explicitly
+        self.dev.synchronize()
         send = self.dev.lattice_tensor(torch)[local_replica].clone()
         recv = torch.empty_like(send)
         ops = [dist.P2POp(dist.isend, send, peer_rank), dist.P2POp(dist.irecv, recv, peer_rank)]
         for r in dist.batch_isend_irecv(ops):
             r.wait()
         self.dev.lattice_tensor(torch)[local_replica].copy_(recv)
+        if send.is_cuda:
+            torch.cuda.current_stream().synchronize()
 
     def _flat_windows(self, min_hist=None):
-        """flatness = minval(hist)/(sum(hist)/mpi_bins) > flatness per local window (:222-226)."""
+        """flatness = minval(hist)/(sum(hist)/mpi_bins) > flatness per local window (:222-226), from the device's
+        (min, mean) of the window-averaged histograms."""
         ok = []
         for q in range(self.w_local):
-            w0 = q * self.walkers
-            nb = self.win_hi[w0] - self.win_lo[w0] + 1
-            h = self.hist[w0, :nb]
-            flat = h.min() / (h.sum() / nb) if h.sum() > 0 else 0.0
-            good = flat > self.p.flatness
+            mn, mean = float(self.hist_min[q]), float(self.hist_mean[q])
+            good = (mn / mean if mean > 0 else 0.0) > self.p.flatness
             if min_hist is not None:
-                good = good and h.min() > min_hist
+                good = good and mn > min_hist
             ok.append(bool(good))
         return ok
 
@@ -518,23 +601,32 @@ class WangLandau:
         converged = [False] * self.w_local
         n = 0
         per_sweep = float(self.p.mc_sweeps * self.n_atoms * self.walkers)        # every walker adds its trials (:217, :775)
+        import time
         while True:
             n += 1
+            t0 = time.perf_counter()
             self._sweeps(wl_f)
+            t1 = time.perf_counter()
             for q in range(self.w_local):
                 if not converged[q]:
                     self.wl_mc_steps[self.first_window + q] += per_sweep
-            if n % exchange_every == 0:
-                self._replica_exchange()
             flat = self._flat_windows(min_hist)
             converged = [c or f for c, f in zip(converged, flat)]
-            if self.comm.all_sum(sum(converged)) == self.p.num_windows or n >= max_sweeps:
+            # one collective per iteration: walker energies (replica_exchange, :1435) + the converged count (:230)
+            both = self.comm.all_gather(np.concatenate([self.energies, [float(sum(converged))]]))
+            t2 = time.perf_counter()
+            if n % exchange_every == 0:
+                self._replica_exchange(both[:, :-1].reshape(-1))
+            t3 = time.perf_counter()
+            self.timing["sweeps"] += t1 - t0; self.timing["collectives"] += t2 - t1; self.timing["exchange"] += t3 - t2
+            if both[:, -1].sum() == self.p.num_windows or n >= max_sweeps:
                 break
         self.stage_sweeps.append(n)
-        self.hist[...] = 0.0
+        t4 = time.perf_counter()
         self._save_rho_E()
         combined = dos_combine(self._window_lng_all(), self.window_indices)      # dos_average + dos_combine
-        self.lng[...] = combined[None, :]
+        self.dev.wl_set_lng(combined)
+        self.dev.wl_zero_hist()
         steps = self.comm.all_gather(self.wl_mc_steps).sum(axis=0)               # MPI_ALLREDUCE(wl_mc_steps) (:244, :814)
         self.last_mc_steps = steps.copy()
         if resize and self.p.num_windows > 1:
@@ -543,6 +635,7 @@ class WangLandau:
             self._set_windows(iv)
         self.wl_mc_steps[...] = 0.0
         self.mean_energy = compute_mean_energy(combined, self.edges, self.p.bins, self.bin_width)
+        self.timing["stitch"] += time.perf_counter() - t4
         if resize and self.p.num_windows > 1:
             self.enter_energy_windows(fresh=False)                               # in place of load_window_config
         return combined

@@ -225,6 +225,48 @@ int brawl_cuda_swap_replicas(brawl_cuda_t *h, int a, int b);
 int brawl_cuda_wl_window_average(brawl_cuda_t *h, double *dev_array, int len, int walkers_per_window,
                                  int n_windows, double divisor);
 
+/* ---- Wang-Landau, device-resident ------------------------------------------------------------
+ * The walkers of a window live on one GPU: window q of this handle = replicas q*wpw .. q*wpw+wpw-1.  ln g[walker][bins]
+ * and hist[walker][bins] (hist[i] counts bin win_lo + i) stay in HBM between calls.
+ *   wl_init          allocate + zero the state (create_energy_bins' edges, :969-986)
+ *   wl_set_windows   mpi_start_idx / mpi_end_idx per walker (1-based, equal inside a window); zero_hist != 0 clears hist
+ *   wl_set_lng       every walker := lng[bins] (the MPI_BCAST that ends dos_combine, :1192)
+ *   wl_get           what = 0: ln g, 1: hist of each window (its first walker; equal after an iterate): out[n_windows][bins]
+ *   wl_iterate       one pass of the f-loop body (:214-226): sweeps for n_trials trials per walker (:539-626) from the
+ *                    exact total energy (:547), then the MPI_Allreduce + "/num_walkers" of ln g and hist over each window
+ *                    (:628-631) and the flatness inputs minval(hist), sum(hist)/mpi_bins per window (:222-226).  One host
+ *                    synchronisation; outputs (any may be NULL): energies[n_walkers], hist_min / hist_mean[n_windows],
+ *                    n_accept[n_walkers].  Fails if a walker enters with an energy outside its window. */
+int brawl_cuda_wl_init(brawl_cuda_t *h, int bins, const double *bin_edges, int walkers_per_window);
+int brawl_cuda_wl_set_windows(brawl_cuda_t *h, const int32_t *win_lo, const int32_t *win_hi, int zero_hist);
+int brawl_cuda_wl_zero_hist(brawl_cuda_t *h);
+int brawl_cuda_wl_set_lng(brawl_cuda_t *h, const double *lng);
+int brawl_cuda_wl_get(brawl_cuda_t *h, int what, double *out);
+int brawl_cuda_wl_iterate(brawl_cuda_t *h, double wl_f, int64_t n_trials, int nbr_swap, uint64_t seed, uint64_t offset,
+                          double *energies, double *hist_min, double *hist_mean, int64_t *n_accept);
+
+/* ---- collectives of the multi-GPU drivers (NCCL over NVLink; replaces the MPI calls of src/comms.F90 and
+ * src/wang-landau.F90 listed in SURVEY 2b) ----------------------------------------------------------
+ * One communicator per handle = per MPI rank / GPU.  Rank 0 obtains a 128-byte id (comm_unique_id) and hands it to the
+ * other ranks by whatever the host program has (MPI_Bcast in the Fortran drivers, a file in brawl_driver,
+ * torch.distributed in the Python drivers); every rank then calls comm_create.  NCCL is dlopen()ed on first use.
+ *   comm_allgather       recv[n_ranks][n] := send[n] of every rank (host buffers)       -- walker energies, :1435
+ *   wl_allreduce         buf[n] := sum over ranks (host buffer)                          -- converged flags :230, wl_mc_steps :244
+ *   wl_allgather_lng     lng_all[n_ranks*n_windows][bins] from device memory             -- dos_combine, :1161-1192
+ *   exchange_replica     swap a local configuration with one of rank `peer`, which makes the matching call
+ *                        (grouped ncclSend/ncclRecv of the compact lattice)              -- replica_exchange, :1485-1495 */
+int brawl_cuda_comm_unique_id(uint8_t *id128);
+int brawl_cuda_comm_create(brawl_cuda_t *h, int n_ranks, int rank, const uint8_t *id128);
+int brawl_cuda_comm_destroy(brawl_cuda_t *h);
+int brawl_cuda_comm_allgather(brawl_cuda_t *h, const double *send, int n, double *recv);
+int brawl_cuda_wl_allreduce(brawl_cuda_t *h, double *buf, int n);
+int brawl_cuda_wl_allgather_lng(brawl_cuda_t *h, double *lng_all);
+int brawl_cuda_exchange_replica(brawl_cuda_t *h, int replica, int peer);
+/* n exchanges in one NCCL group; both sides of every pair must list it at the same position among their common pairs */
+int brawl_cuda_exchange_replicas(brawl_cuda_t *h, int n, const int32_t *replica, const int32_t *peer);
+/* all same-GPU swaps of one replica_exchange call in one launch: replicas a[i] <-> b[i], pairs disjoint */
+int brawl_cuda_swap_replicas_batch(brawl_cuda_t *h, int n_pairs, const int32_t *a, const int32_t *b);
+
 /* ---- nested sampling ------------------------------------------------------------------------
  * The constrained random walk of nested_sampling.f90:157-192 for a batch of walkers: walker w
  * (replica walker_ids[w]) with running energy energies[w] takes n_steps steps (site 2 redrawn

@@ -198,15 +198,48 @@ class _OracleDevice:
         self.g[a][...] = self.g[b]
         self.g[b][...] = t
 
-    def wl_sweeps(self, lng, hist, edges, win_lo, win_hi, wl_f, n_trials, seed=0, offset=0, nbr_swap=False):
-        acc, ef = np.zeros(len(self.g), dtype=np.int64), np.zeros(len(self.g))
-        for w in range(len(self.g)):
-            nb = int(win_hi[w] - win_lo[w] + 1)
-            h = np.ascontiguousarray(hist[w, :nb])
-            acc[w], ef[w] = self.sys.wl_sweeps(self.g[w], self.mt[w], lng[w], h, np.asarray(edges), win_lo[w], win_hi[w],
-                                               wl_f, n_trials, nbr_swap)
-            hist[w, :nb] = h
-        return acc, ef
+    # device-resident Wang-Landau state of the product handle (brawl_cuda_wl_init / wl_iterate), kept in numpy here
+    def wl_init(self, bins, bin_edges, walkers_per_window):
+        n = len(self.g)
+        self.bins, self.wpw, self.edges = bins, walkers_per_window, np.asarray(bin_edges, dtype=np.float64)
+        self.lngs, self.hists = np.zeros((n, bins)), np.zeros((n, bins))
+        self.lo, self.hi = np.ones(n, dtype=np.int32), np.full(n, bins, dtype=np.int32)
+
+    def wl_set_windows(self, win_lo, win_hi, zero_hist=True):
+        self.lo, self.hi = np.array(win_lo, dtype=np.int32), np.array(win_hi, dtype=np.int32)
+        if zero_hist:
+            self.hists[...] = 0.0
+
+    def wl_zero_hist(self):
+        self.hists[...] = 0.0
+
+    def wl_set_lng(self, lng):
+        self.lngs[...] = np.asarray(lng)[None, :]
+
+    def wl_get(self, what=0):
+        return (self.hists if what else self.lngs)[::self.wpw].copy()
+
+    def synchronize(self):
+        pass
+
+    def wl_iterate(self, wl_f, n_trials, seed=0, offset=0, nbr_swap=False):
+        n = len(self.g)
+        ef = np.zeros(n)
+        for w in range(n):
+            nb = int(self.hi[w] - self.lo[w] + 1)
+            h = np.ascontiguousarray(self.hists[w, :nb])
+            _, ef[w] = self.sys.wl_sweeps(self.g[w], self.mt[w], self.lngs[w], h, self.edges, self.lo[w], self.hi[w],
+                                          wl_f, n_trials, nbr_swap)
+            self.hists[w, :nb] = h
+        nq = n // self.wpw
+        mn, mean = np.zeros(nq), np.zeros(nq)
+        for q in range(nq):                      # the intra-window average (:628-631) and the flatness inputs (:222-226)
+            sl = slice(q * self.wpw, (q + 1) * self.wpw)
+            self.lngs[sl] = self.lngs[sl].sum(axis=0) / float(np.float32(self.wpw))
+            self.hists[sl] = self.hists[sl].sum(axis=0) / float(np.float32(self.wpw))
+            nb = int(self.hi[q * self.wpw] - self.lo[q * self.wpw] + 1)
+            mn[q], mean[q] = self.hists[q * self.wpw, :nb].min(), self.hists[q * self.wpw, :nb].sum() / nb
+        return ef, mn, mean
 
     def wl_enter_window(self, target, lo_e, hi_e, inv_two_sigma_sq, max_trials, seed=0, offset=0):
         e_out, ent = np.zeros(len(self.g)), np.zeros(len(self.g), dtype=np.int32)
@@ -325,7 +358,7 @@ def _gloo_driver_worker(rank, world, port, q):
                         world=world, seed=5)
     swaps = []
     orig = drv._replica_exchange
-    drv._replica_exchange = lambda: swaps.append(orig()) or swaps[-1]
+    drv._replica_exchange = lambda *a: swaps.append(orig(*a)) or swaps[-1]
     lng = drv.run(max_sweeps_per_stage=400)
     e = np.array([drv.dev.sys.total_energy(g) for g in drv.dev.g])
     lo, hi = drv.edges[drv.win_lo - 1], drv.edges[drv.win_hi]

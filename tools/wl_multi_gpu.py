@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--tolerance", type=float, default=5e-5)
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--out", default=None, help="directory for data/wl_dos.nc, wl_dos_bins.nc, wl_hist.nc (the reference's files)")
+    ap.add_argument("--comm", default="abi", choices=["abi", "torch"],
+                    help="collectives through the C ABI's NCCL communicator (brawl_cuda_comm_*) or torch.distributed")
     ap.add_argument("--performance", type=int, default=4,
                     help="the reference's switch: 0/1 resize windows every f-stage, 2/3 after pre-sampling only, 4 static")
     args = ap.parse_args()
@@ -44,8 +46,16 @@ def main():
     gold = np.load(os.path.join(ROOT, "tests", "golden", "brawl_golden.npz"))
     p = wl.WLParams(mc_sweeps=100, bins=512, num_windows=args.windows, bin_overlap=args.overlap, tolerance=args.tolerance,
                     flatness=0.90, wl_f=0.05, energy_min=-96, energy_max=0.0, performance=args.performance)
+    uid = None
+    if world > 1 and args.comm == "abi":                        # rank 0's NCCL id reaches the others through torch's broadcast
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t.copy_(torch.from_numpy(brawl_b200.Device("bcc", 4, 4, 4, 4, 6, gold["t04_V"], device=local).comm_unique_id()))
+        dist.broadcast(t, 0)
+        uid = t.cpu().numpy()
     drv = wl.WangLandau("bcc", 4, 4, 4, 4, 6, gold["t04_V"], [32] * 4, p, walkers=args.walkers, device=local, rank=rank,
-                        world=world, seed=args.seed, torch_device=torch.device("cuda", local))
+                        world=world, seed=args.seed, torch_device=torch.device("cuda", local),
+                        comm=args.comm if world > 1 else "torch", unique_id=uid)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -62,7 +72,7 @@ def main():
         ref = np.asarray(gold["t04_wl_dos"], dtype=np.float64)
         err = float(np.sqrt(np.mean((ref - lng) ** 2)) / np.mean(np.abs(ref)))
         print(json.dumps({"workload": "WL bcc n=4 4 species 6 shells 512 bins", "n_gpus": world, "windows": args.windows,
-                          "walkers_per_window": args.walkers, "performance": args.performance,
+                          "walkers_per_window": args.walkers, "performance": args.performance, "comm": args.comm if world > 1 else "none",
                           "final_window_widths": (drv.window_indices[:, 1] - drv.window_indices[:, 0] + 1).tolist(),
                           "seconds_to_final_lng": dt, "wl_trials": trials,
                           "wl_trials_per_sec": trials / dt, "sweeps_calls_per_stage": drv.stage_sweeps,
