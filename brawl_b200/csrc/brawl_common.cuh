@@ -213,7 +213,7 @@ struct brawl_cuda_ctx {
   int tune_box[3], tune_steps, disable_fast, cubic_period_only, last_launches;
   int dE_mode;                 // 0: reference association for every trial; 1: screened, byte lattice; 2: screened, word lattice (default)
   int word_split;              // 1 (default): the planner may pick the two-warp-group (SPLIT) word kernels
-  int word_epoch;              // steps per epoch of the count-caching kernels (epoch_metropolis.cuh): 8 (default), 4, or 0 = off
+  int word_epoch;              // steps per epoch of the site-energy-caching kernels (epoch_metropolis.cuh): 4 (default), 8, 2, or 0 = off
   int byte_layout;             // 1: never use the word-lattice kernels / dense decomposition (test hook, A/B comparisons)
   uint32_t *d_order;           // [n_replicas][S][n_sites] occupancy counts (store_state), allocated on first use
   void *wl;                    // BrwWlState*: device-resident Wang-Landau ln g / histograms (wl_resident.inc)

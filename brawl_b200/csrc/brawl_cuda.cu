@@ -140,7 +140,7 @@ extern "C" int brawl_cuda_create(int lattice, int n1, int n2, int n3, int S, int
   h->dE_mode = 2;
   h->word_split = 1;
   h->wl = nullptr; h->comm = nullptr;
-  h->word_epoch = 8;
+  h->word_epoch = 4;
 #define BRW_CREATE_CUDA(x) do { if (brw_cuda_check((x), #x)) { brawl_cuda_destroy(h); return 1; } } while (0)
   BRW_CREATE_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
@@ -965,8 +965,9 @@ extern "C" int brawl_cuda_metropolis_set_layout(brawl_cuda_t *h, int byte_layout
   BRW_CUDA(cudaStreamSynchronize(h->stream));
   h->byte_layout = byte_layout_only == 1;
   h->word_split = byte_layout_only == 2 ? 0 : 1;      // 2: word kernels without the two-warp-group split
-  // 2, 3: the one-gather-per-step word kernels (3: with the two-warp-group split, the round-1 default); 4: epochs of 4
-  h->word_epoch = byte_layout_only == 2 || byte_layout_only == 3 ? 0 : byte_layout_only == 4 ? 4 : byte_layout_only == 5 ? 2 : 8;
+  // 2, 3: the one-gather-per-step word kernels (3: with the two-warp-group split, the round-1 default); 0: epochs of 4
+  // steps (default), 4: epochs of 8, 5: epochs of 2
+  h->word_epoch = byte_layout_only == 2 || byte_layout_only == 3 ? 0 : byte_layout_only == 4 ? 8 : byte_layout_only == 5 ? 2 : 4;
   for (int i = 0; i < 2; i++) { brw_free_plan((BrwPlan *)h->mc_plan[i]); h->mc_plan[i] = nullptr; }
   return 0;
 }

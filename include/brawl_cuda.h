@@ -154,8 +154,11 @@ int brawl_cuda_metropolis_tune(brawl_cuda_t *h, int box_x, int box_y, int box_z,
  * and to the fixed-point unit in mode 2 (epoch kernels: 22-bit table entries, < 2e-10 Ry per accepted swap; the
  * decisions themselves are exact in every mode). */
 int brawl_cuda_metropolis_set_mode(brawl_cuda_t *h, int dE_mode);
-/* byte_layout_only: 0 (default) automatic; 1 never use the word-lattice kernels and their dense decomposition; 2 word
- * kernels, but without the two-warp-group split and the shared z margins (A/B comparisons, tests). */
+/* byte_layout_only: 0 (default) automatic: where instantiated (bcc, 4 shells, <= 5 species) the epoch kernel with the site
+ * energies cached over epochs of 4 steps (epoch_metropolis.cuh); 4 / 5: the same kernel with epochs of 8 / 2 steps (more
+ * attempts per second, fewer of them effective / the reverse: DESIGN.md 4.3); 3: the one-gather-per-step word kernel with two
+ * warp groups (the round-1 default), 2: without the split and the shared z margins; 1: never use the word-lattice kernels and
+ * their dense decomposition (A/B comparisons, tests). */
 int brawl_cuda_metropolis_set_layout(brawl_cuda_t *h, int byte_layout_only);
 /* Describe the decomposition chosen: out10 = { kind + 16*n_orientations, period Px*10000+Py*100+Pz of the
  * first orientation, margin, box_x, box_y, box_z, max trials per step, boxes per replica, |D| (allowed

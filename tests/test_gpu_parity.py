@@ -894,3 +894,94 @@ def test_radial_counts_batch_matches_single(bw, orc, golden):
         assert np.array_equal(dev.radial_densities_batch(4, 2, 3), rho[2:5])
         with pytest.raises(bw.BrawlCudaError):
             dev.radial_densities_batch(4, R - 1, 2)
+
+
+@pytest.mark.parametrize("S,key,T", [(4, "ex_AlTiCrMo_V", 1000.0), (5, "ex_AlCrFeCoNi_V", 800.0)])
+def test_epoch_kernel_statistics_match_oracle(bw, orc, golden, S, key, T):
+    """The headline kernel (epoch kernel: dense non-interacting sets, site energies cached over 4 steps, use_box == 4)
+    against the oracle's sequential reference sampler, directly, at the bench temperature: energy per atom, heat capacity
+    and the Warren-Cowley parameters alpha = 1 - rho/(Z c) (examples/01_metropolis_FeNi/02_simulated_annealing/
+    01_plot_results.py:35-36) of shells 1 and 2.  bcc 32^3 (65 536 atoms).  Six GPU replicas are equilibrated for 4000
+    sweeps; every equilibrated configuration then starts one oracle chain (own MT stream) AND the continuation of its GPU
+    replica: 30 sweeps discarded, 120 sweeps sampled every 5.  Both samplers leave the Boltzmann distribution invariant,
+    so the averages of a pair must agree within the blocked statistical errors (blocks of 4 samples = 20 sweeps, 6 per
+    chain; pairing removes the slow replica-to-replica differences of the ordered state): the mean pair difference must
+    be below 6 standard errors (5 sigma + 1 sigma slack, no other tolerance)."""
+    import threading
+    V = golden[key][: S * S * 4]
+    n, R = 32, 6
+    sysm = orc.System("bcc", n, n, n, S, 4, V)
+    N = sysm.n_atoms
+    beta = 1.0 / (T * bw.K_B_IN_RY)
+    dev = bw.Device("bcc", n, n, n, S, 4, V, n_replicas=R)
+    assert dev.metropolis_plan()["use_box"] == 4 and dev.metropolis_plan()["trials_per_step"] == 960
+    starts = []
+    for r in range(R):
+        rng = np.random.default_rng(40 + r)
+        spec = np.repeat(np.arange(1, S + 1, dtype=np.int8), -(-N // S))[:N]
+        rng.shuffle(spec)
+        g = np.zeros((2 * n,) * 3, dtype=np.int8)
+        par = np.arange(2 * n) & 1
+        g[(par[None, None, :] == par[:, None, None]) & (par[None, :, None] == par[:, None, None])] = spec
+        starts.append(g)
+    dev.set_config(np.stack(starts))
+    dev.metropolis_run(beta, 4000 * N, seed=77)
+    eq = dev.get_config(0, R).copy()
+    conc = np.bincount(starts[0].ravel(), minlength=S + 1)[1:] / float(N)
+    Z = np.array([8.0, 6.0])
+    BS = 4                                                                      # samples per block
+
+    def observables(e_series, rho_series):
+        """one chain: samples of E/N [m], rho [m][2][S][S] -> per block (E/N, C_V per atom, alpha[2][S][S])"""
+        e = np.asarray(e_series); rho = np.asarray(rho_series)
+        nb = e.size // BS
+        eb = e[: nb * BS].reshape(nb, BS)
+        alpha = 1.0 - rho[: nb * BS].reshape(nb, BS, 2, S, S).mean(axis=1) / (Z[None, :, None, None] * conc[None, None, :, None])
+        cv = (eb * N).var(axis=1, ddof=1) / (bw.K_B_IN_RY * T * T) / N        # (<E^2> - <E>^2) / (k_B T^2) per atom
+        return eb.mean(axis=1), cv, alpha
+
+    orc_out = [None] * R
+    def chain(c):                                                               # threads: ctypes releases the GIL
+        g = eq[c].copy()
+        mt = orc.MT(seed=3100 + c)
+        sysm.metropolis_trials(g, mt, beta, 30 * N)
+        es, rs = [], []
+        shells = sysm.lattice_shells(g, 3)
+        for _ in range(24):
+            sysm.metropolis_trials(g, mt, beta, 5 * N)
+            es.append(sysm.total_energy(g) / N)
+            rs.append(sysm.radial_densities(g, 3, shells)[1:3])
+        orc_out[c] = observables(es, rs)
+    ths = [threading.Thread(target=chain, args=(c,)) for c in range(R)]
+    for t in ths:
+        t.start()
+    dev.metropolis_run(beta, 30 * N, seed=78)                                   # the GPU replicas meanwhile
+    es, rs = [[] for _ in range(R)], [[] for _ in range(R)]
+    for k in range(24):
+        dev.metropolis_run(beta, 5 * N, seed=100 + k)
+        e = dev.total_energy(0, R, exact_order=False) / N
+        rho = dev.radial_densities_batch(3, 0, R)
+        for r in range(R):
+            es[r].append(e[r]); rs[r].append(rho[r, 1:3])
+    gpu_out = [observables(es[r], rs[r]) for r in range(R)]
+    for t in ths:
+        t.join()
+
+    worst, report = 0.0, []
+    for i, name in enumerate(("E/N", "C_V", "alpha")):
+        d = np.mean([gpu_out[c][i].mean(axis=0) - orc_out[c][i].mean(axis=0) for c in range(R)], axis=0)
+        var = sum(gpu_out[c][i].var(axis=0, ddof=1) / gpu_out[c][i].shape[0] + orc_out[c][i].var(axis=0, ddof=1) / orc_out[c][i].shape[0]
+                  for c in range(R)) / R ** 2
+        se = np.sqrt(var)
+        assert np.all(se > 0)
+        z = np.abs(d) / se
+        worst = max(worst, float(np.max(z)))
+        report.append((name, np.max(np.abs(d)), np.max(se)))
+        assert np.all(z < 6.0), (name, d, se, z)
+    # the comparison has teeth: the errors are a small fraction of the signal
+    e_mean = np.mean([o[0].mean() for o in orc_out])
+    a_mean = np.mean([o[2].mean(axis=0) for o in orc_out], axis=0)
+    assert report[0][2] < 5e-3 * abs(e_mean), (report, e_mean)
+    assert np.max(np.abs(a_mean)) > 20 * report[2][2], (report, a_mean)        # SRO is resolved, not noise
+    print("epoch kernel vs oracle, S=%d T=%g: <E>/N = %.7f, max |diff| / max se: %s, worst |z| = %.2f"
+          % (S, T, e_mean, ["%s %.2e / %.2e" % r for r in report], worst))

@@ -21,7 +21,7 @@ from oracle import oracle as orc             # noqa: E402  (checker only)
 
 gold = np.load(os.path.join(ROOT, "tests", "golden", "brawl_golden.npz"))
 V4 = np.ascontiguousarray(gold["ex_AlTiCrMo_V"][:64])
-LAYOUTS = {"word_split(r01)": 3, "epoch2": 5, "epoch4": 4, "epoch8": 0}
+LAYOUTS = {"word_split(r01)": 3, "epoch2": 5, "epoch4": 0, "epoch8": 4}
 
 
 def rand_config(n, S, seed):

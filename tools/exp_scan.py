@@ -94,7 +94,7 @@ if __name__ == "__main__":
     out(test="oracle_curve", sweeps=ox.tolist(), e=oe.tolist(), se=ose.tolist())
     targets = {m: float(oe[m]) for m in REF_MARKS}
     configs = [("word_split(r01)", 3, s) for s in (0, 60)]
-    for name, lay in (("epoch2", 5), ("epoch4", 4), ("epoch8", 0)):
+    for name, lay in (("epoch2", 5), ("epoch4", 0), ("epoch8", 4)):
         configs += [(name, lay, s) for s in ((0, 104, 64, 32) if len(sys.argv) < 2 else (0, 104))]
     for name, lay, steps in configs:
         rate, sp, launches = throughput(lay, steps)
