@@ -31,6 +31,7 @@ _SIGNATURES = {
     "brawl_cuda_get_order": [_vp, _i, _vp, _i],
     "brawl_cuda_total_energy": [_vp, _i, _i, _i, _vp],
     "brawl_cuda_site_energies": [_vp, _i, _vp],
+    "brawl_cuda_nbr_energy": [_vp, _i, _i, _i, _i, _i, _vp],
     "brawl_cuda_pair_dE": [_vp, _i, _i64, _vp, _vp, _vp],
     "brawl_cuda_metropolis_replay": [_vp, _i, _d, _i64, _i, _vp, _vp],
     "brawl_cuda_metropolis_replay_sampled": [_vp, _i, _d, _i64, _i64, _i, _vp, _vp, _vp],

@@ -461,6 +461,29 @@ extern "C" int brawl_cuda_site_energies(brawl_cuda_t *h, int replica, double *ou
   BRW_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
 }
+// setup%nbr_energy(config, 1, i, j, k) for one site, optionally with another species on it (the operator takes the species
+// of the centre as an argument, src/bw_hamiltonian.f90:898-1262): species = 0 uses the occupant
+__global__ void brw_one_site_energy_kernel(BrwGeom g, const double *__restrict__ V, const uint8_t *__restrict__ lat, int x, int y,
+                                           int z, int species, double *out) {
+  const int c = brw_grid_to_compact(g, x, y, z);
+  *out = brw_site_energy(g, V, x, y, z, species > 0 ? species - 1 : lat[c], BrwPlainSpec{lat});
+}
+extern "C" int brawl_cuda_nbr_energy(brawl_cuda_t *h, int replica, int x, int y, int z, int species, double *energy) {
+  BRW_ENTER(h);
+  BRW_REPLICA(h, replica);
+  if (!energy) return brw_fail("null output pointer");
+  const BrwGeom &g = h->g;
+  if (x < 0 || y < 0 || z < 0 || x >= g.gx || y >= g.gy || z >= g.gz) return brw_fail("site (%d,%d,%d) outside the %dx%dx%d grid", x, y, z, g.gx, g.gy, g.gz);
+  const bool on = g.lattice == 0 ? true : g.lattice == 1 ? ((x & 1) == (z & 1) && (y & 1) == (z & 1)) : (((x + y + z) & 1) == 0);
+  if (!on) return brw_fail("(%d,%d,%d) is not a lattice site", x, y, z);
+  if (species < 0 || species > g.S) return brw_fail("species %d out of 0..%d", species, g.S);
+  if (brw_small(h, sizeof(double))) return 1;
+  brw_one_site_energy_kernel<<<1, 1, 0, h->stream>>>(g, h->d_V, h->d_lat + (size_t)replica * g.n_sites, x, y, z, species, (double *)h->d_small);
+  BRW_LAUNCH_CHECK("brw_one_site_energy_kernel");
+  BRW_CUDA(cudaMemcpyAsync(energy, h->d_small, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
 extern "C" int brawl_cuda_pair_dE(brawl_cuda_t *h, int replica, int64_t n, const int32_t *i1, const int32_t *i2, double *dE) {
   BRW_ENTER(h);
   BRW_REPLICA(h, replica);

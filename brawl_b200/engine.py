@@ -128,6 +128,12 @@ class Device:
         check(self.L.brawl_cuda_site_energies(self.h, replica, _p(out)))
         return out
 
+    def nbr_energy(self, x, y, z, species=0, replica=0):
+        """setup%nbr_energy for the 0-based grid site (x, y, z); species > 0 overrides the centre species."""
+        e = C.c_double()
+        check(self.L.brawl_cuda_nbr_energy(self.h, replica, int(x), int(y), int(z), int(species), C.byref(e)))
+        return e.value
+
     def pair_dE(self, idx1, idx2, replica=0):
         i1 = np.ascontiguousarray(idx1, dtype=np.int32)
         i2 = np.ascontiguousarray(idx2, dtype=np.int32)
@@ -402,7 +408,7 @@ class RunParams:
         if site_b != 1:
             raise BrawlCudaError("n_basis is 1 for every supported lattice")
         self.dev.set_config(config)
-        return float(self.dev.site_energies()[site_k - 1, site_j - 1, site_i - 1])
+        return self.dev.nbr_energy(site_i - 1, site_j - 1, site_k - 1)
 
     def _flat(self, idx):
         b, i, j, k = idx

@@ -1,9 +1,11 @@
 // brawl_driver -- Fortran-free equivalent of `brawl.run` (src/main.F90:10-177) for the swap hot path:
 // reads the reference's own input files from the current directory and writes its output files, with
 // every trial / energy / pair count on the GPU (libbrawl_cuda.so).
-//   brawl_driver [input=brawl.inp] [metropolis=metropolis.inp] [rng=mt19937|philox] [ranks=N] [device=D] [seed=S]
+//   brawl_driver [input=brawl.inp] [metropolis=metropolis.inp] [wl=wl_input.inp] [rng=mt19937|philox] [ranks=N] [gpus=G]
+//                [device=D] [seed=S]
 // rng=mt19937 (default) replays the reference's MT19937 stream: outputs are the reference's, bit for bit.
-// ranks=N emulates `mpirun -np N` (independent replicas, seeds 110179+11*rank, proc_000r_* + av_* files).
+// ranks=N emulates `mpirun -np N` (independent replicas, seeds 110179+11*rank, proc_000r_* + av_* files; Wang-Landau:
+// N walkers = N / num_windows per window, sharded with gpus=G over G processes / GPUs that talk NCCL through the C ABI).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -12,7 +14,7 @@
 #include "brawl_host.hpp"
 
 int main(int argc, char **argv) {
-  std::string input = "brawl.inp", metro = "metropolis.inp";
+  std::string input = "brawl.inp", metro = "metropolis.inp", wl = "wl_input.inp";
   brawl::DriverOptions opt;
   int dryrun = 0;   // dryrun=1: parse the inputs, build rank 0's initial configuration on the host and write it; no GPU
   for (int i = 1; i < argc; i++) {                       // key=value, like src/command_line.f90
@@ -22,6 +24,8 @@ int main(int argc, char **argv) {
     std::string k = a.substr(0, p), v = a.substr(p + 1);
     if (k == "input") input = v;
     else if (k == "metropolis") metro = v;
+    else if (k == "wl") wl = v;
+    else if (k == "gpus") opt.gpus = std::atoi(v.c_str());
     else if (k == "rng") opt.rng = v;
     else if (k == "ranks") opt.ranks = std::atoi(v.c_str());
     else if (k == "device") opt.device = std::atoi(v.c_str());
@@ -62,8 +66,9 @@ int main(int argc, char **argv) {
     } else if (setup.mode == 303) {                      // main.F90:121-130 (serial only)
       if (opt.ranks > 1) throw brawl::Stop("Nested sampling is serial only");
       brawl::nested_sampling_main(setup, opt);
-    } else if (setup.mode == 302) {
-      throw brawl::Stop("Wang-Landau (mode 302) is driven by brawl_b200/wang_landau.py / tools/wl_multi_gpu.py");
+    } else if (setup.mode == 302) {                      // main.F90:101-120 (MPI build only): ranks = walkers in total
+      brawl::WLParams wp = brawl::read_wl_file(wl);
+      brawl::wl_main(setup, wp, opt);
     } else if (setup.mode == 304) {
       throw brawl::Stop("TMMC is WIP in the reference and does not function (src/tmmc.F90:67-73)");
     } else {

@@ -363,7 +363,8 @@ std::string nc_header(const std::vector<std::pair<std::string, uint32_t>> &dims,
     h.u32(0);                                              // numrecs
     h.u32(0x0A); h.u32((uint32_t)dims.size());
     for (auto &d : dims) { h.name(d.first); h.u32(d.second); }
-    h.u32(0x0C); h.u32((uint32_t)atts.size());
+    if (atts.empty()) { h.u32(0); h.u32(0); }              // ABSENT
+    else { h.u32(0x0C); h.u32((uint32_t)atts.size()); }
     for (auto &a : atts) {
       h.name(a.name); h.u32((uint32_t)a.type);
       if (a.type == NC_INT) { h.u32((uint32_t)a.iv.size()); for (auto v : a.iv) h.u32((uint32_t)v); }
@@ -394,6 +395,59 @@ std::string nc_header(const std::vector<std::pair<std::string, uint32_t>> &dims,
 }
 std::string rtrim(std::string s) { while (!s.empty() && s.back() == ' ') s.pop_back(); return s; }
 }  // namespace
+
+// =====================================================================================================
+// xyz_writer (src/write_xyz.f90:39-116): extended XYZ -- particle count, Lattice="..." line, then one line per atom in the
+// reference's loop order (x outermost, then y, then z: configuration(1, j, k, l) with l fastest) with
+//   pos = ((j-1) a1 + (k-1) a2 + (l-1) a3 + basis) * lattice_parameter,  a_i = 0.5 e_i for every lattice the drivers support
+// (initialise.F90:176-223: the grid is the doubled conventional cell).  The reference writes list-directed (`write(7,*)`);
+// the field layout below follows gfortran's list-directed output (integer(4): I11 after the record's leading blank;
+// real(8): 17 significant digits in a 25-wide field; real(4) zeros as 0.00000000 in a 16-wide field).  There is no golden
+// .xyz in the reference's tests, so the exact whitespace is unpinned; the tokens (what extended-XYZ readers parse) are not.
+// =====================================================================================================
+static std::string ld_real64(double v) {                 // G25.17E3 as list-directed output uses it for 0.1 <= |v| < 1e17
+  char b[64];
+  if (v == 0.0) { std::snprintf(b, sizeof b, "%20.16f     ", 0.0); return b; }
+  const double a = std::fabs(v);
+  if (a >= 0.1 && a < 1e17) {
+    const int intdigits = a >= 1.0 ? (int)std::floor(std::log10(a)) + 1 : 0;
+    std::snprintf(b, sizeof b, "%20.*f     ", std::max(0, 17 - std::max(intdigits, 1)), v);
+  } else std::snprintf(b, sizeof b, "%25.16E", v);
+  return b;
+}
+void xyz_writer(const std::string &f, const Config &config, const RunParams &s, bool trajectory) {
+  std::ofstream fp(f, trajectory ? std::ios::app : std::ios::trunc);
+  if (!fp) throw Stop("cannot open " + f);
+  const int gx = 2 * s.n_1, gy = 2 * s.n_2, gz = 2 * s.n_3;
+  long n_particles = 0;
+  for (int8_t v : config) n_particles += v != 0;
+  char b[64];
+  std::snprintf(b, sizeof b, " %11ld\n", n_particles);
+  fp << b;
+  const std::string z4 = "   0.00000000    ";
+  fp << " Lattice=\"" << ld_real64(s.lattice_parameter * s.n_1) << z4 << z4 << z4 << ld_real64(s.lattice_parameter * s.n_2) << z4 << z4 << z4
+     << ld_real64(s.lattice_parameter * s.n_3) << "\"\n";
+  for (int x = 0; x < gx; x++) for (int y = 0; y < gy; y++) for (int z = 0; z < gz; z++) {
+    const int8_t sp = config[((size_t)z * gy + y) * gx + x];
+    if (sp == 0) continue;
+    std::string name = sp <= (int)s.species_names.size() ? s.species_names[sp - 1] : "X";
+    name.resize(2, ' ');                                                      // character(len=2)
+    fp << " " << name << ld_real64(0.5 * x * s.lattice_parameter) << ld_real64(0.5 * y * s.lattice_parameter)
+       << ld_real64(0.5 * z * s.lattice_parameter) << "\n";
+  }
+}
+
+void ncdf_writer_1d(const std::string &f, const std::vector<double> &grid_data) {        // netcdf_io.f90:731-806
+  std::vector<std::pair<std::string, uint32_t>> dims = {{"x", (uint32_t)grid_data.size()}};
+  std::vector<NcVar> vars = {{"grid data", {0}, NC_DOUBLE, grid_data.size()}};
+  std::vector<uint32_t> begins;
+  NcBuf out;
+  out.b = nc_header(dims, {}, vars, begins);
+  for (double v : grid_data) out.f64(v);
+  std::ofstream fp(f, std::ios::binary);
+  if (!fp) throw Stop("cannot open " + f);
+  fp.write(out.b.data(), (std::streamsize)out.b.size());
+}
 
 void ncdf_grid_state_writer(const std::string &f, const Config &state, const RunParams &s) {
   std::vector<std::pair<std::string, uint32_t>> dims = {{"b", (uint32_t)s.n_basis}, {"x", (uint32_t)(2 * s.n_1)},
@@ -514,9 +568,11 @@ static std::string rank_tag(int r) { char b[16]; std::snprintf(b, sizeof b, "%04
 // =====================================================================================================
 // metropolis_main / metropolis_simulated_annealing (src/metropolis.F90:46-558)
 // =====================================================================================================
+static void metropolis_decorrelated_samples(RunParams &setup, MetropolisParams &mp, const DriverOptions &opt);
 void metropolis_main(RunParams &setup, MetropolisParams &mp, const DriverOptions &opt) {
-  if (mp.mode != "simulated_annealing")                    // metropolis.F90:59-69 (decorrelated_samples: not mirrored)
-    throw Stop("Unrecognised mode '" + mp.mode + "' in Metropolis input file (this driver mirrors simulated_annealing)");
+  if (mp.mode == "decorrelated_samples") { metropolis_decorrelated_samples(setup, mp, opt); return; }   // metropolis.F90:59-69
+  if (mp.mode != "simulated_annealing")
+    throw Stop("Unrecognised mode '" + mp.mode + "' in Metropolis input file");
   const int S = setup.n_species, T_steps = mp.T_steps, p = opt.ranks;
   const bool replay = opt.rng == "mt19937";
   if (!replay && opt.rng != "philox") throw Stop("rng must be mt19937 or philox");
@@ -524,7 +580,8 @@ void metropolis_main(RunParams &setup, MetropolisParams &mp, const DriverOptions
   if (mp.calculate_energies) mkdir_p("energies");
   if (mp.calculate_asro) mkdir_p("asro");
   if (mp.calculate_alro) mkdir_p("alro");                                 // :129-131
-  if (mp.write_trajectory_energy || mp.write_trajectory_asro) mkdir_p("trajectories");
+  if (mp.write_trajectory_energy || mp.write_trajectory_asro || mp.write_trajectory_xyz) mkdir_p("trajectories");   // :132-134
+  if (mp.write_initial_config_xyz) mkdir_p("configs");
   std::vector<double> V = read_exchange(setup);
   const size_t nrho = (size_t)S * S * setup.wc_range;
   std::vector<double> av_E(T_steps, 0.0), av_C(T_steps, 0.0), av_acc(T_steps, 0.0), av_rho(nrho * T_steps, 0.0), temperature(T_steps);
@@ -580,6 +637,16 @@ void metropolis_main(RunParams &setup, MetropolisParams &mp, const DriverOptions
         asro = radial_densities(gpu, setup);
         if (mp.write_trajectory_asro) asro_trajectory_writer(afile, 0, asro);
       }
+      const std::string xyz_traj = "trajectories/proc_" + rt + "_trajectory_at_T_" + tt + ".xyz";            // :254-266
+      if (mp.write_trajectory_xyz) {
+        std::remove(xyz_traj.c_str());
+        Gpu::check(brawl_cuda_get_config(gpu.h, 0, 1, config.data()));
+        xyz_writer(xyz_traj, config, setup, true);                                                       // :310-313
+      }
+      if (mp.write_initial_config_xyz) {                                                                  // :320-326
+        Gpu::check(brawl_cuda_get_config(gpu.h, 0, 1, config.data()));
+        xyz_writer("configs/proc_" + rt + "_initial_config_at_T_" + tt + ".xyz", config, setup);
+      }
       if (mp.write_initial_config_nc) {
         Gpu::check(brawl_cuda_get_config(gpu.h, 0, 1, config.data()));
         ncdf_grid_state_writer("configs/proc_" + rt + "_initial_config_at_T_" + tt + ".nc", config, setup);
@@ -603,6 +670,10 @@ void metropolis_main(RunParams &setup, MetropolisParams &mp, const DriverOptions
           if (mp.write_trajectory_asro && step_n % mp.n_sample_steps_trajectory == 0) asro_trajectory_writer(afile, step_n, asro);
         }
         if (mp.calculate_alro && step_n % mp.n_sample_steps_alro == 0) Gpu::check(brawl_cuda_store_state(gpu.h, 0, 1));   // :394-399
+        if (mp.write_trajectory_xyz && step_n % mp.n_sample_steps_trajectory == 0) {                                  // :401-407
+          Gpu::check(brawl_cuda_get_config(gpu.h, 0, 1, config.data()));
+          xyz_writer(xyz_traj, config, setup, true);
+        }
       }
       acceptance_of_T[j - 1] = acceptance / (double)(float)mp.n_mc_steps;           // :412
       if (mp.calculate_energies) {
@@ -616,6 +687,10 @@ void metropolis_main(RunParams &setup, MetropolisParams &mp, const DriverOptions
       if (mp.calculate_alro) {                                                      // :444-447
         Gpu::check(brawl_cuda_get_order(gpu.h, 0, order.data(), 1));
         for (size_t q = 0; q < norder; q++) order_of_T[(size_t)(j - 1) * norder + q] = order[q] / (double)(float)n_save_alro;
+      }
+      if (mp.write_final_config_xyz) {                                                                    // :450-456
+        Gpu::check(brawl_cuda_get_config(gpu.h, 0, 1, config.data()));
+        xyz_writer("configs/proc_" + rt + "_final_config_at_T_" + tt + ".xyz", config, setup);
       }
       if (mp.write_final_config_nc) {
         Gpu::check(brawl_cuda_get_config(gpu.h, 0, 1, config.data()));
@@ -648,6 +723,67 @@ void metropolis_main(RunParams &setup, MetropolisParams &mp, const DriverOptions
 // gfortran list-directed real64 output: a 25-character field holding 17 significant digits.
 // 0.1 <= |v| < 1e16: F form, right-aligned in 20 characters followed by 5 blanks (where the exponent
 // would be); otherwise d.ddddddddddddddddE+ddd right-aligned in 25.
+// =====================================================================================================
+// metropolis_decorrelated_samples (src/metropolis.F90:572-738): burn in at every temperature of the ladder, then
+// n_mc_steps trials at the LAST temperature, dumping the configuration as configs/proc_RRRR_config_NNNN_at_T_TTTT.T.xyz
+// every n_sample_steps trials (the file index is i / n_sample_steps_asro, as in the reference).
+// =====================================================================================================
+static void metropolis_decorrelated_samples(RunParams &setup, MetropolisParams &mp, const DriverOptions &opt) {
+  const bool replay = opt.rng == "mt19937";
+  if (!replay && opt.rng != "philox") throw Stop("rng must be mt19937 or philox");
+  mkdir_p("configs");
+  if (mp.calculate_energies) mkdir_p("energies");
+  if (mp.calculate_asro) mkdir_p("asro");
+  if (mp.calculate_alro) mkdir_p("alro");
+  if (mp.write_trajectory_energy || mp.write_trajectory_asro || mp.write_trajectory_xyz) mkdir_p("trajectories");
+  std::vector<double> V = read_exchange(setup);
+  uint64_t offset = 0;
+  for (int my_rank = 0; my_rank < opt.ranks; my_rank++) {
+    MT19937 rng;
+    rng.f90_init_genrand(setup.static_seed ? 0 : 1, my_rank, 0);
+    Config config;
+    initial_setup(setup, config, rng);                                      // :588
+    Gpu gpu(setup, V, opt.device, 1);
+    Gpu::check(brawl_cuda_set_config(gpu.h, 0, 1, config.data()));
+    uint32_t st[625];
+    auto trials = [&](double beta, int64_t n) -> double {
+      if (n <= 0) return 0.0;
+      if (replay) {
+        int64_t acc = 0;
+        rng.export625(st);
+        Gpu::check(brawl_cuda_metropolis_replay(gpu.h, 0, beta, n, mp.nbr_swap ? 1 : 0, st, &acc));
+        rng.import625(st);
+        return (double)acc;
+      }
+      int64_t att = 0, acc = 0; double dE = 0.0;
+      Gpu::check(brawl_cuda_metropolis_run(gpu.h, &beta, n, mp.nbr_swap ? 1 : 0, opt.seed + (uint64_t)my_rank, offset, &offset, &att, &acc, &dE));
+      return att > 0 ? (double)acc * (double)n / (double)att : 0.0;
+    };
+    double temp = mp.T, beta = 1.0 / (temp * k_b_in_Ry);
+    for (int j = 1; j <= mp.T_steps; j++) {                                 // :641-671
+      temp = mp.T + (double)(j - 1) * mp.delta_T;
+      beta = 1.0 / (temp * k_b_in_Ry);
+      if (mp.burn_in) {
+        const double acceptance = trials(beta, mp.n_burn_in_steps);
+        if (my_rank == 0)
+          std::printf(" Burn-in complete at temperature %7.2f on process 0.\n Accepted %7d Monte Carlo moves at this temperature,\n"
+                      " Corresponding to an acceptance rate of %7.2f %%\n\n", temp, (int)acceptance, 100.0 * acceptance / (float)mp.n_burn_in_steps);
+      }
+    }
+    const int64_t n_samples = mp.n_mc_steps / mp.n_sample_steps;            // the i-loop (:676-703) in blocks of n_sample_steps
+    for (int64_t k = 1; k <= n_samples; k++) {
+      const double acceptance = trials(beta, mp.n_sample_steps);
+      const int64_t i = k * mp.n_sample_steps;
+      Gpu::check(brawl_cuda_get_config(gpu.h, 0, 1, config.data()));
+      char name[128];
+      std::snprintf(name, sizeof name, "configs/proc_%04d_config_%04d_at_T_%s.xyz", my_rank, (int)(i / mp.n_sample_steps_asro), temp_tag(temp).c_str());
+      xyz_writer(name, config, setup);
+      if (my_rank == 0) std::printf(" Accepted an additional %7d Monte Carlo moves before sample.\n\n", (int)acceptance);
+    }
+    trials(beta, mp.n_mc_steps - n_samples * mp.n_sample_steps);            // the tail of the loop writes nothing
+  }
+}
+
 static std::string ld_real17_field(double v) {
   char b[64], out[64];
   double a = std::fabs(v);

@@ -53,10 +53,18 @@ struct NSParams {
   std::string outfile_ener, outfile_traj;
 };
 
+// ---- type(wl_params), src/derived_types.f90:322-350 (reals are single precision there) ----------------
+struct WLParams {
+  int mc_sweeps = 100, bins = 512, num_windows = 4, radial_samples = 8, performance = 0;
+  float bin_overlap = 0.25f, tolerance = 5e-5f, flatness = 0.9f, wl_f = 0.05f, energy_min = -96.0f, energy_max = 0.0f;
+  bool nbr_swap = false;
+};
+
 // ---- parsers (src/io.f90) ---------------------------------------------------------------------------
 RunParams read_control_file(const std::string &filename);               // io.f90:135-330
 MetropolisParams read_metropolis_file(const std::string &filename);     // io.f90:519-686
 NSParams read_ns_file(const std::string &filename);                     // io.f90:740-817
+WLParams read_wl_file(const std::string &filename);                     // io.f90:951-1086
 std::vector<double> read_exchange(const RunParams &setup);              // io.f90:389-415 -> V_ex(S,S,n_shells)
 void initialise_function_pointers(RunParams &setup);                    // initialise.F90:153-257 (n_atoms, validation)
 
@@ -89,6 +97,8 @@ void ncdf_radial_density_writer(const std::string &f, const std::vector<double> 
                                 const std::vector<double> &r, const std::vector<double> &T,
                                 const std::vector<double> &U, const RunParams &setup);         // netcdf_io.f90:150-244
 void ncdf_config_reader(const std::string &f, Config &config, const RunParams &setup);        // netcdf_io.f90:1368-1429
+void ncdf_writer_1d(const std::string &f, const std::vector<double> &grid_data);              // netcdf_io.f90:731-806
+void xyz_writer(const std::string &f, const Config &config, const RunParams &setup, bool trajectory = false);   // write_xyz.f90:39-116
 void mkdir_p(const std::string &d);
 
 // ---- GPU handle (RAII over brawl_cuda_t) --------------------------------------------------------------
@@ -106,8 +116,21 @@ struct DriverOptions {
   int ranks = 1;                 // emulate `mpirun -np ranks`: rank r uses seed 110179+11 r and writes proc_000r files
   int device = 0;
   uint64_t seed = 0x42726157ull;
+  int gpus = 1;                  // Wang-Landau: processes (one per GPU, devices device .. device+gpus-1) the windows are sharded over
 };
 void metropolis_main(RunParams &setup, MetropolisParams &metropolis, const DriverOptions &opt);   // metropolis.F90:46-71
 void nested_sampling_main(RunParams &setup, const DriverOptions &opt);                             // nested_sampling.f90:45-206
+void wl_main(RunParams &setup, const WLParams &wl_setup, const DriverOptions &opt);                // wang-landau.F90:101-314
+
+// ---- Wang-Landau host arithmetic (1-based inclusive bin indices; src/wang-landau.F90 lines at each definition) ------
+std::vector<int64_t> wl_divide_range(int bins, int W);
+std::vector<int64_t> wl_create_overlap(const std::vector<int64_t> &intervals, float bin_overlap);
+std::vector<double> wl_create_energy_bins(int n_atoms, float energy_min, float energy_max, int bins, double *bin_width);
+int wl_bin_index(double e, const std::vector<double> &edges, int bins);
+std::vector<double> wl_dos_combine(const std::vector<double> &lng, const std::vector<int64_t> &win, int W, int bins);
+std::vector<std::pair<int, int>> wl_replica_exchange(const std::vector<double> &energies, const double *lng, const std::vector<int64_t> &win,
+                                                     int W, int walkers, const std::vector<double> &edges, int bins, MT19937 *mts);
+void wl_window_optimise(int it, std::vector<int64_t> &iv, const std::vector<double> &mc_steps, std::vector<double> &prev, int bins);
+std::vector<double> wl_compute_mean_energy(const std::vector<double> &lng, const std::vector<double> &edges, int bins, double bin_width);
 
 }  // namespace brawl

@@ -98,6 +98,10 @@ int brawl_cuda_total_energy(brawl_cuda_t *h, int first_replica, int n, int exact
 /* nbr_energy == setup%nbr_energy(config, 1, x+1, y+1, z+1) (src/bw_hamiltonian.f90:898-1262,
  * 1712-1910, 2059-2106) for every cell of one replica; 0.0 on empty cells.  out[grid]. */
 int brawl_cuda_site_energies(brawl_cuda_t *h, int replica, double *out);
+/* The operator itself, one site: setup%nbr_energy(config, 1, x+1, y+1, z+1) with the reference's summation order
+ * (bit-identical).  species = 0: the occupant is the centre; species = s > 0: species s is (the Fortran functions take the
+ * centre species from config after pair_swap, src/metropolis.F90:783-792 -- this argument spares the swap). */
+int brawl_cuda_nbr_energy(brawl_cuda_t *h, int replica, int x, int y, int z, int species, double *energy);
 /* Per-swap dE exactly as monte_carlo_step_* forms it: pair_energy(after) - pair_energy(before)
  * (src/metropolis.F90:783-792, src/bw_hamiltonian.f90:99-114); configuration is not modified. */
 int brawl_cuda_pair_dE(brawl_cuda_t *h, int replica, int64_t n_pairs, const int32_t *idx1,

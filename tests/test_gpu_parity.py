@@ -111,6 +111,32 @@ def test_site_and_total_energy_bit_exact(bw, orc, lattice, shells):
     assert abs(dev.total_energy(exact_order=False)[0] - e_ref) <= 1e-12 * max(1.0, abs(e_ref))
 
 
+def test_nbr_energy_single_site_bit_exact(bw, orc):
+    """brawl_cuda_nbr_energy == setup%nbr_energy for single sites, every lattice, incl. the wrapped
+    corner sites and the centre-species override, bit for bit; off-lattice cells and bad arguments fail."""
+    for lattice, shells, S in (("bcc", 6, 4), ("fcc", 4, 5), ("simple_cubic", 2, 3)):
+        V = rand_V(S, shells, 9)
+        sysm = orc.System(lattice, 4, 5, 6, S, shells, V)
+        g = random_config(orc, sysm, 5)
+        dev = bw.Device(lattice, 4, 5, 6, S, shells, V)
+        dev.set_config(g)
+        sites = np.argwhere(g > 0)
+        rng = np.random.default_rng(1)
+        pick = np.concatenate([sites[:3], sites[-3:], sites[rng.integers(0, len(sites), 30)]])
+        for z, y, x in pick:
+            assert dev.nbr_energy(x, y, z) == sysm.nbr_energy(g, int(x), int(y), int(z))
+        z, y, x = (int(v) for v in sites[7])
+        other = 1 + (int(g[z, y, x]) % S)
+        g2 = g.copy(); g2[z, y, x] = other
+        assert dev.nbr_energy(x, y, z, species=other) == sysm.nbr_energy(g2, x, y, z)
+        with pytest.raises(bw.BrawlCudaError):
+            dev.nbr_energy(99, 0, 0)
+        if lattice != "simple_cubic":
+            off = np.argwhere(g == 0)[0]
+            with pytest.raises(bw.BrawlCudaError):
+                dev.nbr_energy(int(off[2]), int(off[1]), int(off[0]))
+
+
 def test_total_energy_small_and_tiny_boxes(bw, orc, golden):
     """n=1 and n=2 boxes, where neighbour offsets wrap more than once."""
     for lattice, V, S, shells in (("bcc", golden["t02_V"], 4, 6), ("fcc", golden["t01_V"], 5, 6)):
