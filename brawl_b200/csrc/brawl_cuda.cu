@@ -19,6 +19,7 @@
 #include "tile_metropolis.cuh"
 #include "word_metropolis.cuh"
 #include "epoch_metropolis.cuh"
+#include "epoch_byte_metropolis.cuh"
 #include "walker_kernels.cuh"
 
 // ---- error state ---------------------------------------------------------------------------------
@@ -540,11 +541,16 @@ extern "C" int brawl_cuda_metropolis_replay(brawl_cuda_t *h, int replica, double
 typedef void (*BrwFastKernel)(BrwGeom, BrwBoxParams, uint8_t *, const double *, const double *, const int4 *,
                               const int4 *, uint32_t, uint32_t, uint32_t, int, unsigned long long *, unsigned long long *,
                               double *);
-struct BrwFastEntry { int lat, nsh, px, py, maxt; BrwFastKernel fn, fn_screen; };
+// fn_epoch[k][exact]: epoch_byte_metropolis.cuh, epochs of 4 (k = 0) / 8 (k = 1) steps, screened / reference association
+struct BrwFastEntry { int lat, nsh, px, py, maxt; BrwFastKernel fn, fn_screen; BrwFastKernel fn_epoch[2][2]; };
 // MAXT = launch bound: CTAs of <= 384 threads (e.g. the 128^3 single chain, 352 threads) may use up to
 // 168 registers/thread, CTAs of <= 768 threads (e.g. one 32^3-cell replica per CTA, 736 threads) 80.
 #define BRW_FAST(LAT, NSH, PX, PY, MAXT) {LAT, NSH, PX, PY, MAXT, brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, false, MAXT>, \
-                                          brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, true, MAXT>}
+                                          brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, true, MAXT>, \
+                                          {{brw_box_metropolis_byte_epoch_kernel<LAT, NSH, PX, PY, false, 4, MAXT>, \
+                                            brw_box_metropolis_byte_epoch_kernel<LAT, NSH, PX, PY, true, 4, MAXT>}, \
+                                           {brw_box_metropolis_byte_epoch_kernel<LAT, NSH, PX, PY, false, 8, MAXT>, \
+                                            brw_box_metropolis_byte_epoch_kernel<LAT, NSH, PX, PY, true, 8, MAXT>}}}
 static const BrwFastEntry brw_fast_table[] = {
     BRW_FAST(1, 4, 32, 32, 512), BRW_FAST(1, 4, 32, 32, 768), BRW_FAST(1, 6, 32, 32, 512), BRW_FAST(1, 6, 32, 32, 768),
     BRW_FAST(2, 4, 32, 64, 512), BRW_FAST(2, 4, 32, 64, 768), BRW_FAST(2, 6, 32, 64, 512), BRW_FAST(2, 6, 32, 64, 768),
@@ -593,6 +599,49 @@ static int brw_walker_prepare(const BrwGeom &g, int extra_doubles, K kernel, Brw
   }
   if (brw_cuda_check(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total()), "cudaFuncSetAttribute")) return 1;
   return 0;
+}
+
+
+// Site-energy table of the epoch kernels (epoch_metropolis.cuh, epoch_byte_metropolis.cuh): X_n[a][s] = V_n(a, s) - V_n(a, 4) -
+// (V_n(4, s) - V_n(4, 4)) for the species a of a cache row (S = 5; V_n(a, s) - V_n(3, s) for S = 4, plain V_n(a, s) below),
+// rounded to 2^-k units and split into three signed 8-bit digits.  |h - real| <= Z/2 units per cached value, four values per
+// dE  =>  guard = 2 Z units (+ the f64 rounding slack against the reference association).  S <= 4: all four counts are
+// explicit, energies relative to species 3 (its row is identically zero and not computed).
+static void brw_epoch_tables(const brawl_cuda_ctx *h, BrwBoxParams &p, double umax) {
+  const BrwGeom &g = h->g;
+  const int S = g.S, NSH = g.n_shells;
+  auto Vn = [&](int n, int centre, int nbr) { return h->hV[(n * S + nbr) * S + centre]; };
+  p.h_rows = S == 5 ? 4 : 3;
+  auto X = [&](int n, int a, int s2) {
+    double x = Vn(n, a, s2);
+    if (S == 5) x -= Vn(n, a, 4) + Vn(n, 4, s2) - Vn(n, 4, 4);
+    else if (S == 4) x -= Vn(n, 3, s2);
+    return x;
+  };
+  double xmax = 0.0, vmax = 0.0;
+  for (int n = 0; n < NSH; n++) for (int a = 0; a < std::min(S, 4); a++) for (int s2 = 0; s2 < std::min(S, 4); s2++)
+    xmax = std::max(xmax, std::fabs(X(n, a, s2)));
+  for (int i = 0; i < S * S * NSH; i++) vmax = std::max(vmax, std::fabs(h->hV[i]));
+  if (umax <= 0.0) umax = 2.0 * vmax;
+  int kx = 0;
+  if (xmax > 0.0) kx = (int)std::floor(std::log2(std::ldexp(1.0, 22) / xmax));
+  p.fix_scale = std::ldexp(1.0, -kx);
+  p.guard = 2.0 * g.ztot * p.fix_scale + 1e-9 * g.ztot * umax;
+  p.gfix = (int)std::ceil(p.guard / p.fix_scale) + 1;
+  std::memset(p.xdig, 0, sizeof p.xdig);
+  for (int c = 0; c < 4; c++) {
+    const int a = c;                                  // cache row <-> species c
+    if (a >= S || c >= p.h_rows) continue;
+    for (int n = 0; n < NSH; n++)
+      for (int s2 = 0; s2 < std::min(S, 4); s2++) {
+        long long v = std::llrint(std::ldexp(X(n, a, s2), kx));
+        for (int k = 0; k < 3; k++) {
+          long long dgt = k == 2 ? v : ((v + 128) & 255) - 128;
+          v = (v - dgt) >> 8;
+          p.xdig[(n * 3 + k) * 4 + c] |= (int)((uint32_t)(uint8_t)(int8_t)dgt << (8 * s2));
+        }
+      }
+  }
 }
 
 static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
@@ -800,6 +849,17 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
     int steps = h->tune_steps > 0 ? h->tune_steps : ((we ? 6 : 4) * p.box_sites + Mmax - 1) / Mmax;
     p.steps = std::max(8, std::min(steps, 512));
     if (we && we->epoch) p.steps = ((p.steps + we->epoch - 1) / we->epoch) * we->epoch;      // whole epochs
+    // byte-lattice epoch kernels (epoch_byte_metropolis.cuh): every geometry with a specialised kernel but no dense-set
+    // word kernel (fcc, 6-shell bcc), unless the caller asked for the one-gather-per-step kernels (byte_layout, dE_mode 1,
+    // set_layout 2/3)
+    const int byte_epoch = (!we && !nbr_swap && !h->disable_fast && !h->byte_layout && h->dE_mode != 1 && g.S <= 5 &&
+                            h->word_epoch > 0 && Mmax <= 768) ? (h->word_epoch == 8 ? 8 : 4) : 0;
+    if (byte_epoch && has_fast) {
+      // a trial costs ~10x less than a gather-per-step trial: six sweeps per phase amortise the box copies
+      if (h->tune_steps <= 0) steps = (6 * p.box_sites + Mmax - 1) / Mmax;
+      p.steps = std::max(8, std::min(steps, 1024));
+      p.steps = ((p.steps + byte_epoch - 1) / byte_epoch) * byte_epoch;
+    }
     p.steps_a = p.steps;
     pl->M_a = 0;
     if (we && we->split) {
@@ -845,6 +905,13 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
           pl->screened = screen;
           pl->fast_smem = (size_t)p.v_entries * 16 * 8 + 32 * 8 + (size_t)p.steps * sizeof(BrwStepParams) + p.box_sites;
           pl->threads = std::min(768, ((Mmax + 31) / 32) * 32);
+          if (byte_epoch) {
+            brw_epoch_tables(h, p, 0.0);
+            pl->fast_fn = (void *)fe.fn_epoch[byte_epoch == 8][h->dE_mode == 0];
+            pl->screened = h->dE_mode != 0; pl->byte_epoch = true;
+            pl->fast_smem = (size_t)p.v_entries * 16 * 8 + 32 * 8 + (size_t)(p.steps / byte_epoch) * sizeof(BrwByteEpochT<4>) +
+                            (size_t)((fe.maxt + 31) / 32) * 320 * 4 + (size_t)fe.maxt * 4 + p.box_sites;
+          }
           BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)pl->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
         }
     if (we) {
@@ -896,39 +963,7 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
           blob[urow_words + par * g.ztot + k] = dz * we->plp + dyc * we->pxp + dxc;
         }
       if (we->epoch) {
-        // site-energy table of the epoch kernels: X_n[c][s] = V_n(a, s) - V_n(a, 4) - (V_n(4, s) - V_n(4, 4)) for the species a
-        // of cache row a + 1 (S = 5; plain V_n(a, s) for S <= 4), rounded to 2^-k units and split into three signed 8-bit digits.
-        // |h - real| <= Z/2 units per cached value, four values per dE  =>  guard = 2 Z units (+ the f64 rounding slack)
-        // S <= 4: all four counts are explicit, energies relative to species 3 (its row is identically zero and not computed)
-        p.h_rows = S == 5 ? 4 : 3;
-        auto X = [&](int n, int a, int s2) {
-          double x = Vn(n, a, s2);
-          if (S == 5) x -= Vn(n, a, 4) + Vn(n, 4, s2) - Vn(n, 4, 4);
-          else if (S == 4) x -= Vn(n, 3, s2);
-          return x;
-        };
-        double xmax = 0.0;
-        for (int n = 0; n < NSH; n++) for (int a = 0; a < std::min(S, 4); a++) for (int s2 = 0; s2 < std::min(S, 4); s2++)
-          xmax = std::max(xmax, std::fabs(X(n, a, s2)));
-        int kx = 0;
-        if (xmax > 0.0) kx = (int)std::floor(std::log2(std::ldexp(1.0, 22) / xmax));
-        p.fix_scale = std::ldexp(1.0, -kx);
-        p.guard = 2.0 * g.ztot * p.fix_scale + 1e-9 * g.ztot * umax;
-        p.gfix = (int)std::ceil(p.guard / p.fix_scale) + 1;
-        std::memset(p.xdig, 0, sizeof p.xdig);
-        for (int c = 0; c < 4; c++) {
-          const int a = c;                                  // cache row = species + 1
-          if (a >= S || c >= p.h_rows) continue;
-          for (int n = 0; n < NSH; n++)
-            for (int s2 = 0; s2 < std::min(S, 4); s2++) {
-              long long v = std::llrint(std::ldexp(X(n, a, s2), kx));
-              for (int k = 0; k < 3; k++) {
-                long long dgt = k == 2 ? v : ((v + 128) & 255) - 128;
-                v = (v - dgt) >> 8;
-                p.xdig[(n * 3 + k) * 4 + c] |= (int)((uint32_t)(uint8_t)(int8_t)dgt << (8 * s2));
-              }
-            }
-        }
+        brw_epoch_tables(h, p, umax);
       }
       std::memcpy(blob.data() + tab_words, h->hV, sizeof(double) * p.v_entries);
       cudaFree(pl->d_Vrep); pl->d_Vrep = nullptr;
@@ -1002,7 +1037,7 @@ extern "C" int brawl_cuda_metropolis_plan(brawl_cuda_t *h, int nbr_swap, int *o)
     const BrwBoxMode &m0 = pl->p.mode[0];
     o[0] = pl->use_box; o[1] = m0.P[0] * 10000 + m0.P[1] * 100 + m0.P[2]; o[2] = pl->p.m; o[3] = pl->p.B[0]; o[4] = pl->p.B[1];
     o[5] = pl->p.B[2]; o[6] = pl->Mmax; o[7] = pl->p.boxes_per_replica; o[8] = m0.n_disp; o[9] = pl->p.steps;
-    if (pl->fast_fn) o[0] = pl->word ? (pl->screened ? 4 : 5) : pl->screened ? 3 : 2;
+    if (pl->fast_fn) o[0] = pl->word ? (pl->screened ? 4 : 5) : pl->byte_epoch ? (pl->screened ? 6 : 7) : pl->screened ? 3 : 2;
     o[0] += 16 * pl->p.n_modes;                 // number of period orientations in bits 4..11
     if (pl->word && pl->split) o[0] += 4096;    // bit 12: two warp groups per CTA, box_z = layer pitch (box depth = pitch + margin)
   }

@@ -45,7 +45,7 @@ struct BrwBoxParams {          // POD kernel parameter
   int row_mul;                 // word kernel: row of its fixed-point table = code_a*row_mul + code_b
   // epoch kernels (epoch_metropolis.cuh): signed 8-bit digits of the fixed-point site-energy table, packed over the four
   // count fields, index (shell*3 + digit)*4 + species; guard band in fixed-point units
-  int xdig[48];
+  int xdig[72];
   int gfix;
   int h_rows;                  // cached rows per site: 4 (five species, relative to species 4) or 3 (relative to species 3)
 };
@@ -64,6 +64,7 @@ struct BrwPlan {
   void *fast_fn = nullptr;     // specialised kernel for this (lattice, shells, pitch), if instantiated
   bool screened = false;
   bool split = false;          // word kernel with two warp groups per CTA and shared z margin planes
+  bool byte_epoch = false;     // fast_fn is a byte-lattice epoch kernel (epoch_byte_metropolis.cuh)
   bool word = false;           // fast_fn is a word-lattice kernel (word_metropolis.cuh); d_Vrep holds its table blob
   size_t fast_smem = 0;
   // per-box counters

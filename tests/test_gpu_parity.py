@@ -520,13 +520,15 @@ def test_specialised_kernel_equals_generic_kernel(bw, orc, golden, lattice, n, S
 
 @pytest.mark.parametrize("lattice,n,S,shells,key,T", [("bcc", 32, 4, 4, "ex_AlTiCrMo_V", 300.0), ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", 2000.0),
                                                       ("bcc", 32, 5, 4, "ex_AlCrFeCoNi_V", 800.0), ("fcc", 32, 5, 4, "ex_AlCrFeCoNi_V", 600.0),
-                                                      ("fcc", 32, 2, 6, "t01_V", 500.0)])
+                                                      ("fcc", 32, 2, 6, "t01_V", 500.0), ("bcc", 32, 4, 6, "t02_V", 700.0),
+                                                      ("fcc", 32, 2, 4, "ex_FeNi_V", 400.0)])
 def test_screened_kernel_trajectory_identical(bw, orc, golden, lattice, n, S, shells, key, T):
     """dE_mode 1 (integer-count screening on the byte lattice) and dE_mode 2 (word lattice, fixed-point dp4a dE,
     ex2.approx acceptance test) recompute every trial inside their guard bands with the reference association,
     so they take exactly the accept/reject decisions of dE_mode 0 (reference association for every trial):
     same seed => identical configuration and identical accept counts after millions of trials."""
-    V = golden[key][: 5 * 5 * shells].reshape(shells, 5, 5)[:, :S, :S].copy().ravel() if key != "ex_AlTiCrMo_V" else golden[key][: S * S * shells]
+    S0 = {"ex_AlTiCrMo_V": 4, "t02_V": 4, "ex_FeNi_V": 2}.get(key, 5)          # species of the stored table
+    V = golden[key][: S0 * S0 * shells].reshape(shells, S0, S0)[:, :S, :S].copy().ravel()
     g = np.zeros((2 * n, 2 * n, 2 * n), dtype=np.int8)
     rng = np.random.default_rng(4)
     par = np.arange(2 * n) & 1
@@ -536,7 +538,8 @@ def test_screened_kernel_trajectory_identical(bw, orc, golden, lattice, n, S, sh
     res = []
     word = lattice == "bcc" and shells == 4
     # (layout, mode, expected kernel kind); runs with the same layout share one decomposition
-    runs = [(True, 0, 2), (True, 1, 3)] + ([(False, 0, 5), (False, 2, 4)] if word else [(False, 2, 3)])
+    # (default layout on the other geometries: the byte-lattice epoch kernels, 7 = reference association, 6 = cached energies)
+    runs = [(True, 0, 2), (True, 1, 3)] + ([(False, 0, 5), (False, 2, 4)] if word else [(False, 0, 7), (False, 2, 6)])
     res = {}
     for byte_layout, mode, kind in runs:
         dev = bw.Device(lattice, n, n, n, S, shells, V)
@@ -546,7 +549,7 @@ def test_screened_kernel_trajectory_identical(bw, orc, golden, lattice, n, S, sh
         dev.set_config(g)
         out = dev.metropolis_run(1.0 / (T * bw.K_B_IN_RY), 12 * int(mask.sum()), seed=99)
         res[(byte_layout, mode)] = (dev.get_config().copy(), out, dev.total_energy()[0])
-    pairs = [((True, 0), (True, 1), 1e-9)] + ([((False, 0), (False, 2), 1e-4)] if word else [((True, 1), (False, 2), 1e-9)])
+    pairs = [((True, 0), (True, 1), 1e-9), ((False, 0), (False, 2), 1e-4)]
     for ka, kb, tol in pairs:
         a, b = res[ka], res[kb]
         assert np.array_equal(a[0], b[0])
@@ -922,25 +925,27 @@ def test_radial_counts_batch_matches_single(bw, orc, golden):
             dev.radial_densities_batch(4, R - 1, 2)
 
 
-@pytest.mark.parametrize("S,key,T", [(4, "ex_AlTiCrMo_V", 1000.0), (5, "ex_AlCrFeCoNi_V", 800.0)])
-def test_epoch_kernel_statistics_match_oracle(bw, orc, golden, S, key, T):
-    """The headline kernel (epoch kernel: dense non-interacting sets, site energies cached over 4 steps, use_box == 4)
+@pytest.mark.parametrize("lattice,shells,S,key,T,kind", [("bcc", 4, 4, "ex_AlTiCrMo_V", 1000.0, 4), ("bcc", 4, 5, "ex_AlCrFeCoNi_V", 800.0, 4),
+                                                         ("bcc", 6, 4, "t02_V", 1000.0, 6), ("fcc", 4, 5, "ex_AlCrFeCoNi_V", 800.0, 6)])
+def test_epoch_kernel_statistics_match_oracle(bw, orc, golden, lattice, shells, S, key, T, kind):
+    """The headline kernel (epoch kernel: dense non-interacting sets, site energies cached over 4 steps, use_box == 4) and
+    the byte-lattice epoch kernels of the other geometries (6-shell bcc, fcc: period-P classes, use_box == 6)
     against the oracle's sequential reference sampler, directly, at the bench temperature: energy per atom, heat capacity
     and the Warren-Cowley parameters alpha = 1 - rho/(Z c) (examples/01_metropolis_FeNi/02_simulated_annealing/
-    01_plot_results.py:35-36) of shells 1 and 2.  bcc 32^3 (65 536 atoms).  Six GPU replicas are equilibrated for 4000
+    01_plot_results.py:35-36) of shells 1 and 2.  32^3 cells (bcc 65 536 atoms, fcc 131 072).  Six GPU replicas are equilibrated for 4000
     sweeps; every equilibrated configuration then starts one oracle chain (own MT stream) AND the continuation of its GPU
     replica: 30 sweeps discarded, 120 sweeps sampled every 5.  Both samplers leave the Boltzmann distribution invariant,
     so the averages of a pair must agree within the blocked statistical errors (blocks of 4 samples = 20 sweeps, 6 per
     chain; pairing removes the slow replica-to-replica differences of the ordered state): the mean pair difference must
     be below 6 standard errors (5 sigma + 1 sigma slack, no other tolerance)."""
     import threading
-    V = golden[key][: S * S * 4]
+    V = golden[key][: S * S * shells]
     n, R = 32, 6
-    sysm = orc.System("bcc", n, n, n, S, 4, V)
+    sysm = orc.System(lattice, n, n, n, S, shells, V)
     N = sysm.n_atoms
     beta = 1.0 / (T * bw.K_B_IN_RY)
-    dev = bw.Device("bcc", n, n, n, S, 4, V, n_replicas=R)
-    assert dev.metropolis_plan()["use_box"] == 4 and dev.metropolis_plan()["trials_per_step"] == 960
+    dev = bw.Device(lattice, n, n, n, S, shells, V, n_replicas=R)
+    assert dev.metropolis_plan()["use_box"] == kind and (kind != 4 or dev.metropolis_plan()["trials_per_step"] == 960)
     starts = []
     for r in range(R):
         rng = np.random.default_rng(40 + r)
@@ -948,13 +953,16 @@ def test_epoch_kernel_statistics_match_oracle(bw, orc, golden, S, key, T):
         rng.shuffle(spec)
         g = np.zeros((2 * n,) * 3, dtype=np.int8)
         par = np.arange(2 * n) & 1
-        g[(par[None, None, :] == par[:, None, None]) & (par[None, :, None] == par[:, None, None])] = spec
+        if lattice == "bcc":
+            g[(par[None, None, :] == par[:, None, None]) & (par[None, :, None] == par[:, None, None])] = spec
+        else:
+            g[((par[None, None, :] + par[None, :, None] + par[:, None, None]) & 1) == 0] = spec
         starts.append(g)
     dev.set_config(np.stack(starts))
     dev.metropolis_run(beta, 4000 * N, seed=77)
     eq = dev.get_config(0, R).copy()
     conc = np.bincount(starts[0].ravel(), minlength=S + 1)[1:] / float(N)
-    Z = np.array([8.0, 6.0])
+    Z = np.array([8.0, 6.0]) if lattice == "bcc" else np.array([12.0, 6.0])
     BS = 4                                                                      # samples per block
 
     def observables(e_series, rho_series):
@@ -1009,5 +1017,5 @@ def test_epoch_kernel_statistics_match_oracle(bw, orc, golden, S, key, T):
     a_mean = np.mean([o[2].mean(axis=0) for o in orc_out], axis=0)
     assert report[0][2] < 5e-3 * abs(e_mean), (report, e_mean)
     assert np.max(np.abs(a_mean)) > 20 * report[2][2], (report, a_mean)        # SRO is resolved, not noise
-    print("epoch kernel vs oracle, S=%d T=%g: <E>/N = %.7f, max |diff| / max se: %s, worst |z| = %.2f"
-          % (S, T, e_mean, ["%s %.2e / %.2e" % r for r in report], worst))
+    print("epoch kernel vs oracle, %s %d shells S=%d T=%g: <E>/N = %.7f, max |diff| / max se: %s, worst |z| = %.2f"
+          % (lattice, shells, S, T, e_mean, ["%s %.2e / %.2e" % r for r in report], worst))
