@@ -257,28 +257,32 @@ def plan_replica_exchange(energies, lng_windows, window_indices, walkers, edges,
     rank computes the same plan.  Returns [(walker_a, walker_b), ...] of accepted exchanges."""
     W = window_indices.shape[0]
     bins = edges.size - 1
-    ib = [bin_index(e, edges, bins) for e in energies]
-    loc = [overlap_location(ib[g], g // walkers + 1, window_indices) for g in range(W * walkers)]
+    # bin_index and overlap_location of every walker at once (same f64 arithmetic, element by element)
+    e = np.asarray(energies, dtype=np.float64)
+    ib = (np.trunc(((e - edges[0]) / (edges[bins] - edges[0])) * float(bins))).astype(np.int64) + 1
+    q = np.arange(W * walkers) // walkers + 1
+    wi = np.asarray(window_indices, dtype=np.int64)
+    lo_prev_hi = wi[np.maximum(q - 2, 0), 1]; lo_own = wi[q - 1, 0]; hi_own = wi[q - 1, 1]; up_next_lo = wi[np.minimum(q, W - 1), 0]
+    lower_reg = (q > 1) & (ib < lo_prev_hi + 1) & (ib > lo_own - 1)
+    upper_reg = (q < W) & (ib > up_next_lo - 1) & (ib < hi_own + 1)
+    loc = np.where(upper_reg, q, np.where(lower_reg, q - 1, 0))
     swaps = []
     for i in range(1, W):
         lower = [g for g in range((i - 1) * walkers, i * walkers)]
         upper = [g for g in range(i * walkers, (i + 1) * walkers)]
         rng.shuffle(lower)
         rng.shuffle(upper)
-        used = set()
-        for a in lower:
-            if loc[a] != i:
-                continue
-            for b in upper:
-                if b in used or loc[b] != i:
-                    continue
-                used.add(b)
-                lng = lng_windows[i - 1]
-                # bins / regions are NOT refreshed after an exchange -- the reference evaluates them once
-                # per call (:1405-1431); a walker sits in at most one region, so it is paired at most once
-                if rng.random() < math.exp(min(0.0, lng[ib[a] - 1] - lng[ib[b] - 1])):
-                    swaps.append((a, b))
-                break
+        # every lower walker of the region takes the first unused upper walker of the region: the two filtered orders, zipped
+        # (bins / regions are NOT refreshed after an exchange -- the reference evaluates them once per call (:1405-1431); a
+        # walker sits in at most one region, so it is paired at most once)
+        lower_c = [a for a in lower if loc[a] == i]
+        if not lower_c:
+            continue
+        upper_c = [b for b in upper if loc[b] == i]
+        lng = lng_windows[i - 1]
+        for a, b in zip(lower_c, upper_c):
+            if rng.random() < math.exp(min(0.0, lng[ib[a] - 1] - lng[ib[b] - 1])):
+                swaps.append((a, b))
     return swaps
 
 
