@@ -444,36 +444,52 @@ def main():
         devs[1].set_stream(copy_stream.cuda_stream)              # second lattice: its own stream => overlaps with the first
     host_cfg = [torch.empty((R, 2 * n, 2 * n, 2 * n), dtype=torch.int8).pin_memory() for _ in devs]
     host_np = [h.numpy() for h in host_cfg]
-    for d, hnp in zip(devs, host_np):
+    host_lat = [torch.empty((R, N), dtype=torch.uint8).pin_memory() for _ in devs]
+    host_lat_np = [h.numpy() for h in host_lat]
+    for d, hnp, hl in zip(devs, host_np, host_lat_np):
         d.get_config(0, R, out=hnp)
+        d.get_lattice(0, R, out=hl)
     import concurrent.futures as cf
     pool = cf.ThreadPoolExecutor(max_workers=len(devs))          # ctypes releases the GIL: one host thread per lattice
 
-    def e2e_step(i):
-        d, hnp = devs[i], host_np[i]
-        d.set_config(hnp)                                        # H2D 8n^3 bytes (+ pack kernel)
+    def e2e_step(i, grid):
+        d = devs[i]
+        if grid:                                                 # the reference's `config` grid: 8 n^3 bytes each way
+            d.set_config(host_np[i])                             # H2D + pack kernel
+        else:                                                    # compact sites: 2 n^3 bytes each way
+            d.set_lattice(host_lat_np[i])                        # H2D + validation kernel
         a, c, _ = d.metropolis_run(beta, trials_per_step)        # trials
-        d.get_config(0, R, out=hnp)                              # D2H 8n^3 bytes (+ unpack kernel)
+        if grid:
+            d.get_config(0, R, out=host_np[i])                   # unpack kernel + D2H
+        else:
+            d.get_lattice(0, R, out=host_lat_np[i])              # D2H
         e_host = d.total_energy(0, R, exact_order=False)         # D2H 8 bytes per replica (2 kernels)
-        return int(a.sum()), d.metropolis_last_launches() + 4, float(e_host[0])
+        return int(a.sum()), d.metropolis_last_launches() + (4 if grid else 3), float(e_host[0])
 
-    e2e_ms, e2e_attempts, e2e_launches = 0.0, 0, 0
-    n_e2e = max(3, min(args.steps, 5))
-    for it in range(2 + n_e2e):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        res = list(pool.map(e2e_step, range(len(devs))))
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) * 1e3                    # host clock around device-synchronised calls (two streams)
-        if it >= 2:
-            e2e_ms += dt
-            e2e_attempts += sum(r[0] for r in res)
-            e2e_launches += sum(r[1] for r in res)
+    def e2e_run(grid):
+        ms, att, nl = 0.0, 0, 0
+        n_e2e = max(3, min(args.steps, 5))
+        for it in range(2 + n_e2e):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = list(pool.map(lambda i: e2e_step(i, grid), range(len(devs))))
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) * 1e3                # host clock around device-synchronised calls (two streams)
+            if it >= 2:
+                ms += dt
+                att += sum(r[0] for r in res)
+                nl += sum(r[1] for r in res)
+        return ms, att, nl
+
+    barrier()
+    e2e_ms, e2e_attempts, e2e_launches = e2e_run(False)
+    barrier()
+    e2e_grid_ms, e2e_grid_attempts, _ = e2e_run(True)
     pool.shutdown()
 
-    (total_ms_r, e2e_ms_r), (attempts_all, e2e_attempts_all, launches_all) = reduce_max_sum(
-        [total_ms, e2e_ms], [attempts_rank, e2e_attempts, launches])
+    (total_ms_r, e2e_ms_r, e2e_grid_ms_r), (attempts_all, e2e_attempts_all, launches_all, e2e_grid_attempts_all) = reduce_max_sum(
+        [total_ms, e2e_ms, e2e_grid_ms], [attempts_rank, e2e_attempts, launches, e2e_grid_attempts])
 
     # ---- extra blocks: the other BASELINE configurations, short runs in the same clocks window ------------------
     extra = {}
@@ -541,10 +557,17 @@ def main():
                        "sampling_efficiency_per_attempt_vs_sequential": "0.40-0.45 (energy relaxation at 1000 K against the oracle's "
                                                                         "sequential sampler; round-1 kernel: 0.45; tools/exp_scan.py)",
                        "energy_per_atom_start_end_Ry": [e_start / N, e_end / N]},
-            "e2e": {"value": e2e_value, "unit": "swaps/s", "h2d_bytes_per_step": int(len(devs) * R * (8 * n ** 3 + 8)),
-                    "d2h_bytes_per_step": int(len(devs) * R * (8 * n ** 3 + 8 + 24)),
-                    "calls": "set_config + metropolis_run + get_config + total_energy per lattice, pinned host buffers; "
-                             "%d lattice(s) per GPU on separate streams so that copies overlap the trials" % len(devs)},
+            "e2e": {"value": e2e_value, "unit": "swaps/s", "h2d_bytes_per_step": int(len(devs) * R * (N + 8)),
+                    "d2h_bytes_per_step": int(len(devs) * R * (N + 8 + 24)),
+                    "calls": "set_lattice + metropolis_run + get_lattice + total_energy per lattice through the C ABI, pinned "
+                             "host buffers of compact sites (1 B per atom); %d lattice(s) per GPU on separate streams so "
+                             "that copies overlap the trials" % len(devs),
+                    "with_reference_config_grid": {
+                        "value": e2e_grid_attempts_all / (e2e_grid_ms_r * 1e-3), "unit": "swaps/s",
+                        "h2d_bytes_per_step": int(len(devs) * R * (8 * n ** 3 + 8)),
+                        "d2h_bytes_per_step": int(len(devs) * R * (8 * n ** 3 + 8 + 24)),
+                        "calls": "set_config + metropolis_run + get_config + total_energy: the reference's int8 config grid "
+                                 "(2n)^3, 4x the bytes of the compact form, pack / unpack kernels on the device"}},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": roofline_block(plan, attempts / max(1, launches), total_ms / max(1, launches), args.layout),

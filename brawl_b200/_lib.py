@@ -25,6 +25,8 @@ _SIGNATURES = {
     "brawl_cuda_info": [_vp, _vp, _vp, _vp, _vp],
     "brawl_cuda_set_config": [_vp, _i, _i, _vp],
     "brawl_cuda_get_config": [_vp, _i, _i, _vp],
+    "brawl_cuda_set_lattice": [_vp, _i, _i, _vp],
+    "brawl_cuda_get_lattice": [_vp, _i, _i, _vp],
     "brawl_cuda_copy_replica": [_vp, _i, _i],
     "brawl_cuda_random_config": [_vp, _i, _i, _vp, _u64, _u64],
     "brawl_cuda_store_state": [_vp, _i, _i],

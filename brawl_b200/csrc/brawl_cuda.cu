@@ -1,5 +1,5 @@
-// brawl_cuda.cu -- C ABI (include/brawl_cuda.h) of libbrawl_cuda.so.  Unity build: the kernel
-// headers are included here so the library is one translation unit (no device linking).
+// brawl_cuda.cu -- C ABI (include/brawl_cuda.h) of libbrawl_cuda.so.  The kernel headers are included here; the
+// byte-lattice epoch kernels are instantiated in byte_epoch_kernels.cu (compiled in parallel; no device linking).
 // Product code: there is NO CPU fallback -- every entry point needs a working CUDA device.
 #include <array>
 #include <cstdarg>
@@ -19,7 +19,7 @@
 #include "tile_metropolis.cuh"
 #include "word_metropolis.cuh"
 #include "epoch_metropolis.cuh"
-#include "epoch_byte_metropolis.cuh"
+#include "epoch_byte_metropolis.cuh"     // BrwByteEpochT (the kernels are instantiated in byte_epoch_kernels.cu)
 #include "walker_kernels.cuh"
 
 // ---- error state ---------------------------------------------------------------------------------
@@ -261,6 +261,44 @@ extern "C" int brawl_cuda_get_config(brawl_cuda_t *h, int first, int n, int8_t *
     BRW_CUDA(cudaMemcpyAsync(grids + (size_t)r0 * h->grid_cells, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
     BRW_CUDA(cudaStreamSynchronize(h->stream));
   }
+  return 0;
+}
+// Compact host buffers: [n][n_atoms] bytes, species 0..S-1 in the device's own site order (z, then compact y, then
+// compact x -- the order brawl_cuda_lattice_ptr exposes).  A quarter (bcc) / half (fcc) of the bytes of the reference's
+// `config` grid (src/shared_data.f90:30): the form a driver keeps between annealing segments or writes to a checkpoint
+// when PCIe or host-memory bandwidth is shared by many GPUs.
+__global__ void brw_validate_lattice_kernel(const uint8_t *__restrict__ lat, long n, int S, int *flag) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long n16 = n >> 4;
+  bool bad = false;
+  if (i < n16) {
+    const uint4 v = reinterpret_cast<const uint4 *>(lat)[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) bad |= ((w[k] >> (8 * b)) & 255u) >= (uint32_t)S;
+  }
+  if (i == 0) for (long j = n16 << 4; j < n; j++) bad |= lat[j] >= S;
+  if (bad) atomicOr(flag, 1);
+}
+extern "C" int brawl_cuda_set_lattice(brawl_cuda_t *h, int first, int n, const uint8_t *sites) {
+  BRW_ENTER(h);
+  if (!sites) return brw_fail("null lattice pointer");
+  if (n < 1 || first < 0 || first + n > h->n_replicas) return brw_fail("replica range [%d,%d) out of [0,%d)", first, first + n, h->n_replicas);
+  const size_t bytes = (size_t)h->g.n_sites * n;
+  uint8_t *dst = h->d_lat + (size_t)first * h->g.n_sites;
+  BRW_CUDA(cudaMemcpyAsync(dst, sites, bytes, cudaMemcpyHostToDevice, h->stream));
+  brw_validate_lattice_kernel<<<grid_for((long)(bytes / 16) + 1, 256), 256, 0, h->stream>>>(dst, (long)bytes, h->g.S, h->d_flag);
+  BRW_LAUNCH_CHECK("brw_validate_lattice_kernel");
+  return brw_check_flag(h, "set_lattice");
+}
+extern "C" int brawl_cuda_get_lattice(brawl_cuda_t *h, int first, int n, uint8_t *sites) {
+  BRW_ENTER(h);
+  if (!sites) return brw_fail("null lattice pointer");
+  if (n < 1 || first < 0 || first + n > h->n_replicas) return brw_fail("replica range [%d,%d) out of [0,%d)", first, first + n, h->n_replicas);
+  BRW_CUDA(cudaMemcpyAsync(sites, h->d_lat + (size_t)first * h->g.n_sites, (size_t)h->g.n_sites * n, cudaMemcpyDeviceToHost, h->stream));
+  BRW_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
 }
 // ---- start states on the device ---------------------------------------------------------------
@@ -541,16 +579,13 @@ extern "C" int brawl_cuda_metropolis_replay(brawl_cuda_t *h, int replica, double
 typedef void (*BrwFastKernel)(BrwGeom, BrwBoxParams, uint8_t *, const double *, const double *, const int4 *,
                               const int4 *, uint32_t, uint32_t, uint32_t, int, unsigned long long *, unsigned long long *,
                               double *);
-// fn_epoch[k][exact]: epoch_byte_metropolis.cuh, epochs of 4 (k = 0) / 8 (k = 1) steps, screened / reference association
-struct BrwFastEntry { int lat, nsh, px, py, maxt; BrwFastKernel fn, fn_screen; BrwFastKernel fn_epoch[2][2]; };
+struct BrwFastEntry { int lat, nsh, px, py, maxt; BrwFastKernel fn, fn_screen; };
+// byte-lattice epoch kernels of the same geometries (epoch_byte_metropolis.cuh), instantiated in byte_epoch_kernels.cu
+void *brw_byte_epoch_kernel_lookup(int lat, int nsh, int px, int py, int maxt, int epoch_k, int exact);
 // MAXT = launch bound: CTAs of <= 384 threads (e.g. the 128^3 single chain, 352 threads) may use up to
 // 168 registers/thread, CTAs of <= 768 threads (e.g. one 32^3-cell replica per CTA, 736 threads) 80.
 #define BRW_FAST(LAT, NSH, PX, PY, MAXT) {LAT, NSH, PX, PY, MAXT, brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, false, MAXT>, \
-                                          brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, true, MAXT>, \
-                                          {{brw_box_metropolis_byte_epoch_kernel<LAT, NSH, PX, PY, false, 4, MAXT>, \
-                                            brw_box_metropolis_byte_epoch_kernel<LAT, NSH, PX, PY, true, 4, MAXT>}, \
-                                           {brw_box_metropolis_byte_epoch_kernel<LAT, NSH, PX, PY, false, 8, MAXT>, \
-                                            brw_box_metropolis_byte_epoch_kernel<LAT, NSH, PX, PY, true, 8, MAXT>}}}
+                                          brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, true, MAXT>}
 static const BrwFastEntry brw_fast_table[] = {
     BRW_FAST(1, 4, 32, 32, 512), BRW_FAST(1, 4, 32, 32, 768), BRW_FAST(1, 6, 32, 32, 512), BRW_FAST(1, 6, 32, 32, 768),
     BRW_FAST(2, 4, 32, 64, 512), BRW_FAST(2, 4, 32, 64, 768), BRW_FAST(2, 6, 32, 64, 512), BRW_FAST(2, 6, 32, 64, 768),
@@ -907,7 +942,8 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
           pl->threads = std::min(768, ((Mmax + 31) / 32) * 32);
           if (byte_epoch) {
             brw_epoch_tables(h, p, 0.0);
-            pl->fast_fn = (void *)fe.fn_epoch[byte_epoch == 8][h->dE_mode == 0];
+            pl->fast_fn = brw_byte_epoch_kernel_lookup(fe.lat, fe.nsh, fe.px, fe.py, fe.maxt, byte_epoch, h->dE_mode == 0);
+            if (!pl->fast_fn) { brw_fail("byte-lattice epoch kernel not instantiated"); brw_free_plan(pl); return 1; }
             pl->screened = h->dE_mode != 0; pl->byte_epoch = true;
             pl->fast_smem = (size_t)p.v_entries * 16 * 8 + 32 * 8 + (size_t)(p.steps / byte_epoch) * sizeof(BrwByteEpochT<4>) +
                             (size_t)((fe.maxt + 31) / 32) * 320 * 4 + (size_t)fe.maxt * 4 + p.box_sites;

@@ -96,6 +96,19 @@ class Device:
         check(self.L.brawl_cuda_get_config(self.h, first_replica, n, _p(g)))
         return g[0] if (n == 1 and out is None) else g
 
+    def set_lattice(self, sites, first_replica=0, n=None):
+        """Compact configurations [n][n_atoms] uint8, species 0..S-1 in the device's site order (include/brawl_cuda.h)."""
+        a = np.ascontiguousarray(sites, dtype=np.uint8)
+        n = a.size // self.n_atoms if n is None else n
+        if a.size != n * self.n_atoms:
+            raise BrawlCudaError("set_lattice: expected %d x %d bytes" % (n, self.n_atoms))
+        check(self.L.brawl_cuda_set_lattice(self.h, first_replica, n, _p(a)))
+
+    def get_lattice(self, first_replica=0, n=1, out=None):
+        a = np.empty((n, self.n_atoms), dtype=np.uint8) if out is None else out
+        check(self.L.brawl_cuda_get_lattice(self.h, first_replica, n, _p(a)))
+        return a
+
     def random_config(self, species_count, first_replica=0, n=1, seed=0x42726157, offset=0):
         """Independent uniformly random arrangements of the species multiset for replicas [first, first+n), generated
         on the device (initial_setup / WL re-randomisation for batches, SURVEY 8f#2)."""

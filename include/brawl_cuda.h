@@ -69,6 +69,13 @@ int brawl_cuda_info(brawl_cuda_t *h, int64_t *n_atoms, int64_t *grid_bytes, int 
  * > n_species is an error. */
 int brawl_cuda_set_config(brawl_cuda_t *h, int first_replica, int n, const int8_t *grids);
 int brawl_cuda_get_config(brawl_cuda_t *h, int first_replica, int n, int8_t *grids);
+/* The same configurations as compact host buffers: sites[n][n_atoms] bytes, species 0..S-1 (NOT 1..S) in the device's
+ * site order (z slowest, then compact y, compact x: site (x, y, z) of the doubled grid -> bcc ((z*n2 + y/2)*n1 + x/2),
+ * fcc ((z*2*n2 + y)*n1 + x/2)); 1/4 (bcc) or 1/2 (fcc) of the bytes of the reference's config grid
+ * (src/shared_data.f90:30).  For drivers that keep the configuration between annealing segments / in checkpoints and
+ * share PCIe or host-memory bandwidth between many GPUs.  set_lattice fails if a byte is >= n_species. */
+int brawl_cuda_set_lattice(brawl_cuda_t *h, int first_replica, int n, const uint8_t *sites);
+int brawl_cuda_get_lattice(brawl_cuda_t *h, int first_replica, int n, uint8_t *sites);
 /* replica dst := replica src on the device (nested_sampling.f90:151 walker cloning;
  * wang-landau.F90:1475-1495 same-GPU replica exchange) */
 int brawl_cuda_copy_replica(brawl_cuda_t *h, int src, int dst);

@@ -93,6 +93,32 @@ def test_config_roundtrip_vectorised_converters(bw, orc):
 CASES = [("bcc", n) for n in range(1, 11)] + [("fcc", n) for n in range(1, 7)] + [("simple_cubic", 1), ("simple_cubic", 2)]
 
 
+def test_compact_lattice_host_buffers(bw, orc):
+    """brawl_cuda_set_lattice / get_lattice: the compact host form (1 B per atom, species 0..S-1, device site order) is
+    the reference's config grid without the empty cells, in the same z, y, x order -- bcc, fcc and sc, several replicas;
+    a species byte >= S is refused."""
+    for lattice, dims, S in (("bcc", (6, 4, 8), 4), ("fcc", (4, 6, 5), 5), ("sc", (5, 4, 3), 3)):
+        n1, n2, n3 = dims
+        sysm = orc.System(lattice, n1, n2, n3, S, 2, np.zeros(S * S * 2))
+        R = 3
+        gs = np.stack([random_config(orc, sysm, 30 + r) for r in range(R)])
+        dev = bw.Device(lattice, n1, n2, n3, S, 2, np.zeros(S * S * 2), n_replicas=R)
+        dev.set_config(gs)
+        lat = dev.get_lattice(0, R)
+        assert lat.shape == (R, sysm.n_atoms)
+        for r in range(R):
+            assert np.array_equal(lat[r], gs[r][gs[r] > 0].astype(np.uint8) - 1)
+        rolled = np.ascontiguousarray(lat[::-1])
+        dev.set_lattice(rolled)
+        assert np.array_equal(dev.get_config(0, R), gs[::-1])
+        dev.set_lattice(lat[1], first_replica=2, n=1)
+        assert np.array_equal(dev.get_config(2, 1), gs[1])
+        bad = lat[0].copy()
+        bad[sysm.n_atoms // 2] = S
+        with pytest.raises(bw.BrawlCudaError):
+            dev.set_lattice(bad, first_replica=0, n=1)
+
+
 @pytest.mark.parametrize("lattice,shells", CASES)
 def test_site_and_total_energy_bit_exact(bw, orc, lattice, shells):
     """nbr_energy on every site and total_energy in reference order: bit-exact (incl. the buggy

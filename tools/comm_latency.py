@@ -26,7 +26,8 @@ dev.wl_init(512, np.linspace(-1.0, 0.0, 513), 16)
 a = np.arange(129.0)
 for name, fn in (("comm_allgather(129)", lambda: dev.comm_allgather(a)), ("comm_allreduce(16)", lambda: dev.comm_allreduce(a[:16])),
                  ("wl_allgather_lng(8x512)", lambda: dev.wl_allgather_lng(world)),
-                 ("exchange_replica", lambda: dev.exchange_replica(3, 1 - rank) or dev.synchronize())):
+                 ("exchange_replica(rank^1)", lambda: dev.exchange_replica(3, rank ^ 1) or dev.synchronize()),
+                 ("exchange_replicas(ring)", lambda: dev.exchange_replicas([3, 4], [(rank + 1) % world, (rank - 1) % world]) or dev.synchronize())):
     for _ in range(5):
         fn()
     dist.barrier()
