@@ -639,7 +639,7 @@ static int brw_walker_prepare(const BrwGeom &g, int extra_doubles, K kernel, Brw
 
 // Site-energy table of the epoch kernels (epoch_metropolis.cuh, epoch_byte_metropolis.cuh): X_n[a][s] = V_n(a, s) - V_n(a, 4) -
 // (V_n(4, s) - V_n(4, 4)) for the species a of a cache row (S = 5; V_n(a, s) - V_n(3, s) for S = 4, plain V_n(a, s) below),
-// rounded to 2^-k units and split into three signed 8-bit digits.  |h - real| <= Z/2 units per cached value, four values per
+// rounded to fixed-point units (fix_scale) and split into three signed 8-bit digits.  |h - real| <= Z/2 units per cached value, four values per
 // dE  =>  guard = 2 Z units (+ the f64 rounding slack against the reference association).  S <= 4: all four counts are
 // explicit, energies relative to species 3 (its row is identically zero and not computed).
 static void brw_epoch_tables(const brawl_cuda_ctx *h, BrwBoxParams &p, double umax) {
@@ -658,10 +658,13 @@ static void brw_epoch_tables(const brawl_cuda_ctx *h, BrwBoxParams &p, double um
     xmax = std::max(xmax, std::fabs(X(n, a, s2)));
   for (int i = 0; i < S * S * NSH; i++) vmax = std::max(vmax, std::fabs(h->hV[i]));
   if (umax <= 0.0) umax = 2.0 * vmax;
-  int kx = 0;
-  if (xmax > 0.0) kx = (int)std::floor(std::log2(std::ldexp(1.0, 22) / xmax));
-  p.fix_scale = std::ldexp(1.0, -kx);
+  // unit of the fixed-point table: the largest entry maps to 8.3e6 (three signed 8-bit digits reach 127 * 65793 = 8.36e6),
+  // or less where four cached values of up to Z * that could overflow the int32 dE
+  const double top = std::min(8.3e6, 0.99 * 2147483647.0 / (4.0 * g.ztot));
+  const double inv_unit = xmax > 0.0 ? top / xmax : 1.0;
+  p.fix_scale = 1.0 / inv_unit;
   p.guard = 2.0 * g.ztot * p.fix_scale + 1e-9 * g.ztot * umax;
+  p.guard2 = 1e-9 * g.ztot * vmax;                   // f64 count-based dE vs the reference association: rounding ~1e-16 * Z * max|V|
   p.gfix = (int)std::ceil(p.guard / p.fix_scale) + 1;
   std::memset(p.xdig, 0, sizeof p.xdig);
   for (int c = 0; c < 4; c++) {
@@ -669,7 +672,7 @@ static void brw_epoch_tables(const brawl_cuda_ctx *h, BrwBoxParams &p, double um
     if (a >= S || c >= p.h_rows) continue;
     for (int n = 0; n < NSH; n++)
       for (int s2 = 0; s2 < std::min(S, 4); s2++) {
-        long long v = std::llrint(std::ldexp(X(n, a, s2), kx));
+        long long v = std::llrint(X(n, a, s2) * inv_unit);
         for (int k = 0; k < 3; k++) {
           long long dgt = k == 2 ? v : ((v + 128) & 255) - 128;
           v = (v - dgt) >> 8;

@@ -23,10 +23,40 @@ template <int K> struct __align__(16) BrwByteEpochT {
   uint32_t pad;
 };
 
-// reference association for one trial (rare in the screened kernel): one copy per instantiation, not per unrolled step
-template <int LAT, int NSH, int PX, int PY>
-__device__ __noinline__ double brw_byte_exact_dE(const uint8_t *box, const char *Vl, int S, int c1, int c2, int par1, int par2,
-                                                 int sa, int sb) {
+// The decision of a trial that the cached fixed-point energies cannot take with certainty (~1e-5 of the trials).  1. second screening level: f64 dE from the exact integer counts of both
+// sites; outside its guard band (guard2 = 1e-9 Z max|V|, propagated through exp) the decision is the reference's.
+// 2. inside, or always when EXACT: the reference association (brw_fast_shells: sequential per shell, shells left to right).
+template <int LAT, int NSH, int PX, int PY, bool EXACT>
+__device__ __forceinline__ bool brw_byte_decide_cold(const uint8_t *box, const char *Vl, int S, int c1, int c2, int par1, int par2,
+                                                  int sa, int sb, uint32_t rw, double my_beta, double guard2, double *dE_out) {
+  const double u = brw_u01(rw);
+  double dE = 0.0;
+  if (!EXACT) {
+    const uint32_t box_s = (uint32_t)__cvta_generic_to_shared(box);
+    uint32_t C1[NSH], C2[NSH];
+    if (par1) brw_count_shells<LAT, NSH, PX, PY, 1, 0>(box_s + c1, C1); else brw_count_shells<LAT, NSH, PX, PY, 0, 0>(box_s + c1, C1);
+    if (par2) brw_count_shells<LAT, NSH, PX, PY, 1, 0>(box_s + c2, C2); else brw_count_shells<LAT, NSH, PX, PY, 0, 0>(box_s + c2, C2);
+#pragma unroll
+    for (int n = 0; n < NSH; n++) {
+      const double *Va = reinterpret_cast<const double *>(Vl + ((n * S + sa) * S) * 128);
+      const double *Vb = reinterpret_cast<const double *>(Vl + ((n * S + sb) * S) * 128);
+      int rest = 0;
+#pragma unroll
+      for (int sp = 0; sp < 4; sp++) {
+        if (sp < S) {
+          const int d = (int)((C1[n] >> (8 * sp)) & 255u) - (int)((C2[n] >> (8 * sp)) & 255u);
+          rest -= d;
+          dE = fma((double)d, Vb[sp * 16] - Va[sp * 16], dE);
+        }
+      }
+      if (S == 5) dE = fma((double)rest, Vb[4 * 16] - Va[4 * 16], dE);
+    }
+    if (fabs(dE) > guard2) {
+      if (dE < 0.0) { *dE_out = dE; return true; }
+      const double t = exp(-my_beta * dE);
+      if (fabs(u - t) > t * (my_beta * guard2 + 1e-12)) { *dE_out = dE; return u < t; }
+    }
+  }
   double E1a, E1b, E2b, E2a;
   if (par1) brw_fast_shells<LAT, NSH, PX, PY, 1, 0>(box + c1, Vl, S, sa, sb, E1a, E1b);
   else brw_fast_shells<LAT, NSH, PX, PY, 0, 0>(box + c1, Vl, S, sa, sb, E1a, E1b);
@@ -34,7 +64,11 @@ __device__ __noinline__ double brw_byte_exact_dE(const uint8_t *box, const char 
   else brw_fast_shells<LAT, NSH, PX, PY, 0, 0>(box + c2, Vl, S, sb, sa, E2b, E2a);
   const double before = __dadd_rn(E1a, E2b);           // pair_energy, sites unswapped
   const double after = __dadd_rn(E1b, E2a);            // pair_energy, sites swapped
-  return __dsub_rn(after, before);                     // src/metropolis.F90:792
+  dE = __dsub_rn(after, before);                       // src/metropolis.F90:792
+  bool accept = dE < 0.0;                              // :796
+  if (!accept) accept = u < exp(-my_beta * dE);        // :802
+  *dE_out = dE;
+  return accept;
 }
 
 template <int LAT, int NSH, int PX, int PY, bool EXACT, int K, int MAXT>
@@ -93,7 +127,7 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_byte_epoch_kernel(
   const uint32_t box_s = (uint32_t)__cvta_generic_to_shared(box);
   const int S = g.S;
   const float c0 = (float)(-beta[replica] * 1.4426950408889634 * p.fix_scale);
-  const float bandf = (float)(beta[replica] * p.guard) + 4e-5f;
+  const float bandf = (float)(beta[replica] * p.guard) + 6e-6f;
   const int gfix = p.gfix;
   const int warp = tid >> 5, lane = tid & 31;
   const int n_lanes = min(32, md.M - 32 * warp);                          // coarse cells held by this warp (<= 0: none)
@@ -165,10 +199,11 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_byte_epoch_kernel(
             } else fast = false;
           }
           if (!fast) {
+            // ~1e-5 of the trials: second screening level in f64, then the reference association
             efix = 0;
-            const double dE = brw_byte_exact_dE<LAT, NSH, PX, PY>(box, Vl, S, c1, c2, E.q.par1, E.q.par2, a >> 3, b >> 3);
-            accept = dE < 0.0;                                             // :796
-            if (!accept) accept = brw_u01(rw) < exp(-beta[replica] * dE);  // :802
+            double dE;
+            accept = brw_byte_decide_cold<LAT, NSH, PX, PY, EXACT>(box, Vl, S, c1, c2, E.q.par1, E.q.par2, a >> 3, b >> 3, rw,
+                                                                   beta[replica], p.guard2, &dE);
             if (accept) atomicAdd(&red[warp], dE);
           }
           if (accept) {

@@ -118,6 +118,78 @@ __device__ __forceinline__ void brw_sts32(uint32_t a, int v) { asm volatile("st.
 
 // signed 8-bit digits of the fixed-point site-energy table (kernel parameter: read straight from the constant bank)
 #define BRW_HLIMB 3
+#ifndef BRW_EXP
+#define BRW_EXP 0       // timing experiments only (results invalid): bit 0 never takes the reference-association path,
+#endif                  // bit 1 replaces the per-epoch CTA barrier by a warp barrier
+
+// The decision of a trial that the cached fixed-point energies cannot take with certainty (~1e-5 of the trials).  Inlined:
+// as a __noinline__ call it was 6 % slower (call ABI in the step loop); a build that never takes this path at all (invalid
+// results) is 8 % faster still -- tools/xp_run.py.
+//  1. second screening level: dE in f64 from the exact integer neighbour counts of the two sites,
+//     dE = sum_n sum_s (c1 - c2)[n][s] (V_n(b, s) - V_n(a, s)) -- the reference's value up to f64 rounding (~1e-16 Z max|V|).
+//     Outside its own guard band (guard2 = 1e-9 Z max|V|, and the same band propagated through exp) the decision is the
+//     reference's;
+//  2. inside (~1e-9 of the trials), or always when EXACT: the reference association (src/bw_hamiltonian.f90:171-173,
+//     :1014-1017, :111-112; src/metropolis.F90:792-802), generic loop.
+template <int NSH, int PXP, int PLP, bool EXACT>
+__device__ __forceinline__ bool brw_epoch_decide_cold(const uint32_t *w1, const uint32_t *w2, int flags, uint32_t wa, uint32_t wb,
+                                                   uint32_t rw, double my_beta, const double *Vs, const int *off, int S, int ztot,
+                                                   int4 shell_end, double guard2, double *dE_out) {
+  const double u = brw_u01(rw);
+  const int sa = brw_code_species(brw_pair_code(wa)), sb2 = brw_code_species(brw_pair_code(wb));
+  bool accept = false;
+  double dE = 0.0;
+  if (!EXACT) {
+    uint32_t C1[NSH], C2[NSH];
+    if (flags & 1) BrwPairGatherBcc<NSH, PXP, PLP, 1>::run(w1, C1); else BrwPairGatherBcc<NSH, PXP, PLP, 0>::run(w1, C1);
+    if (flags & 2) BrwPairGatherBcc<NSH, PXP, PLP, 1>::run(w2, C2); else BrwPairGatherBcc<NSH, PXP, PLP, 0>::run(w2, C2);
+#pragma unroll
+    for (int n = 0; n < NSH; n++) {
+      const double *Vn = Vs + n * S * S;
+      int rest = 0;
+#pragma unroll
+      for (int s2 = 0; s2 < 4; s2++) {
+        if (s2 < S) {
+          const int d = (int)((C1[n] >> (8 * s2)) & 255u) - (int)((C2[n] >> (8 * s2)) & 255u);
+          rest -= d;
+          dE = fma((double)d, Vn[s2 * S + sb2] - Vn[s2 * S + sa], dE);
+        }
+      }
+      if (S == 5) dE = fma((double)rest, Vn[4 * S + sb2] - Vn[4 * S + sa], dE);
+    }
+    if (fabs(dE) > guard2) {
+      if (dE < 0.0) { *dE_out = dE; return true; }
+      const double t = exp(-my_beta * dE);
+      if (fabs(u - t) > t * (my_beta * guard2 + 1e-12)) { *dE_out = dE; return u < t; }
+    }
+  }
+  const int *off1 = off + (flags & 1) * ztot, *off2 = off + ((flags >> 1) & 1) * ztot;
+  const int ends[4] = {shell_end.x, shell_end.y, shell_end.z, shell_end.w};
+  double E1a = 0.0, E1b = 0.0, E2b = 0.0, E2a = 0.0;
+  int k = 0;
+#pragma unroll 1
+  for (int n = 0; n < NSH; n++) {
+    double e1a = 0.0, e1b = 0.0, e2b = 0.0, e2a = 0.0;
+    const double *Vn = Vs + n * S * S;
+    const int end = n == 0 ? ends[0] : n == 1 ? ends[1] : n == 2 ? ends[2] : ends[3];
+#pragma unroll 1
+    for (; k < end; k++) {
+      const int s1 = brw_code_species(brw_pair_code(brw_lo16(w1 + off1[k])));
+      const int s2 = brw_code_species(brw_pair_code(brw_lo16(w2 + off2[k])));
+      e1a = __dadd_rn(e1a, Vn[s1 * S + sa]); e1b = __dadd_rn(e1b, Vn[s1 * S + sb2]);
+      e2b = __dadd_rn(e2b, Vn[s2 * S + sb2]); e2a = __dadd_rn(e2a, Vn[s2 * S + sa]);
+    }
+    if (n == 0) { E1a = e1a; E1b = e1b; E2b = e2b; E2a = e2a; }
+    else { E1a = __dadd_rn(E1a, e1a); E1b = __dadd_rn(E1b, e1b); E2b = __dadd_rn(E2b, e2b); E2a = __dadd_rn(E2a, e2a); }
+  }
+  const double before = __dadd_rn(E1a, E2b);             // pair_energy, sites unswapped
+  const double after = __dadd_rn(E1b, E2a);              // pair_energy, sites swapped
+  dE = __dsub_rn(after, before);                         // src/metropolis.F90:792
+  accept = dE < 0.0;                                     // :796
+  if (!accept) accept = u < exp(-my_beta * dE);          // :802
+  *dE_out = dE;
+  return accept;
+}
 
 template <int NSH, int PX, int PY, int PZ, int MARGIN, int PXP, int PLP, int NLIMB, bool EXACT, int K>
 __global__ void __launch_bounds__(1024) brw_box_metropolis_epoch_kernel(
@@ -176,10 +248,12 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_epoch_kernel(
   brw_pbox_copy<PX, PY, PXP, PLP, MARGIN / 2, false>(g, L, wbox, 0, PY * PZ, ox, oy, oz);
   __syncthreads();
 
-  // fast acceptance test in f32: x = efix * c0 (two roundings, |x| <= 126: < 2e-5 relative in 2^x), ex2.approx (2^-22),
-  // u from the top 23 bits of the Philox word (< 1.2e-7 absolute), plus the dE guard propagated through exp
+  // fast acceptance test in f32: t = ex2.approx(x), x = fl(fl(efix) * c0): three roundings, |dx| <= 1.8e-7 |x|.  For |x| <= 32
+  // that is < 4e-6 relative in t, plus 2^-22 of ex2.approx: band 6e-6 t (+ the dE guard propagated through exp); for
+  // |x| > 32, t < 2.4e-10 and any relative error of t disappears in the absolute term 2.5e-7, which also covers u taken
+  // from the top 23 bits of the Philox word (< 1.2e-7) and the rounding of u - t (< 6e-8)
   const float c0 = (float)(-beta[replica] * 1.4426950408889634 * p.fix_scale);
-  const float bandf = (float)(beta[replica] * p.guard) + 4e-5f;
+  const float bandf = (float)(beta[replica] * p.guard) + 6e-6f;
   const int gfix = p.gfix;                                                // guard band in fixed-point units
   long long efix_sum = 0;                                                 // accepted fixed-point dE (exact)
   const int warp = tid >> 5, lane = tid & 31;
@@ -259,36 +333,14 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_epoch_kernel(
               fast = fabsf(d) > fmaf(t, bandf, 2.5e-7f);
             } else fast = false;
           }
+          if ((BRW_EXP & 1) && !EXACT) fast = true;
           if (!fast) {
-            // reference association, generic loop (screened kernel: ~1e-4 of the trials)
+            // ~1e-5 of the trials: second screening level in f64, then the reference association
             efix = 0;
-            const double my_beta = beta[replica];
-            const double u = brw_u01(rw);
-            const int sa = brw_code_species(brw_pair_code(wa)), sb2 = brw_code_species(brw_pair_code(wb));
-            const int S = g.S;
-            const int *off1 = off + (flags & 1) * g.ztot, *off2 = off + ((flags >> 1) & 1) * g.ztot;
-            double E1a = 0.0, E1b = 0.0, E2b = 0.0, E2a = 0.0;
-            int k = 0;
-#pragma unroll 1
-            for (int n = 0; n < NSH; n++) {
-              double e1a = 0.0, e1b = 0.0, e2b = 0.0, e2a = 0.0;
-              const double *Vn = Vs + n * S * S;
-              const int end = g.shell_end[n];
-#pragma unroll 1
-              for (; k < end; k++) {
-                const int s1 = brw_code_species(brw_pair_code(brw_lo16(w1 + off1[k])));
-                const int s2 = brw_code_species(brw_pair_code(brw_lo16(w2 + off2[k])));
-                e1a = __dadd_rn(e1a, Vn[s1 * S + sa]); e1b = __dadd_rn(e1b, Vn[s1 * S + sb2]);
-                e2b = __dadd_rn(e2b, Vn[s2 * S + sb2]); e2a = __dadd_rn(e2a, Vn[s2 * S + sa]);
-              }
-              if (n == 0) { E1a = e1a; E1b = e1b; E2b = e2b; E2a = e2a; }
-              else { E1a = __dadd_rn(E1a, e1a); E1b = __dadd_rn(E1b, e1b); E2b = __dadd_rn(E2b, e2b); E2a = __dadd_rn(E2a, e2a); }
-            }
-            const double before = __dadd_rn(E1a, E2b);             // pair_energy, sites unswapped
-            const double after = __dadd_rn(E1b, E2a);              // pair_energy, sites swapped
-            const double dE = __dsub_rn(after, before);            // src/metropolis.F90:792
-            accept = dE < 0.0;                                     // :796
-            if (!accept) accept = u < exp(-my_beta * dE);          // :802
+            double dE;
+            accept = brw_epoch_decide_cold<NSH, PXP, PLP, EXACT>(w1, w2, flags, wa, wb, rw, beta[replica], Vs, off, g.S, g.ztot,
+                                                                 make_int4(g.shell_end[0], g.shell_end[1], g.shell_end[2], g.shell_end[3]),
+                                                                 p.guard2, &dE);
             if (accept) atomicAdd(&red[warp], dE);
           }
           if (accept) {
@@ -304,7 +356,7 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_epoch_kernel(
       }
       __syncwarp();
     }
-    __syncthreads();
+    if (BRW_EXP & 2) __syncwarp(); else __syncthreads();
   }
 
   // frozen margin planes are unchanged (and shared with the neighbouring box in z): not stored

@@ -32,6 +32,7 @@ struct BrwBoxMode {            // one orientation of the (rectangular) period, s
 };
 struct BrwBoxParams {          // POD kernel parameter
   double guard;                // screening guard band on dE (Ry); see brw_box_metropolis_fast_kernel
+  double guard2;               // epoch kernels: guard band of the f64 count-based dE (second screening level), 1e-9 * Z * max|V|
   double fix_scale;            // word kernel: 2^-k, the unit of its fixed-point dE (word_metropolis.cuh)
   int m;
   int B[3], nb[3];

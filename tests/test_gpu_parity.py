@@ -97,7 +97,7 @@ def test_compact_lattice_host_buffers(bw, orc):
     """brawl_cuda_set_lattice / get_lattice: the compact host form (1 B per atom, species 0..S-1, device site order) is
     the reference's config grid without the empty cells, in the same z, y, x order -- bcc, fcc and sc, several replicas;
     a species byte >= S is refused."""
-    for lattice, dims, S in (("bcc", (6, 4, 8), 4), ("fcc", (4, 6, 5), 5), ("sc", (5, 4, 3), 3)):
+    for lattice, dims, S in (("bcc", (6, 4, 8), 4), ("fcc", (4, 6, 5), 5), ("simple_cubic", (5, 4, 3), 3)):
         n1, n2, n3 = dims
         sysm = orc.System(lattice, n1, n2, n3, S, 2, np.zeros(S * S * 2))
         R = 3
