@@ -23,6 +23,21 @@ template <int K> struct __align__(16) BrwByteEpochT {
   uint32_t pad;
 };
 
+// reference association for one trial (~1e-9 of the trials of the screened kernel): one out-of-line copy per instantiation,
+// not one per unrolled step -- inlined, the unrolled chains bloat the step loop (measured: -20 %)
+template <int LAT, int NSH, int PX, int PY>
+__device__ __noinline__ double brw_byte_exact_dE(const uint8_t *box, const char *Vl, int S, int c1, int c2, int par1, int par2,
+                                                 int sa, int sb) {
+  double E1a, E1b, E2b, E2a;
+  if (par1) brw_fast_shells<LAT, NSH, PX, PY, 1, 0>(box + c1, Vl, S, sa, sb, E1a, E1b);
+  else brw_fast_shells<LAT, NSH, PX, PY, 0, 0>(box + c1, Vl, S, sa, sb, E1a, E1b);
+  if (par2) brw_fast_shells<LAT, NSH, PX, PY, 1, 0>(box + c2, Vl, S, sb, sa, E2b, E2a);
+  else brw_fast_shells<LAT, NSH, PX, PY, 0, 0>(box + c2, Vl, S, sb, sa, E2b, E2a);
+  const double before = __dadd_rn(E1a, E2b);           // pair_energy, sites unswapped
+  const double after = __dadd_rn(E1b, E2a);            // pair_energy, sites swapped
+  return __dsub_rn(after, before);                     // src/metropolis.F90:792
+}
+
 // The decision of a trial that the cached fixed-point energies cannot take with certainty (~1e-5 of the trials).  1. second screening level: f64 dE from the exact integer counts of both
 // sites; outside its guard band (guard2 = 1e-9 Z max|V|, propagated through exp) the decision is the reference's.
 // 2. inside, or always when EXACT: the reference association (brw_fast_shells: sequential per shell, shells left to right).
@@ -57,14 +72,7 @@ __device__ __forceinline__ bool brw_byte_decide_cold(const uint8_t *box, const c
       if (fabs(u - t) > t * (my_beta * guard2 + 1e-12)) { *dE_out = dE; return u < t; }
     }
   }
-  double E1a, E1b, E2b, E2a;
-  if (par1) brw_fast_shells<LAT, NSH, PX, PY, 1, 0>(box + c1, Vl, S, sa, sb, E1a, E1b);
-  else brw_fast_shells<LAT, NSH, PX, PY, 0, 0>(box + c1, Vl, S, sa, sb, E1a, E1b);
-  if (par2) brw_fast_shells<LAT, NSH, PX, PY, 1, 0>(box + c2, Vl, S, sb, sa, E2b, E2a);
-  else brw_fast_shells<LAT, NSH, PX, PY, 0, 0>(box + c2, Vl, S, sb, sa, E2b, E2a);
-  const double before = __dadd_rn(E1a, E2b);           // pair_energy, sites unswapped
-  const double after = __dadd_rn(E1b, E2a);            // pair_energy, sites swapped
-  dE = __dsub_rn(after, before);                       // src/metropolis.F90:792
+  dE = brw_byte_exact_dE<LAT, NSH, PX, PY>(box, Vl, S, c1, c2, par1, par2, sa, sb);
   bool accept = dE < 0.0;                              // :796
   if (!accept) accept = u < exp(-my_beta * dE);        // :802
   *dE_out = dE;
@@ -119,6 +127,9 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_byte_epoch_kernel(
     const int ci = tid % A0, cr = tid / A0, cj = cr % A1, ck = cr / A1;
     if (tid < MAXT) base_tab[tid] = ci * stx + cj * sty + ck * stz;
   }
+  // programmatic dependent launch (see epoch_metropolis.cuh): the table set-up above overlaps the previous phase's tail
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
   brw_box_copy<LAT, PX, PY, false>(g, L, box, PY * p.bzc, ox, oy, oz);
   if (tid < 32) red[tid] = 0.0;
   __syncthreads();

@@ -90,7 +90,7 @@ __device__ __forceinline__ void brw_pbox_copy(const BrwGeom &g, uint8_t *L, uint
   int gx1 = gx0 + 32; if (gx1 >= g.cx) gx1 -= g.cx; if (gx1 >= g.cx) gx1 -= g.cx;
   // CTAs of PY warps: warp w always copies compact-y row w of a plane, the plane index advances by one per iteration
   const bool row_per_warp = nwarps == PY && row_begin % PY == 0;
-#pragma unroll 4
+#pragma unroll 8
   for (int r = row_begin + warp; r < row_end; r += nwarps) {
     const int lyc = row_per_warp ? warp : r % PY, lz = row_per_warp ? (r - warp) / PY : r / PY;
     int gzz = oz + lz; if (gzz >= g.gz) gzz -= g.gz; if (gzz >= g.gz) gzz -= g.gz;
@@ -116,11 +116,30 @@ __device__ __forceinline__ void brw_pbox_copy(const BrwGeom &g, uint8_t *L, uint
 __device__ __forceinline__ int brw_lds32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void brw_sts32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
+// split-phase CTA barrier (mbarrier in shared memory): a warp ARRIVES when its epoch is done, prepares what the next epoch
+// needs that no other warp can change (epoch parameters, addresses, the Philox draw), then WAITS for the other warps
+#ifndef BRW_SPLITBAR
+#define BRW_SPLITBAR 1
+#endif
+__device__ __forceinline__ void brw_mbar_init(uint32_t a, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void brw_mbar_arrive(uint32_t a) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void brw_mbar_wait(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+
 // signed 8-bit digits of the fixed-point site-energy table (kernel parameter: read straight from the constant bank)
 #define BRW_HLIMB 3
 #ifndef BRW_EXP
-#define BRW_EXP 0       // timing experiments only (results invalid): bit 0 never takes the reference-association path,
-#endif                  // bit 1 replaces the per-epoch CTA barrier by a warp barrier
+#define BRW_EXP 0       // timing experiment only (results invalid): bit 0 never takes the reference-association path
+#endif
 
 // The decision of a trial that the cached fixed-point energies cannot take with certainty (~1e-5 of the trials).  Inlined:
 // as a __noinline__ call it was 6 % slower (call ABI in the step loop); a build that never takes this path at all (invalid
@@ -218,12 +237,15 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_epoch_kernel(
   int *hcache = reinterpret_cast<int *>(ep + n_epochs);                       // [32 warps][2][5][32]
   uint32_t *wbox = reinterpret_cast<uint32_t *>(hcache + 32 * 320);           // [PZ][PLP]
   __shared__ unsigned int s_att[32], s_acc[32];
+  __shared__ __align__(8) unsigned long long s_mbar;
 
   const int tid = threadIdx.x;
   const int replica = blockIdx.x / p.boxes_per_replica;
   const int bid = blockIdx.x - replica * p.boxes_per_replica;
   const int bi = bid % p.nb[0], bj = (bid / p.nb[0]) % p.nb[1], bk = bid / (p.nb[0] * p.nb[1]);
   uint8_t *L = lat + (long)replica * g.n_sites;
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+  if (BRW_SPLITBAR && tid == 0) brw_mbar_init(mbar, blockDim.x >> 5);       // one arrival per warp and epoch
 
   BrwPhilox4 ro = brw_philox(0xFFFFFFFEu, 0u, (uint32_t)replica, phase_lo, k0, k1);
   const int ox = 2 * (int)brw_below(ro.x, g.gx >> 1) + bi * p.B[0];
@@ -245,6 +267,11 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_epoch_kernel(
     hcache[(i >> 5) * 160 + (i & 31)] = 0;                                                         // row 0 = species 4
     hcache[(i >> 5) * 160 + 128 + (i & 31)] = 0;                                                   // row 4 = species 3: the reference species when S <= 4
   }
+  // programmatic dependent launch: everything above reads constant tables only and may overlap the tail of the previous
+  // phase's grid (a CTA of this grid starts as soon as an SM frees up); the lattice is read after the previous grid has
+  // completed and flushed.  The next phase may be scheduled from now on (it waits at the same point).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
   brw_pbox_copy<PX, PY, PXP, PLP, MARGIN / 2, false>(g, L, wbox, 0, PY * PZ, ox, oy, oz);
   __syncthreads();
 
@@ -265,18 +292,30 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_epoch_kernel(
   if (tid < 32) red[tid] = 0.0;                                           // sum of accepted dE of the reference-association path
   __syncthreads();
 
-  for (int e = 0; e < n_epochs; e++) {
-    const Ep E = ep[e];
-    const int flags = E.flags;
-    uint32_t *w1 = wbox, *row2 = wbox;
-    uint32_t wa = 0, ra = 0;
-    // home sites: slot = lane; slots [0, NI) = sub-class A (even word addresses), [NI, 2 NI) = sub-class B (odd)
-    const int c2A = E.c2[0], c2B = E.c2[1] - 2 * G::NI;
+  // the part of an epoch's set-up that does not read the lattice: done for epoch e + 1 between the arrival at the epoch
+  // barrier and the wait (BRW_SPLITBAR), so that it overlaps the wait for the slowest warp
+  Ep E = ep[0];
+  uint32_t *w1 = wbox, *row2 = wbox;
+  const uint32_t *w2h = wbox;
+  auto prepare = [&](int e) {
+    E = ep[e];
     if (active) {
       const int sub = lane >= G::NI ? 1 : 0;
       row2 = wbox + rowoff[warp + (E.rot >> 16)];
       w1 = wbox + (sub ? E.c1[1] - 2 * G::NI : E.c1[0]) + 2 * lane + rowoff[warp + (E.rot & 0xFFFF)];
-      const uint32_t *w2h = row2 + (sub ? c2B : c2A) + 2 * lane;
+      w2h = row2 + (sub ? E.c2[1] - 2 * G::NI : E.c2[0]) + 2 * lane;
+      if (K >= 4 || (e & 1) == 0) rnd = brw_philox((uint32_t)tid, (uint32_t)((e * K) >> 2), box_id, phase_lo, k0, k1);
+    }
+  };
+  prepare(0);
+
+  for (int e = 0; e < n_epochs; e++) {
+    const int flags = E.flags;
+    uint32_t wa = 0, ra = 0;
+    // home sites: slot = lane; slots [0, NI) = sub-class A (even word addresses), [NI, 2 NI) = sub-class B (odd)
+    const int c2A = E.c2[0], c2B = E.c2[1] - 2 * G::NI;
+    const uint32_t sw0 = E.sw[0], sw1 = E.sw[1];
+    if (active) {
       wa = *w1 & 0xFFFFu;
       ra = ((wa * 0x1234u) >> 5) & 0x380u;
       if (!EXACT) {
@@ -310,11 +349,11 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_epoch_kernel(
       const int gs = K >= 4 ? j : ((e & 1) * 2 + j);            // step index mod 4 (compile-time for K = 4, 8)
       if (active) {
         // partner = home site 2 of slot (lane + shift) mod 2 NI of this warp's row pair
-        int slot2 = lane + (int)((E.sw[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+        int slot2 = lane + (int)(((j >> 2 ? sw1 : sw0) >> (8 * (j & 3))) & 0xFFu);
         if (slot2 >= 2 * G::NI) slot2 -= 2 * G::NI;
         uint32_t *w2 = row2 + (slot2 >= G::NI ? c2B : c2A) + 2 * slot2;
         const uint32_t wb = *w2 & 0xFFFFu;
-        if ((gs & 3) == 0) rnd = brw_philox((uint32_t)tid, (uint32_t)((e * K + j) >> 2), box_id, phase_lo, k0, k1);
+        if ((gs & 3) == 0 && j > 0) rnd = brw_philox((uint32_t)tid, (uint32_t)((e * K + j) >> 2), box_id, phase_lo, k0, k1);
         const uint32_t rw = (gs & 3) == 0 ? rnd.x : (gs & 3) == 1 ? rnd.y : (gs & 3) == 2 ? rnd.z : rnd.w;
         n_acc += wa == wb;                                          // :774-777
         if (wa != wb) {
@@ -356,7 +395,14 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_epoch_kernel(
       }
       __syncwarp();
     }
-    if (BRW_EXP & 2) __syncwarp(); else __syncthreads();
+    if (BRW_SPLITBAR) {
+      if (lane == 0) brw_mbar_arrive(mbar);                  // the __syncwarp above ordered the warp's stores before it
+      if (e + 1 < n_epochs) prepare(e + 1);
+      brw_mbar_wait(mbar, (uint32_t)(e & 1));
+    } else {
+      __syncthreads();
+      if (e + 1 < n_epochs) prepare(e + 1);
+    }
   }
 
   // frozen margin planes are unchanged (and shared with the neighbouring box in z): not stored

@@ -65,6 +65,7 @@ struct BrwPlan {
   void *fast_fn = nullptr;     // specialised kernel for this (lattice, shells, pitch), if instantiated
   bool screened = false;
   bool split = false;          // word kernel with two warp groups per CTA and shared z margin planes
+  bool pdl = false;            // fast_fn synchronises with the previous grid itself (griddepcontrol.wait): programmatic dependent launch
   bool byte_epoch = false;     // fast_fn is a byte-lattice epoch kernel (epoch_byte_metropolis.cuh)
   bool word = false;           // fast_fn is a word-lattice kernel (word_metropolis.cuh); d_Vrep holds its table blob
   size_t fast_smem = 0;
