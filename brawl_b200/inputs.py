@@ -85,7 +85,11 @@ def species_quotas(p):
     S, N = p["n_species"], n_atoms(p)
     conc = list(p.get("species_concentrations", [0.0] * (S + 1)))
     numbers = p.get("species_numbers")
-    if numbers is not None and sum(numbers) == N:
+    if numbers is not None and sum(numbers) != N:
+        # the reference falls through to the concentration branch with all-zero concentrations and never leaves its
+        # redistribution loop (src/initialise.F90:468-506): refuse instead
+        raise BrawlCudaError("species_numbers sum to %d, the lattice has %d sites" % (sum(numbers), N))
+    if numbers is not None:
         count = list(numbers)
         conc = [0.0] + [float(np.float32(c) / np.float32(N)) for c in count]
     else:
@@ -93,6 +97,8 @@ def species_quotas(p):
         count = [nint(float(np.float32(N)) * conc[i + 1]) for i in range(S)]
         chk = sum(count) - N
         inc = -1 if chk > 0 else 1
+        if chk != 0 and not any(count):
+            raise BrawlCudaError("species concentrations are all zero")
         while chk != 0:
             for j in range(S):
                 if count[j] == 0 or chk == 0:

@@ -75,7 +75,7 @@ class NestedSampling:
             i_max = np.argmax(self.energies, axis=1)                     # maxloc: first maximum
             lim = self.energies[np.arange(R), i_max]
             culled[:, it - 1] = lim
-            if it % int(K / 2.0) == 0:                                   # :129-144
+            if it % max(int(K / 2.0), 1) == 0:                           # :129-144 (n_walkers = 1: the reference divides by zero)
                 grow = (n_acc < self.n_at * np.float32(0.05)) & (extra < p.n_steps * 100)
                 extra[grow] += p.n_steps
             irnd = np.maximum(np.ceil(self.rng.random(R) * K).astype(np.int64), 1)     # :149-150

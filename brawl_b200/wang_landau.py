@@ -126,11 +126,10 @@ def dos_combine(lng_windows, window_indices):
 
 def _seq_sum(v):
     """Fortran SUM of a short f64 array as gfortran evaluates it without -ffast-math: left to right
-    (Python's built-in sum() is compensated since 3.12 and numpy's is pairwise, so neither is used)."""
-    t = 0.0
-    for x in v:
-        t = t + float(x)
-    return t
+    (Python's built-in sum() is compensated since 3.12 and numpy's is pairwise, so neither is used;
+    np.add.accumulate IS the sequential left-to-right recurrence, 0.0 + v[0] + v[1] + ...)."""
+    v = np.asarray(v, dtype=np.float64).ravel()
+    return float(np.add.accumulate(v)[-1]) if v.size else 0.0
 
 
 def energy_bin_width(n_atoms, energy_min, energy_max, bins):

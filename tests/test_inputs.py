@@ -50,6 +50,18 @@ def test_quotas_rounding_matches_oracle(orc, golden):
         assert list(n_ref) == count and sum(count) == sysm.n_atoms
 
 
+def test_quotas_refuse_inputs_the_reference_would_hang_on():
+    """species_numbers that do not sum to the number of sites (the reference then loops for ever in its redistribution,
+    src/initialise.F90:468-506), and all-zero concentrations."""
+    from brawl_b200 import inputs, BrawlCudaError
+    base = dict(lattice="bcc", n_1=4, n_2=4, n_3=4, n_species=4)
+    assert inputs.species_quotas(dict(base, species_numbers=[32, 32, 32, 32]))[1] == [32, 32, 32, 32]
+    with pytest.raises(BrawlCudaError, match="species_numbers sum to 127"):
+        inputs.species_quotas(dict(base, species_numbers=[32, 32, 32, 31]))
+    with pytest.raises(BrawlCudaError, match="all zero"):
+        inputs.species_quotas(dict(base, species_concentrations=[0.0] * 5))
+
+
 def test_error_messages_match_the_reference(golden, tmp_path):
     from brawl_b200 import inputs, BrawlCudaError
     with pytest.raises(BrawlCudaError, match="Could not find input file"):
