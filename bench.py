@@ -404,16 +404,23 @@ def main():
                 prof = json.load(open(tp))
             except Exception:
                 prof = {}
+        kern = KERNELS[plan["use_box"]].format(k="epoch" if epoch else "word")
+        if plan["use_box"] in (6, 7):
+            # byte-lattice epoch kernels: the ncu capture of the matching geometry, if one is committed
+            key = {(6, 6, 6): "bcc_6shell", (4, 4, 6): "fcc_4shell", (4, 6, 4): "fcc_4shell", (6, 4, 4): "fcc_4shell"}.get(tuple(plan["P"]))
+            prof = prof.get("byte_epoch", {}).get(key, {}) if b_alg != 2 * 86 + 4 else {}
+        elif not epoch:
+            prof = {}
         return {
             # SURVEY 8(d) nominal figure: algorithmic bytes (2Z+4 per attempted swap) over the measured HBM copy peak.  The
-            # lattice is L2- and shared-memory-resident by design, so HBM is NOT what binds this kernel (traffic below is
+            # lattice is L2- and shared-memory-resident by design, so HBM is NOT what binds these kernels (traffic below is
             # one read + one write of the lattice per launch); what does -- measured with ncu, profiles/ -- is named in `limiter`.
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "frac_hbm_nominal": achieved / peak,
             "traffic": prof.get("dram_bytes_per_launch"),
-            "limiter": prof.get("limiter", "instruction issue (ALU + FMA pipes) with one CTA barrier per epoch"),
+            "limiter": prof.get("limiter", "not profiled for this kernel / geometry"),
             "ncu": prof.get("ncu"),
-            "kernel": KERNELS[plan["use_box"]].format(k="epoch" if epoch else "word"),
+            "kernel": kern,
             "algorithmic_bytes_per_attempt": b_alg, "attempts_per_launch": per_launch_trials,
             "ms_per_launch": per_launch_ms, "peak_source": peak_src}
 
@@ -549,8 +556,9 @@ def main():
                                    1: "integer-count screening + reference association inside the guard band "
                                       "(accept/reject decisions identical to mode 0)",
                                    2: "dense non-interacting-set decomposition, site energies cached over epochs of 4 steps, "
-                                      "fixed-point dE + f32 acceptance pre-test, reference f64 association inside the guard "
-                                      "band (accept/reject decisions identical to mode 0)"}[args.dE_mode],
+                                      "fixed-point dE + f32 acceptance pre-test; inside its guard band (~1e-5 of the trials) f64 "
+                                      "dE from the exact integer counts, inside that one's band (~1e-9) the reference f64 "
+                                      "association (accept/reject decisions identical to mode 0)"}[args.dE_mode],
                        "acceptance": acceptance,
                        # same-species attempts count as attempts but touch 2 B and no flops
                        "distinct_species_fraction": 1.0 - 1.0 / S,

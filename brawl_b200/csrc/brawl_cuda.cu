@@ -592,6 +592,9 @@ static const BrwFastEntry brw_fast_table[] = {
 };
 
 // Word-lattice kernels with the dense decomposition (word_metropolis.cuh): fixed box and margin per entry.
+#ifndef BRW_TMA_LOAD
+#define BRW_TMA_LOAD 1    // epoch kernel: box load through cp.async.bulk (A/B switch)
+#endif
 #ifndef BRW_BYTE_PDL
 #define BRW_BYTE_PDL 1    // programmatic dependent launch for the byte-lattice epoch kernels (A/B switch)
 #endif
@@ -1028,6 +1031,11 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
         pl->fast_smem = blob.size() * sizeof(int) + 32 * 8 + 2 * (size_t)p.mode[0].A[1] * p.mode[0].A[2] * 4 + 16 +
                         (size_t)(p.steps / we->epoch) * 32 + 32 * 320 * 4 + (size_t)we->plp * p.bzc * 4;
       pl->threads = 32 * std::min(32, p.mode[0].A[1] * (p.mode[0].A[2] - (we->split ? 1 : 0)));
+      p.tma_stages = 0;
+      // box load through the bulk-async copy engine (TMA): whole global x-rows of <= 128 bytes land in the storage of the
+      // pair-word rows they are expanded into (epoch_metropolis.cuh, brw_pbox_load_tma)
+      if (we->epoch && BRW_TMA_LOAD && pl->threads == 32 * we->byc && g.cx % 16 == 0 && g.cx <= 128 && g.n_sites % 16 == 0)
+        p.tma_stages = 1;
       BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)pl->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
     }
     pl->use_box = true;

@@ -140,6 +140,70 @@ __device__ __forceinline__ void brw_mbar_wait(uint32_t a, uint32_t parity) {
   } while (!ok);
 }
 
+// ---- box load through the bulk-async copy engine (TMA, cp.async.bulk) -----------------------------------------------------
+// Warp w owns compact-y row w of every plane of the box.  Each lane asks the copy engine for the whole global x-row (g.cx
+// bytes <= 128: 16-byte aligned and a multiple of 16, checked by the host) of one plane, straight INTO the storage of the
+// pair-word row it will become (136 bytes; the bytes go to its first 16-byte aligned address), all on one mbarrier per
+// warp (transaction bytes).  All 1024 row copies of a box are in flight at once and no register holds data in flight;
+// when they have landed the warp expands its rows in place -- every lane reads its bytes, then the words are written over
+// them.  The periodic wrap in y and z is resolved per row by the source address, the wrap in x by the index into the row.
+__device__ __forceinline__ void brw_mbar_expect_tx(uint32_t a, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void brw_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+template <int PX, int PY, int PZ, int PXP, int PLP>
+__device__ __forceinline__ void brw_pbox_load_tma(const BrwGeom &g, const uint8_t *L, uint32_t *wbox, unsigned long long *mbars,
+                                                  int ox, int oy, int oz) {
+  constexpr int XT = PX - 32;
+  static_assert(PXP * 4 >= 128 + 8 && (PLP * 4) % 16 == 0, "a 128-byte row fits behind the alignment gap of a pair-word row");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;           // blockDim = 32 * PY: warp = compact-y row of a plane
+  const uint32_t cx = (uint32_t)g.cx;
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(mbars + warp);
+  const uint32_t row0 = (uint32_t)__cvta_generic_to_shared(wbox + warp * PXP);      // this warp's row of plane 0
+  const uint32_t gap = (row0 & 8u);                                                 // PXP * 4 = 8 mod 16, PLP * 4 = 0 mod 16
+  int gx0 = (ox >> 1) + lane; if (gx0 >= g.cx) gx0 -= g.cx; if (gx0 >= g.cx) gx0 -= g.cx;
+  int gx1 = gx0 + 32; if (gx1 >= g.cx) gx1 -= g.cx; if (gx1 >= g.cx) gx1 -= g.cx;
+  if (lane == 0) {
+    brw_mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    brw_mbar_expect_tx(mbar, (uint32_t)PZ * cx);
+  }
+  __syncwarp();
+  for (int lz = lane; lz < PZ; lz += 32) {
+    int gzz = oz + lz; if (gzz >= g.gz) gzz -= g.gz; if (gzz >= g.gz) gzz -= g.gz;
+    int gyy = oy + 2 * warp + (lz & 1); if (gyy >= g.gy) gyy -= g.gy; if (gyy >= g.gy) gyy -= g.gy;
+    brw_bulk_g2s(row0 + (uint32_t)lz * (PLP * 4) + gap, L + ((long)gzz * g.cy + (gyy >> 1)) * g.cx, cx, mbar);
+  }
+  brw_mbar_wait(mbar, 0u);
+  const uint8_t *bytes = reinterpret_cast<const uint8_t *>(wbox + warp * PXP) + gap;
+  constexpr int CH = 8;
+  static_assert(PZ % CH == 0, "planes in chunks of eight");
+#pragma unroll 1
+  for (int base = 0; base < PZ; base += CH) {
+    uint32_t v0[CH], v1[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      const uint8_t *srow = bytes + (size_t)(base + k) * (PLP * 4);
+      v0[k] = brw_species_nibbles(srow[gx0]);
+      v1[k] = lane < XT ? brw_species_nibbles(srow[gx1]) : 0u;
+    }
+    __syncwarp();                                                          // every lane has read its bytes of these rows
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      uint32_t h0 = __shfl_down_sync(0xffffffffu, v0[k], 1);
+      const uint32_t h1 = __shfl_down_sync(0xffffffffu, v1[k], 1);       // lane XT-1 receives 0: beyond the row, never a neighbour
+      const uint32_t first1 = __shfl_sync(0xffffffffu, v1[k], 0);
+      if (lane == 31) h0 = first1;
+      uint32_t *w = wbox + (base + k) * PLP + warp * PXP;
+      w[lane] = v0[k] | (h0 << 16);
+      if (lane < XT) w[32 + lane] = v1[k] | (h1 << 16);
+    }
+  }
+}
+
 // signed 8-bit digits of the fixed-point site-energy table (kernel parameter: read straight from the constant bank)
 #define BRW_HLIMB 3
 #ifndef BRW_EXP
@@ -242,7 +306,7 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_epoch_kernel(
   int *hcache = reinterpret_cast<int *>(ep + n_epochs);                       // [32 warps][2][5][32]
   uint32_t *wbox = reinterpret_cast<uint32_t *>(hcache + 32 * 320);           // [PZ][PLP]
   __shared__ unsigned int s_att[32], s_acc[32];
-  __shared__ __align__(8) unsigned long long s_mbar;
+  __shared__ __align__(8) unsigned long long s_mbar, s_tma_bar[32];
 
   const int tid = threadIdx.x;
   const int replica = blockIdx.x / p.boxes_per_replica;
@@ -277,7 +341,8 @@ __global__ void __launch_bounds__(1024) brw_box_metropolis_epoch_kernel(
   // completed and flushed.  The next phase may be scheduled from now on (it waits at the same point).
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;");
-  brw_pbox_copy<PX, PY, PXP, PLP, MARGIN / 2, false>(g, L, wbox, 0, PY * PZ, ox, oy, oz);
+  if (p.tma_stages > 0) brw_pbox_load_tma<PX, PY, PZ, PXP, PLP>(g, L, wbox, s_tma_bar, ox, oy, oz);
+  else brw_pbox_copy<PX, PY, PXP, PLP, MARGIN / 2, false>(g, L, wbox, 0, PY * PZ, ox, oy, oz);
   __syncthreads();
 
   // fast acceptance test in f32: t = ex2.approx(x), x = fl(fl(efix) * c0): three roundings, |dx| <= 1.8e-7 |x|.  For |x| <= 32

@@ -48,6 +48,7 @@ struct BrwBoxParams {          // POD kernel parameter
   // count fields, index (shell*3 + digit)*4 + species; guard band in fixed-point units
   int xdig[72];
   int gfix;
+  int tma_stages;              // epoch kernel: 1 = box load through the bulk-async copy engine (TMA), 0 = LDG loop
   int h_rows;                  // cached rows per site: 4 (five species, relative to species 4) or 3 (relative to species 3)
 };
 

@@ -3,7 +3,8 @@
 # -> tools/xp/lib<name>.so (select with BRAWL_CUDA_LIB).  The second translation unit is compiled once and shared.
 cd "$(dirname "$0")/../brawl_b200/csrc" || exit 1
 F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
-[ -f /tmp/xp_byte_epoch.o ] && [ /tmp/xp_byte_epoch.o -nt epoch_byte_metropolis.cuh ] || nvcc $F -c -o /tmp/xp_byte_epoch.o byte_epoch_kernels.cu &
+newest=$(ls -t *.cuh *.inc *.cu | head -1)
+[ -f /tmp/xp_byte_epoch.o ] && [ /tmp/xp_byte_epoch.o -nt "$newest" ] || nvcc $F -c -o /tmp/xp_byte_epoch.o byte_epoch_kernels.cu &
 for spec in "$@"; do
   name=${spec%%:*}; defs=${spec#*:}
   nvcc $F $defs -c -o /tmp/xp_$name.o brawl_cuda.cu &
