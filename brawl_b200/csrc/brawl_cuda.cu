@@ -582,6 +582,7 @@ typedef void (*BrwFastKernel)(BrwGeom, BrwBoxParams, uint8_t *, const double *, 
 struct BrwFastEntry { int lat, nsh, px, py, maxt; BrwFastKernel fn, fn_screen; };
 // byte-lattice epoch kernels of the same geometries (epoch_byte_metropolis.cuh), instantiated in byte_epoch_kernels.cu
 void *brw_byte_epoch_kernel_lookup(int lat, int nsh, int px, int py, int maxt, int epoch_k, int exact);
+int brw_byte_epoch_pitch(int lat, int nsh);
 // MAXT = launch bound: CTAs of <= 384 threads (e.g. the 128^3 single chain, 352 threads) may use up to
 // 168 registers/thread, CTAs of <= 768 threads (e.g. one 32^3-cell replica per CTA, 736 threads) 80.
 #define BRW_FAST(LAT, NSH, PX, PY, MAXT) {LAT, NSH, PX, PY, MAXT, brw_box_metropolis_fast_kernel<LAT, NSH, PX, PY, false, MAXT>, \
@@ -955,7 +956,8 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
             if (!pl->fast_fn) { brw_fail("byte-lattice epoch kernel not instantiated"); brw_free_plan(pl); return 1; }
             pl->screened = h->dE_mode != 0; pl->byte_epoch = true;
             pl->fast_smem = (size_t)p.v_entries * 16 * 8 + 32 * 8 + (size_t)(p.steps / byte_epoch) * sizeof(BrwByteEpochT<4>) +
-                            (size_t)((fe.maxt + 31) / 32) * 320 * 4 + (size_t)fe.maxt * 4 + p.box_sites;
+                            (size_t)((fe.maxt + 31) / 32) * 320 * 4 + (size_t)fe.maxt * 4 +
+                            (size_t)(p.box_sites / p.bxc) * brw_byte_epoch_pitch(fe.lat, fe.nsh);
             // programmatic dependent launch only for single-wave grids, and then with a shared-memory request of more than
             // half an SM: CTAs of the next phase launched early must not pile up next to running ones (measured: -20 %)
             int n_sm = 148;

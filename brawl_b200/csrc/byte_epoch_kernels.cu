@@ -25,6 +25,12 @@ const Entry table[] = {
 };
 }  // namespace
 
+// bytes between consecutive x-rows of the shared-memory box of these kernels (the host sizes the launch with it)
+int brw_byte_epoch_pitch(int lat, int nsh) {
+  return lat == 1 ? (nsh <= 4 ? BrwBytePitch<1, 4>::value : BrwBytePitch<1, 6>::value)
+                  : (nsh <= 4 ? BrwBytePitch<2, 4>::value : BrwBytePitch<2, 6>::value);
+}
+
 // epoch_k = 4 or 8; exact != 0: reference association for every trial.  nullptr if not instantiated.
 void *brw_byte_epoch_kernel_lookup(int lat, int nsh, int px, int py, int maxt, int epoch_k, int exact) {
   for (const Entry &e : table)

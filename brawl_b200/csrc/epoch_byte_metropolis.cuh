@@ -79,6 +79,11 @@ __device__ __forceinline__ bool brw_byte_decide_cold(const uint8_t *box, const c
   return accept;
 }
 
+// PX = compact sites per x-row of the box, PITCH >= PX = bytes between consecutive rows in shared memory: with PITCH = PX =
+// 32 the 2-3 rows of coarse cells a warp covers start 128 bytes apart (fcc) and their gathers collide in the banks (43 %
+// replays measured); the padded pitches below were chosen with a bank simulation of all period orientations.
+template <int LAT, int NSH> struct BrwBytePitch { static constexpr int value = LAT == 2 && NSH <= 4 ? 56 : 52; };
+
 template <int LAT, int NSH, int PX, int PY, bool EXACT, int K, int MAXT>
 __global__ void __launch_bounds__(MAXT) brw_box_metropolis_byte_epoch_kernel(
     BrwGeom g, BrwBoxParams p, uint8_t *__restrict__ lat, const double *__restrict__ beta,
@@ -86,6 +91,8 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_byte_epoch_kernel(
     uint32_t k1, uint32_t phase_lo, int mode, unsigned long long *__restrict__ att_out,
     unsigned long long *__restrict__ acc_out, double *__restrict__ dE_out) {
   using Ep = BrwByteEpochT<K>;
+  constexpr int PITCH = BrwBytePitch<LAT, NSH>::value;
+  static_assert(PITCH >= PX && PITCH % 4 == 0, "padded row pitch");
   static_assert(K == 4 || K == 8, "one Philox call serves four steps");
   static_assert(NSH * BRW_HLIMB * 4 <= 72, "xdig table of BrwBoxParams");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_byte_epoch_kernel(
   const int n_warps = (MAXT + 31) / 32;
   int *hcache = reinterpret_cast<int *>(ep + n_epochs);                    // [n_warps][2][5][32]; rows = species, zeros for the reference
   int *base_tab = hcache + n_warps * 320;                                  // [MAXT] compact box offset of every thread's coarse cell
-  uint8_t *box = reinterpret_cast<uint8_t *>(base_tab + MAXT);             // [bzc][PY][PX], bytes hold 8*species
+  uint8_t *box = reinterpret_cast<uint8_t *>(base_tab + MAXT);             // [bzc][PY][PITCH], bytes hold 8*species
   __shared__ unsigned int s_att[32], s_acc[32];
 
   const int tid = threadIdx.x;
@@ -115,12 +122,14 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_byte_epoch_kernel(
   for (int i = tid; i < p.v_entries * 16; i += blockDim.x) Vs[i] = Vrep[i];
   for (int e = tid; e < n_epochs; e += blockDim.x) {
     brw_make_step<0>(g, p, md, classes, disp, k0, k1, (uint32_t)e, box_id, phase_lo, &ep[e].q);
+    ep[e].q.c1_base = (ep[e].q.c1_base / PX) * PITCH + ep[e].q.c1_base % PX;       // row pitch PX (p.bxc) -> PITCH
+    ep[e].q.c2_base = (ep[e].q.c2_base / PX) * PITCH + ep[e].q.c2_base % PX;
     const BrwPhilox4 t = brw_philox(0xFFFFFFFCu, (uint32_t)e, box_id, phase_lo, k0, k1);
     ep[e].sh[0] = t.x; ep[e].sh[1] = t.y;
     ep[e].rot = (int)brw_below(t.z, (uint32_t)md.M);
   }
   for (int i = tid; i < n_warps * 320; i += blockDim.x) hcache[i] = 0;     // the reference species' rows stay zero
-  const int stx = md.P[0] >> 1, sty = (LAT == 1 ? (md.P[1] >> 1) : md.P[1]) * PX, stz = md.P[2] * PY * PX;
+  const int stx = md.P[0] >> 1, sty = (LAT == 1 ? (md.P[1] >> 1) : md.P[1]) * PITCH, stz = md.P[2] * PY * PITCH;
   const bool active = tid < md.M;
   {
     const int A0 = md.A[0], A1 = md.A[1];
@@ -130,7 +139,7 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_byte_epoch_kernel(
   // programmatic dependent launch (see epoch_metropolis.cuh): the table set-up above overlaps the previous phase's tail
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;");
-  brw_box_copy<LAT, PX, PY, false>(g, L, box, PY * p.bzc, ox, oy, oz);
+  brw_box_copy<LAT, PX, PY, false, PITCH>(g, L, box, PY * p.bzc, ox, oy, oz);
   if (tid < 32) red[tid] = 0.0;
   __syncthreads();
 
@@ -163,8 +172,8 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_byte_epoch_kernel(
         for (int kind = 0; kind < 2; kind++) {
           uint32_t C[NSH];
           const uint32_t sa = box_s + (kind ? E.q.c2_base + base1 : c1);
-          if (kind ? E.q.par2 : E.q.par1) brw_count_shells<LAT, NSH, PX, PY, 1, 0>(sa, C);
-          else brw_count_shells<LAT, NSH, PX, PY, 0, 0>(sa, C);
+          if (kind ? E.q.par2 : E.q.par1) brw_count_shells<LAT, NSH, PITCH, PY, 1, 0>(sa, C);
+          else brw_count_shells<LAT, NSH, PITCH, PY, 0, 0>(sa, C);
           const uint32_t hk = kind ? hb1 + 640 : hb1;
 #pragma unroll
           for (int c = 0; c < 4; c++) {
@@ -213,7 +222,7 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_byte_epoch_kernel(
             // ~1e-5 of the trials: second screening level in f64, then the reference association
             efix = 0;
             double dE;
-            accept = brw_byte_decide_cold<LAT, NSH, PX, PY, EXACT>(box, Vl, S, c1, c2, E.q.par1, E.q.par2, a >> 3, b >> 3, rw,
+            accept = brw_byte_decide_cold<LAT, NSH, PITCH, PY, EXACT>(box, Vl, S, c1, c2, E.q.par1, E.q.par2, a >> 3, b >> 3, rw,
                                                                    beta[replica], p.guard2, &dE);
             if (accept) atomicAdd(&red[warp], dE);
           }
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_byte_epoch_kernel(
     __syncthreads();
   }
 
-  brw_box_copy<LAT, PX, PY, true>(g, L, box, PY * p.bzc, ox, oy, oz);
+  brw_box_copy<LAT, PX, PY, true, PITCH>(g, L, box, PY * p.bzc, ox, oy, oz);
   unsigned int n_att = active ? (unsigned int)(n_epochs * K) : 0u;
   double dE_sum = (double)efix_sum * p.fix_scale;
   for (int o = 16; o > 0; o >>= 1) {

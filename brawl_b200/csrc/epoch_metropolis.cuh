@@ -121,6 +121,9 @@ __device__ __forceinline__ void brw_sts32(uint32_t a, int v) { asm volatile("st.
 #ifndef BRW_SPLITBAR
 #define BRW_SPLITBAR 1
 #endif
+#ifndef BRW_MBAR_SLEEP
+#define BRW_MBAR_SLEEP 0
+#endif
 #ifndef BRW_MBAR_HINT
 #define BRW_MBAR_HINT 20000u
 #endif
@@ -137,6 +140,9 @@ __device__ __forceinline__ void brw_mbar_wait(uint32_t a, uint32_t parity) {
     // polls of waiting warps were 7 % of the executed instructions, taking issue slots from the warps still working)
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
                  : "=r"(ok) : "r"(a), "r"(parity), "r"(BRW_MBAR_HINT) : "memory");
+#if BRW_MBAR_SLEEP
+    if (!ok) __nanosleep(BRW_MBAR_SLEEP);                  // waiting warps stay out of the issue slots of the working ones
+#endif
   } while (!ok);
 }
 

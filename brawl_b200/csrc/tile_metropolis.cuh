@@ -505,7 +505,9 @@ __global__ void __launch_bounds__(256) brw_energy_tile_kernel(BrwGeom g, const d
 
 // box <-> global copy: one warp per compact-x row (PX consecutive bytes, wrapping inside the
 // global row), rows unrolled x8 so the independent loads overlap.  STORE=false: global -> shared.
-template <int LAT, int PX, int PY, bool STORE>
+// PITCH: bytes between consecutive x-rows of the shared-memory box (>= PX; padded where the gathers would otherwise hit
+// the same banks from the 2-3 rows a warp covers).
+template <int LAT, int PX, int PY, bool STORE, int PITCH = PX>
 __device__ __forceinline__ void brw_box_copy(const BrwGeom &g, uint8_t *L, uint8_t *box, int n_rows, int ox, int oy,
                                              int oz) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -520,8 +522,8 @@ __device__ __forceinline__ void brw_box_copy(const BrwGeom &g, uint8_t *L, uint8
     if (lane < PX) {
       int gxc = oxc + lane; if (gxc >= g.cx) gxc -= g.cx; if (gxc >= g.cx) gxc -= g.cx;
       const long gi = ((long)gzz * g.cy + (gyy >> g.ys)) * g.cx + gxc;
-      if (STORE) L[gi] = (uint8_t)(box[r * PX + lane] >> 3);     // shared-memory bytes hold 8*species
-      else box[r * PX + lane] = (uint8_t)(L[gi] << 3);
+      if (STORE) L[gi] = (uint8_t)(box[r * PITCH + lane] >> 3);  // shared-memory bytes hold 8*species
+      else box[r * PITCH + lane] = (uint8_t)(L[gi] << 3);
     }
   }
 }
