@@ -151,6 +151,12 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def workload_name(n):
+    """config.workload of the headline configuration -- the same string in both arms (--impl cuda / reference)."""
+    return ("AlTiCrMo bcc %d^3 (%d atoms), 4 species @0.25, 4 shells (Z=50), Metropolis whole-lattice swaps, T=%g K; "
+            "replicas only for N>1 (one chain per GPU)" % (n, 2 * n ** 3, T_KELVIN))
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -167,8 +173,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "swaps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "AlTiCrMo bcc 128^3, 4 species, 4 shells, Metropolis whole-lattice swaps, T=1000K",
-                   "n_atoms": 2 * N_CELLS ** 3, "step": sample},
+        "config": {"workload": workload_name(N_CELLS), "n_atoms": 2 * N_CELLS ** 3, "step": sample},
         "cpu_baseline": {"value": value, "unit": "swaps/s", "cores": cores, "kind": "port",
                          "sample": sample + "; C restatement of the reference (no Fortran toolchain in the image), "
                                             "bit-exact vs reference goldens"},
@@ -542,8 +547,7 @@ def main():
     if rank == 0:
         value = attempts_all / (total_ms_r * 1e-3)
         e2e_value = e2e_attempts_all / (e2e_ms_r * 1e-3)
-        wl_name = desc or ("AlTiCrMo bcc %d^3 (%d atoms), 4 species @0.25, 4 shells (Z=50), Metropolis whole-lattice swaps, T=%g K; "
-                           "replicas only for N>1 (one chain per GPU)" % (n, N, T_KELVIN))
+        wl_name = desc or workload_name(n)
         out = {
             "metric": METRIC, "value": value, "unit": "swaps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_r / args.steps, "higher_is_better": True,

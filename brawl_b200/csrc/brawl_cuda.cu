@@ -4,6 +4,7 @@
 #include <array>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <string>
@@ -1036,7 +1037,9 @@ static int brw_build_plan(brawl_cuda_ctx *h, int nbr_swap, BrwPlan **out) {
       p.tma_stages = 0;
       // box load through the bulk-async copy engine (TMA): whole global x-rows of <= 128 bytes land in the storage of the
       // pair-word rows they are expanded into (epoch_metropolis.cuh, brw_pbox_load_tma)
-      if (we->epoch && BRW_TMA_LOAD && pl->threads == 32 * we->byc && g.cx % 16 == 0 && g.cx <= 128 && g.n_sites % 16 == 0)
+      // (diagnostic switch: BRAWL_CUDA_NO_TMA=1 in the environment keeps the LDG loop -- the tests compare the two loads)
+      if (we->epoch && BRW_TMA_LOAD && !getenv("BRAWL_CUDA_NO_TMA") && pl->threads == 32 * we->byc && g.cx % 16 == 0 && g.cx <= 128 &&
+          g.n_sites % 16 == 0)
         p.tma_stages = 1;
       BRW_PLAN_CUDA(cudaFuncSetAttribute((const void *)pl->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem));
     }

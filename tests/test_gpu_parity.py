@@ -1045,3 +1045,34 @@ def test_epoch_kernel_statistics_match_oracle(bw, orc, golden, lattice, shells, 
     assert np.max(np.abs(a_mean)) > 20 * report[2][2], (report, a_mean)        # SRO is resolved, not noise
     print("epoch kernel vs oracle, %s %d shells S=%d T=%g: <E>/N = %.7f, max |diff| / max se: %s, worst |z| = %.2f"
           % (lattice, shells, S, T, e_mean, ["%s %.2e / %.2e" % r for r in report], worst))
+
+
+@pytest.mark.parametrize("n", [64, 96, 160])
+def test_epoch_kernel_box_load_paths(bw, golden, n, monkeypatch):
+    """The box of the epoch kernel arrives through the bulk-async copy engine (cp.async.bulk, whole x-rows of <= 128 bytes
+    expanded in place) or, for wider lattices (n = 160) and with BRAWL_CUDA_NO_TMA set, through the LDG loop: same seed =>
+    identical trajectory on both paths; composition conserved, accepted dE sum == energy change."""
+    V = golden["ex_AlTiCrMo_V"][:64]
+    beta = 1.0 / (1000.0 * bw.K_B_IN_RY)
+    out = []
+    for no_tma in (False, True):
+        if no_tma:
+            monkeypatch.setenv("BRAWL_CUDA_NO_TMA", "1")
+        else:
+            monkeypatch.delenv("BRAWL_CUDA_NO_TMA", raising=False)
+        dev = bw.Device("bcc", n, n, n, 4, 4, V)
+        N = dev.n_atoms
+        dev.random_config([N // 4] * 4, seed=17)
+        lat0 = dev.get_lattice()[0].copy()
+        assert dev.metropolis_plan()["use_box"] == 4
+        e0 = dev.total_energy(exact_order=False)[0]
+        att, acc, dE = dev.metropolis_run(beta, 3 * N, seed=5)
+        e1 = dev.total_energy(exact_order=False)[0]
+        lat1 = dev.get_lattice()[0].copy()
+        assert att[0] >= 3 * N and 0 < acc[0] < att[0]
+        assert np.array_equal(np.bincount(lat0, minlength=4), np.bincount(lat1, minlength=4))
+        assert abs((e1 - e0) - dE[0]) < 2e-10 * float(acc[0]) + 1e-9 * abs(e0), (e0, e1, dE[0])
+        out.append((lat0, lat1, int(acc[0])))
+        dev.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
