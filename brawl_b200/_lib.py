@@ -58,6 +58,7 @@ _SIGNATURES = {
     "brawl_cuda_wl_set_windows": [_vp, _vp, _vp, _i],
     "brawl_cuda_wl_zero_hist": [_vp],
     "brawl_cuda_wl_set_lng": [_vp, _vp],
+    "brawl_cuda_wl_set_span": [_vp, _i],
     "brawl_cuda_wl_get": [_vp, _i, _vp],
     "brawl_cuda_wl_iterate": [_vp, _d, _i64, _i, _u64, _u64, _vp, _vp, _vp, _vp],
     "brawl_cuda_comm_unique_id": [_vp],

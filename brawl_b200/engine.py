@@ -309,6 +309,11 @@ class Device:
         hi = np.ascontiguousarray(np.broadcast_to(win_hi, (self.n_replicas,)), dtype=np.int32)
         check(self.L.brawl_cuda_wl_set_windows(self.h, _p(lo), _p(hi), int(zero_hist)))
 
+    def wl_set_span(self, n_ranks):
+        """The windows of this handle are shared with the same windows on all n_ranks ranks of its communicator: the window
+        average of wl_iterate becomes local sum + ncclAllReduce (include/brawl_cuda.h)."""
+        check(self.L.brawl_cuda_wl_set_span(self.h, int(n_ranks)))
+
     def wl_zero_hist(self):
         check(self.L.brawl_cuda_wl_zero_hist(self.h))
 

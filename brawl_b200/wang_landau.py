@@ -362,14 +362,26 @@ class WangLandau:
     the CPU tests) or "abi" (the C ABI's NCCL communicator; needs `unique_id`)."""
 
     def __init__(self, lattice, n_1, n_2, n_3, n_species, n_shells, V_ex, counts, params, walkers=8, device=0,
-                 rank=0, world=1, seed=0x42726157, torch_device=None, wc_range=0, comm="torch", unique_id=None):
+                 rank=0, world=1, seed=0x42726157, torch_device=None, wc_range=0, comm="torch", unique_id=None, span=False):
+        """span = False: the windows are sharded over the GPUs (num_windows divisible by world), every window lives on one
+        GPU.  span = True: EVERY rank holds `walkers` walkers of EVERY window (walkers * world per window in total) and the
+        window average of each `sweeps` call is a cross-GPU all-reduce (brawl_cuda_wl_set_span) -- for runs with fewer
+        windows than GPUs, e.g. the reference's one-window performance/wl_input.inp."""
         self.p, self.walkers, self.rank, self.world, self.seed = params, walkers, rank, world, seed
         W = params.num_windows
-        if W % world:
-            raise BrawlCudaError("num_windows must be divisible by the number of GPUs")
-        self.w_local = W // world
-        self.first_window = rank * self.w_local                 # 0-based
+        self.span = bool(span) and world > 1
+        if not self.span and W % world:
+            raise BrawlCudaError("num_windows must be divisible by the number of GPUs (or use span=True: windows shared by all GPUs)")
+        self.w_local = W if self.span else W // world
+        self.first_window = 0 if self.span else rank * self.w_local                 # 0-based
         self.n_local = self.w_local * walkers
+        self.walkers_total = walkers * (world if self.span else 1)                  # walkers of one window over all ranks
+        # window-major order of the global walker list: wm[j] = rank-major id (rank * n_local + local) of the j-th walker
+        # when the walkers are sorted by window (identity when the windows are sharded in order)
+        if self.span:
+            self.wm = np.array([r * self.n_local + q * walkers + k for q in range(W) for r in range(world) for k in range(walkers)])
+        else:
+            self.wm = np.arange(W * walkers)
         self.dev = Device(lattice, n_1, n_2, n_3, n_species, n_shells, V_ex, device=device, n_replicas=self.n_local)
         self.lattice, self.n, self.counts = lattice, (n_1, n_2, n_3), counts
         self.n_atoms = self.dev.n_atoms
@@ -387,6 +399,8 @@ class WangLandau:
         self.win_lo = self.window_indices[q, 0].astype(np.int32)
         self.win_hi = self.window_indices[q, 1].astype(np.int32)
         self.dev.wl_init(params.bins, self.edges, walkers)
+        if self.span:
+            self.dev.wl_set_span(world)
         self.dev.wl_set_windows(self.win_lo, self.win_hi, zero_hist=True)
         self.energies = np.zeros(self.n_local)
         self.hist_min, self.hist_mean = np.zeros(self.w_local), np.zeros(self.w_local)
@@ -487,7 +501,7 @@ class WangLandau:
         configuration; here the configuration at the end of each `sweeps` call is sampled (same estimator -- the mean
         of rho over configurations of a bin -- at a coarser cadence, ONE batched SRO launch per call).  Per walker and
         bin at most max(radial_samples / num_walkers, 1) samples, as in the reference."""
-        cap = max(self.p.radial_samples // self.walkers, 1)
+        cap = max(self.p.radial_samples // self.walkers_total, 1)
         want = []
         for w in range(self.n_local):
             jb = bin_index(self.energies[w], self.edges, self.p.bins)
@@ -523,6 +537,8 @@ class WangLandau:
 
     def _window_lng_all(self):
         """Window-averaged ln g of all windows of all ranks: [W][bins] (dos_combine's gather, :1161-1192)."""
+        if self.span:                                        # every rank holds every window, already averaged over all ranks
+            return self.dev.wl_get(0)
         if self.world > 1 and getattr(self.comm, "abi", False):
             return self.dev.wl_allgather_lng(self.world).reshape(self.p.num_windows, self.p.bins)
         return self.comm.all_gather(self.dev.wl_get(0)).reshape(self.p.num_windows, self.p.bins)
@@ -536,7 +552,9 @@ class WangLandau:
         t0 = time.perf_counter()
         lng_all = self._window_lng_all()
         t1 = time.perf_counter()
-        swaps = plan_replica_exchange(list(e_all), lng_all, self.window_indices, self.walkers, self.edges, self.rng_shared)
+        e_all = np.asarray(e_all)
+        swaps = plan_replica_exchange(e_all[self.wm], lng_all, self.window_indices, self.walkers_total, self.edges, self.rng_shared)
+        swaps = [(int(self.wm[a]), int(self.wm[b])) for a, b in swaps]          # window-major -> rank-major walker ids
         t2 = time.perf_counter()
         try:
             return self._do_swaps(swaps, e_all)
@@ -622,7 +640,8 @@ class WangLandau:
                 self._replica_exchange(both[:, :-1].reshape(-1))
             t3 = time.perf_counter()
             self.timing["sweeps"] += t1 - t0; self.timing["collectives"] += t2 - t1; self.timing["exchange"] += t3 - t2
-            if both[:, -1].sum() == self.p.num_windows or n >= max_sweeps:
+            # span: every rank sees the same (all-reduced) histograms and reports all windows
+            if (both[0, -1] if self.span else both[:, -1].sum()) == self.p.num_windows or n >= max_sweeps:
                 break
         self.stage_sweeps.append(n)
         t4 = time.perf_counter()
@@ -673,7 +692,7 @@ class WangLandau:
         p = self.p
         self.enter_energy_windows()
         wl_f = p.wl_f
-        combined = self._stage(wl_f, min_hist=1000.0 / float(np.float32(self.walkers)), max_sweeps=max_sweeps_per_stage,
+        combined = self._stage(wl_f, min_hist=1000.0 / float(np.float32(self.walkers_total)), max_sweeps=max_sweeps_per_stage,
                                exchange_every=10, it=0, resize=p.performance in (0, 1, 2, 3))
         it = 1
         while wl_f > p.tolerance:

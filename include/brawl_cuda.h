@@ -253,6 +253,12 @@ int brawl_cuda_wl_window_average(brawl_cuda_t *h, double *dev_array, int len, in
  *                    n_accept[n_walkers].  Fails if a walker enters with an energy outside its window. */
 int brawl_cuda_wl_init(brawl_cuda_t *h, int bins, const double *bin_edges, int walkers_per_window);
 int brawl_cuda_wl_set_windows(brawl_cuda_t *h, const int32_t *win_lo, const int32_t *win_hi, int zero_hist);
+/* Windows that span GPUs: the windows of this handle are the SAME windows on all n_ranks ranks of its communicator
+ * (brawl_cuda_comm_create first), each rank holding walkers_per_window of their walkers.  wl_iterate then divides the
+ * local sums by the total number of walkers and sums ln g and hist over the ranks with ncclAllReduce -- the
+ * MPI_Allreduce of src/wang-landau.F90:628-631 across GPUs (a run with fewer windows than GPUs, e.g. the one-window
+ * performance/wl_input.inp, uses every GPU this way).  n_ranks = 1 (default): every window lives on one GPU. */
+int brawl_cuda_wl_set_span(brawl_cuda_t *h, int n_ranks);
 int brawl_cuda_wl_zero_hist(brawl_cuda_t *h);
 int brawl_cuda_wl_set_lng(brawl_cuda_t *h, const double *lng);
 int brawl_cuda_wl_get(brawl_cuda_t *h, int what, double *out);

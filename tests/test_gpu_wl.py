@@ -2,12 +2,14 @@
 (bcc n=4, 4 species, 6 shells, 512 bins, 4 windows, overlap 0.25, f 0.05 -> 5e-5, flatness 0.9)
 against its golden ln g(E) with the reference's own acceptance criterion (NRMSE < 1 %,
 tests/ci_test.py:42-50)."""
+import os
 import time
 
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def nrmse(ref, test):
@@ -150,3 +152,38 @@ def test_enter_energy_window_replay_matches_oracle(orc, golden, n, lo_bin, hi_bi
     assert np.array_equal(st, mt_o.state625())
     if n == 2:
         assert n_rerand >= 2 and not entered
+
+
+def test_wl_set_span_needs_a_communicator(golden):
+    """brawl_cuda_wl_set_span: windows shared by several ranks need the handle's NCCL communicator; one rank is the default."""
+    import brawl_b200 as bw
+    dev = bw.Device("bcc", 4, 4, 4, 4, 6, golden["t04_V"], n_replicas=4)
+    with pytest.raises(bw.BrawlCudaError, match="wl_init"):
+        dev.wl_set_span(2)
+    dev.wl_init(64, np.linspace(-1.0, 0.0, 65), 2)
+    dev.wl_set_span(1)
+    with pytest.raises(bw.BrawlCudaError, match="communicator"):
+        dev.wl_set_span(2)
+    dev.close()
+
+
+def test_wang_landau_windows_spanning_two_gpus(golden):
+    """Three windows on two GPUs (not shardable): every GPU holds 8 walkers of every window and the window average of each
+    `sweeps` call is an ncclAllReduce over the ABI's communicator (brawl_cuda_wl_set_span).  Reference case 04 within its
+    own criterion.  Needs two devices (gpurun --gpus 2)."""
+    import ctypes as C
+    import json
+    import subprocess
+    import sys
+    n = C.c_int(0)
+    lib = C.CDLL(os.path.join(ROOT, "brawl_b200", "libbrawl_cuda.so"))
+    if lib.brawl_cuda_device_count(C.byref(n)) != 0 or n.value < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(ROOT, "tools", "wl_multi_gpu.py"), "--windows", "3", "--walkers", "8",
+                        "--span"], capture_output=True, text=True, timeout=600)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and line, r.stderr[-2000:]
+    out = json.loads(line[-1])
+    assert out["span"] and out["n_gpus"] == 2 and out["walkers_per_window"] == 16 and out["comm"] == "abi"
+    assert out["nrmse_vs_reference_golden"] < 0.01

@@ -213,6 +213,9 @@ class _OracleDevice:
     def wl_zero_hist(self):
         self.hists[...] = 0.0
 
+    def wl_set_span(self, n_ranks):
+        self.span = int(n_ranks)                 # brawl_cuda_wl_set_span: the windows are shared by n_ranks ranks
+
     def wl_set_lng(self, lng):
         self.lngs[...] = np.asarray(lng)[None, :]
 
@@ -232,11 +235,19 @@ class _OracleDevice:
                                           wl_f, n_trials, nbr_swap)
             self.hists[w, :nb] = h
         nq = n // self.wpw
+        span = getattr(self, "span", 1)
         mn, mean = np.zeros(nq), np.zeros(nq)
-        for q in range(nq):                      # the intra-window average (:628-631) and the flatness inputs (:222-226)
+        for q in range(nq):                      # the intra-window average (:628-631): local sums / total walkers ...
             sl = slice(q * self.wpw, (q + 1) * self.wpw)
-            self.lngs[sl] = self.lngs[sl].sum(axis=0) / float(np.float32(self.wpw))
-            self.hists[sl] = self.hists[sl].sum(axis=0) / float(np.float32(self.wpw))
+            self.lngs[sl] = self.lngs[sl].sum(axis=0) / float(np.float32(self.wpw * span))
+            self.hists[sl] = self.hists[sl].sum(axis=0) / float(np.float32(self.wpw * span))
+        if span > 1:                             # ... summed over the ranks that share the windows (the ABI: ncclAllReduce)
+            import torch
+            import torch.distributed as dist
+            for a in (self.lngs, self.hists):
+                t = torch.from_numpy(a)
+                dist.all_reduce(t)
+        for q in range(nq):                      # the flatness inputs (:222-226)
             nb = int(self.hi[q * self.wpw] - self.lo[q * self.wpw] + 1)
             mn[q], mean[q] = self.hists[q * self.wpw, :nb].min(), self.hists[q * self.wpw, :nb].sum() / nb
         return ef, mn, mean
@@ -388,6 +399,60 @@ def test_driver_dynamic_windows_world_size_2_gloo():
     assert a[3] and b[3] and a[4] and b[4]                                                # energies == configs; inside windows
     assert a[5] == b[5] and a[5] > 0                                                      # same exchange plan, some accepted
     assert a[6] == b[6] and min(a[6]) > 0 and a[7] == b[7]
+
+
+def _gloo_span_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from oracle import oracle
+    from brawl_b200 import wang_landau as wl
+    import test_wl_host_logic as t
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    t._OracleDevice.orc = oracle
+    wl.Device = t._OracleDevice
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "brawl_golden.npz"))
+    # three windows on two ranks: not shardable; every rank holds 2 walkers of every window (4 per window in total)
+    p = wl.WLParams(mc_sweeps=20, bins=64, num_windows=3, bin_overlap=0.25, tolerance=0.02, flatness=0.7, wl_f=0.05,
+                    energy_min=-60.0, energy_max=-5.0, performance=4)
+    drv = wl.WangLandau("bcc", 4, 4, 4, 4, 6, golden["t04_V"], [32, 32, 32, 32], p, walkers=2, device=rank, rank=rank,
+                        world=world, seed=5, span=True)
+    swaps = []
+    orig = drv._do_swaps
+    drv._do_swaps = lambda sw, e: swaps.extend(sw) or orig(sw, e)
+    lng = drv.run(max_sweeps_per_stage=400)
+    e = np.array([drv.dev.sys.total_energy(g) for g in drv.dev.g])
+    lo, hi = drv.edges[drv.win_lo - 1], drv.edges[drv.win_hi]
+    # (running energies of the sweeps: equal to the exact total energies up to f64 rounding)
+    q.put((rank, lng.tolist(), bool(np.allclose(e, drv.energies, rtol=0, atol=1e-12)), bool(np.all((e > lo) & (e < hi))), swaps,
+           drv.last_mc_steps.tolist(), drv.stage_sweeps, drv.dev.wl_get(0).tolist(), drv.walkers_total, drv.n_local))
+    dist.destroy_process_group()
+
+
+def test_driver_windows_spanning_ranks_world_size_2_gloo():
+    """span = True: three windows on two ranks (not shardable) -- every rank holds walkers of every window, the window
+    average of a `sweeps` call is an all-reduce over the ranks (brawl_cuda_wl_set_span on the GPU), the exchange plan runs
+    over the window-major list of all walkers incl. pairs on different ranks.  Both ranks end with the same ln g tables,
+    the same stitched curve, the same plan, consistent energies, every walker inside its window."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_gloo_span_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in ps])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    a, b = res
+    assert a[1] == b[1] and min(a[1]) == 0.0 and max(a[1]) > 0.0                          # same stitched ln g
+    assert a[2] and b[2] and a[3] and b[3]                                                # energies == configs; inside windows
+    assert a[4] == b[4] and len(a[4]) > 0                                                 # same exchange plan, some accepted
+    n_local = a[9]
+    assert any(x // n_local != y // n_local for x, y in a[4])                             # ... incl. pairs on different ranks
+    assert a[5] == b[5] and min(a[5]) > 0 and a[6] == b[6]                                # trial counts summed over the ranks
+    assert a[7] == b[7] and a[8] == 4                                                     # all-reduced window tables agree
 
 
 def test_ncdf_writer_1d_is_byte_identical_to_the_reference_file(golden, tmp_path):

@@ -30,6 +30,9 @@ def main():
     ap.add_argument("--out", default=None, help="directory for data/wl_dos.nc, wl_dos_bins.nc, wl_hist.nc (the reference's files)")
     ap.add_argument("--comm", default="abi", choices=["abi", "torch"],
                     help="collectives through the C ABI's NCCL communicator (brawl_cuda_comm_*) or torch.distributed")
+    ap.add_argument("--span", action="store_true",
+                    help="every GPU holds --walkers walkers of EVERY window; the window average becomes an ncclAllReduce "
+                         "(brawl_cuda_wl_set_span): for fewer windows than GPUs")
     ap.add_argument("--performance", type=int, default=4,
                     help="the reference's switch: 0/1 resize windows every f-stage, 2/3 after pre-sampling only, 4 static")
     args = ap.parse_args()
@@ -55,7 +58,7 @@ def main():
         uid = t.cpu().numpy()
     drv = wl.WangLandau("bcc", 4, 4, 4, 4, 6, gold["t04_V"], [32] * 4, p, walkers=args.walkers, device=local, rank=rank,
                         world=world, seed=args.seed, torch_device=torch.device("cuda", local),
-                        comm=args.comm if world > 1 else "torch", unique_id=uid)
+                        comm=args.comm if world > 1 else "torch", unique_id=uid, span=args.span)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -72,7 +75,7 @@ def main():
         ref = np.asarray(gold["t04_wl_dos"], dtype=np.float64)
         err = float(np.sqrt(np.mean((ref - lng) ** 2)) / np.mean(np.abs(ref)))
         print(json.dumps({"workload": "WL bcc n=4 4 species 6 shells 512 bins", "n_gpus": world, "windows": args.windows,
-                          "walkers_per_window": args.walkers, "performance": args.performance, "comm": args.comm if world > 1 else "none",
+                          "walkers_per_window": drv.walkers_total, "span": bool(drv.span), "performance": args.performance, "comm": args.comm if world > 1 else "none",
                           "final_window_widths": (drv.window_indices[:, 1] - drv.window_indices[:, 0] + 1).tolist(),
                           "seconds_to_final_lng": dt, "wl_trials": trials,
                           "wl_trials_per_sec": trials / dt, "sweeps_calls_per_stage": drv.stage_sweeps,
