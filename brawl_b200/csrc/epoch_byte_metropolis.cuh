@@ -156,13 +156,29 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_byte_epoch_kernel(
   unsigned int n_acc = 0;
   BrwPhilox4 rnd = {0, 0, 0, 0};
 
-  for (int e = 0; e < n_epochs; e++) {
-    const Ep E = ep[e];
+  // split-phase epoch barrier (see epoch_metropolis.cuh): a warp arrives when its epoch is done, prepares what the next epoch
+  // needs that no other warp can change (epoch parameters, its cell, the Philox draw), then waits for the other warps
+  __shared__ __align__(8) unsigned long long s_mbar;
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+  if (BRW_SPLITBAR && tid == 0) brw_mbar_init(mbar, blockDim.x >> 5);
+  Ep E = ep[0];
+  int cell0 = 0, base1 = 0;
+  auto prepare = [&](int e) {
+    E = ep[e];
     // this epoch's coarse cell of the thread: cell = (tid + rot) mod M; a warp holds n_lanes consecutive cells (mod M)
-    int cell0 = 32 * warp + E.rot;
+    cell0 = 32 * warp + E.rot;
     if (cell0 >= md.M) cell0 -= md.M;
-    int base1 = 0;
-    if (active) { int cell = cell0 + lane; if (cell >= md.M) cell -= md.M; base1 = base_tab[cell]; }
+    base1 = 0;
+    if (active) {
+      int cell = cell0 + lane; if (cell >= md.M) cell -= md.M;
+      base1 = base_tab[cell];
+      rnd = brw_philox((uint32_t)tid, (uint32_t)((e * K) >> 2), box_id, phase_lo, k0, k1);
+    }
+  };
+  prepare(0);
+  __syncthreads();                                                         // the mbarrier is initialised
+
+  for (int e = 0; e < n_epochs; e++) {
     const int c1 = E.q.c1_base + base1;
     int a = 0;
     if (active) {
@@ -200,7 +216,7 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_byte_epoch_kernel(
         if (cell2 >= md.M) cell2 -= md.M;
         const int c2 = E.q.c2_base + base_tab[cell2];
         const int b = box[c2];
-        if ((j & 3) == 0) rnd = brw_philox((uint32_t)tid, (uint32_t)((e * K + j) >> 2), box_id, phase_lo, k0, k1);
+        if ((j & 3) == 0 && j > 0) rnd = brw_philox((uint32_t)tid, (uint32_t)((e * K + j) >> 2), box_id, phase_lo, k0, k1);
         const uint32_t rw = (j & 3) == 0 ? rnd.x : (j & 3) == 1 ? rnd.y : (j & 3) == 2 ? rnd.z : rnd.w;
         n_acc += a == b;                                                   // :774-777
         if (a != b) {
@@ -236,7 +252,14 @@ __global__ void __launch_bounds__(MAXT) brw_box_metropolis_byte_epoch_kernel(
       }
       __syncwarp();
     }
-    __syncthreads();
+    if (BRW_SPLITBAR) {
+      if (lane == 0) brw_mbar_arrive(mbar);                  // the __syncwarp above ordered the warp's stores before it
+      if (e + 1 < n_epochs) prepare(e + 1);
+      brw_mbar_wait(mbar, (uint32_t)(e & 1));
+    } else {
+      __syncthreads();
+      if (e + 1 < n_epochs) prepare(e + 1);
+    }
   }
 
   brw_box_copy<LAT, PX, PY, true, PITCH>(g, L, box, PY * p.bzc, ox, oy, oz);
