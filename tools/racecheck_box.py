@@ -13,13 +13,17 @@ import brawl_b200
 
 gold = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "brawl_golden.npz"))
 rng = np.random.default_rng(0)
-# layout: 0 automatic (word kernel with two warp groups where instantiated), 1 byte-lattice kernels, 2 word kernel, one group
+# layout: 0 automatic (epoch kernels: word lattice for bcc-4, byte lattice for fcc / bcc-6), 1 byte-lattice gather-per-step
+# kernels, 2 / 3 the round-1 word kernels without / with the two-warp-group split
 for lattice, n, S, shells, key, nbr, mode, generic, layout in (
-        ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", False, 2, False, 0),      # word kernel, pair words, two warp groups (named barriers)
-        ("bcc", 32, 5, 4, "ex_AlCrFeCoNi_V", False, 2, False, 2),    # word kernel, one warp group, 5 species
-        ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", False, 0, False, 0),      # word kernel, EXACT instantiation
+        ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", False, 2, False, 0),      # epoch kernel: mbarrier epochs, TMA box load, dependent launch
+        ("bcc", 32, 5, 4, "ex_AlCrFeCoNi_V", False, 2, False, 0),    # epoch kernel, 5 species
+        ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", False, 0, False, 0),      # epoch kernel, EXACT instantiation
+        ("fcc", 32, 5, 4, "ex_AlCrFeCoNi_V", False, 2, False, 0),    # byte-lattice epoch kernel, fcc 4 shells
+        ("bcc", 32, 4, 6, "t02_V", False, 2, False, 0),              # byte-lattice epoch kernel, bcc 6 shells
+        ("fcc", 32, 2, 4, "ex_FeNi_V", False, 0, False, 0),          # byte-lattice epoch kernel, EXACT, binary
+        ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", False, 2, False, 3),      # round-1 word kernel, two warp groups (named barriers)
         ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", False, 1, False, 1),
-        ("bcc", 32, 4, 4, "ex_AlTiCrMo_V", False, 0, False, 1),
         ("fcc", 32, 5, 4, "ex_AlCrFeCoNi_V", False, 1, False, 1),
         ("bcc", 16, 4, 6, "t02_V", False, 0, True, 1),
         ("bcc", 16, 4, 4, "ex_AlTiCrMo_V", True, 0, True, 1)):
