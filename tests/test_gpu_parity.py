@@ -812,22 +812,28 @@ def test_tiled_total_energy_matches_reference_order(bw, orc):
         assert abs(dev.total_energy(exact_order=False)[0] - e_tile) <= 1e-12 * abs(e_exact) + 1e-13
 
 
-def test_full_size_128_cubed_properties(bw, golden):
-    """BASELINE configs[1] at full size (128^3 bcc, 4 194 304 atoms): size-independent properties --
-    species counts conserved, occupancy pattern intact, sum of accepted dE == change of the exact
-    (reference-order) total energy, exact and tree energies agree, trajectory reproducible."""
-    n, S = 128, 4
-    V = golden["ex_AlTiCrMo_V"][:64]
+@pytest.mark.parametrize("lattice,S,shells,key,kind", [("bcc", 4, 4, "ex_AlTiCrMo_V", 4), ("fcc", 5, 4, "ex_AlCrFeCoNi_V", 6),
+                                                       ("fcc", 2, 4, "ex_FeNi_V", 6), ("bcc", 4, 6, "t02_V", 6)])
+def test_full_size_128_cubed_properties(bw, golden, lattice, S, shells, key, kind):
+    """BASELINE configs[1] at full size (128^3 bcc, 4 194 304 atoms) and the fcc / 6-shell lattices of the other configs at
+    128^3: size-independent properties -- species counts conserved, occupancy pattern intact, sum of accepted dE == change
+    of the exact (reference-order) total energy, exact and tree energies agree, trajectory reproducible."""
+    n = 128
+    V = golden[key][: S * S * shells]
     rng = np.random.default_rng(1)
     par = (np.arange(2 * n) & 1).astype(np.int8)
-    mask = (par[None, None, :] == par[:, None, None]) & (par[None, :, None] == par[:, None, None])
+    if lattice == "bcc":
+        mask = (par[None, None, :] == par[:, None, None]) & (par[None, :, None] == par[:, None, None])
+    else:
+        mask = ((par[None, None, :] + par[None, :, None] + par[:, None, None]) & 1) == 0
+    N = int(mask.sum())
     g = np.zeros((2 * n,) * 3, dtype=np.int8)
-    spec = np.repeat(np.arange(1, S + 1, dtype=np.int8), 2 * n ** 3 // S); rng.shuffle(spec)
+    spec = np.repeat(np.arange(1, S + 1, dtype=np.int8), -(-N // S))[:N]; rng.shuffle(spec)
     g[mask] = spec
-    N = 2 * n ** 3
     finals = []
     for rep in range(2):
-        dev = bw.Device("bcc", n, n, n, S, 4, V)
+        dev = bw.Device(lattice, n, n, n, S, shells, V)
+        assert dev.metropolis_plan()["use_box"] == kind
         dev.set_config(g)
         e0 = dev.total_energy(exact_order=True)[0]
         assert abs(dev.total_energy(exact_order=False)[0] - e0) < 1e-9 * abs(e0) + 1e-9
@@ -837,10 +843,11 @@ def test_full_size_128_cubed_properties(bw, golden):
         assert att[0] >= 4 * N and 0 < acc[0] < att[0]
         assert np.array_equal(np.bincount(g1.ravel(), minlength=S + 1), np.bincount(g.ravel(), minlength=S + 1))
         assert np.array_equal(g1 == 0, g == 0)
-        # sum of accepted dE of the screened epoch kernel: fixed-point from a 22-bit table, < 2e-10 Ry per accepted swap
+        # sum of accepted dE of the screened epoch kernels: fixed-point from a 23-bit table, < 2e-10 Ry per accepted swap
         # (the DECISIONS are exact; dE_mode 0 returns the sum to f64 rounding)
         assert abs((e1 - e0) - dE[0]) < 2e-10 * float(acc[0]), (e0, e1, dE[0])
         finals.append((g1, att[0], acc[0], e1))
+        dev.close()
     assert np.array_equal(finals[0][0], finals[1][0]) and finals[0][1:] == finals[1][1:]
 
 
