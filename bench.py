@@ -240,6 +240,38 @@ def wl_time_to_flatness(rank, world, local_rank, windows_per_gpu=8, walkers=16, 
             "host_seconds_per_rank": timing}
 
 
+def ns_walk_rate(rank, world, local_rank, n_runs=2048, n_iter=100):
+    """BASELINE configs[3]: nested sampling on the reference's example shape (examples/03: fcc 3x3x3 = 108 atoms, AlCrFeCoNi,
+    4 shells, K = 100 walkers, 500 walk steps per iteration), `n_runs` independent runs per GPU advancing in lock-step: per
+    iteration one batched clone launch + one walk kernel (one warp per walking clone).  Returns the `extra.ns` block."""
+    import torch
+    import torch.distributed as dist
+    from brawl_b200 import nested_sampling as ns
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "brawl_golden.npz"))
+    V = np.ascontiguousarray(gold["t03_V"][: 5 * 5 * 4])
+    p = ns.NSParams(n_walkers=100, n_steps=500, n_iter=n_iter)
+    drv = ns.NestedSampling("fcc", 3, 3, 3, 5, 4, V, [21, 21, 21, 21, 24], p, n_runs=n_runs, device=local_rank, seed=7 + rank)
+    drv.initialise()
+    drv.run(n_iter=10)                                         # warm-up
+    drv.dev.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    culled = drv.run(n_iter=n_iter)
+    drv.dev.synchronize()
+    dt = time.perf_counter() - t0
+    trials = float(n_runs) * n_iter * p.n_steps                # lower bound: runs with few acceptances walk longer (:129-144)
+    if world > 1:
+        v = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        dt, trials = float(v[0]), trials * world
+    return {"metric": "ns_walk_trials_per_sec", "value": trials / dt, "unit": "trials/s", "higher_is_better": True, "n_gpus": world,
+            "workload": "nested sampling, fcc 3x3x3 (108 atoms) AlCrFeCoNi 4 shells, K=100 walkers, 500 walk steps per iteration; "
+                        "%d independent runs per GPU in lock-step, %d iterations timed" % (n_runs, n_iter),
+            "seconds": dt, "iterations_per_sec_per_run": n_iter / dt, "runs_per_gpu": n_runs,
+            "ceilings_monotone": bool(np.all(np.diff(culled, axis=1) <= 0))}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -543,6 +575,7 @@ def main():
         for d in devs[1:]:
             d.close()
         extra["wl"] = wl_time_to_flatness(rank, world, local_rank, args.wl_windows_per_gpu, args.wl_walkers)
+        extra["ns"] = ns_walk_rate(rank, world, local_rank)
 
     if rank == 0:
         value = attempts_all / (total_ms_r * 1e-3)

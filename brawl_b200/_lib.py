@@ -70,6 +70,7 @@ _SIGNATURES = {
     "brawl_cuda_exchange_replica": [_vp, _i, _i],
     "brawl_cuda_exchange_replicas": [_vp, _i, _vp, _vp],
     "brawl_cuda_swap_replicas_batch": [_vp, _i, _vp, _vp],
+    "brawl_cuda_copy_replicas_batch": [_vp, _i, _vp, _vp],
     "brawl_cuda_ns_walk_replay": [_vp, _i, _vp, _d, _i64, _vp, _vp],
     "brawl_cuda_ns_walk": [_vp, _i, _vp, _vp, _vp, _i64, _u64, _u64, _vp],
 }

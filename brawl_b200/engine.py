@@ -374,6 +374,12 @@ class Device:
         q = np.ascontiguousarray(peers, dtype=np.int32)
         check(self.L.brawl_cuda_exchange_replicas(self.h, r.size, _p(r), _p(q)))
 
+    def copy_replicas_batch(self, src, dst):
+        """replica dst[i] := replica src[i], all pairs in one launch (walker cloning of batched nested-sampling runs)"""
+        s = np.ascontiguousarray(src, dtype=np.int32)
+        d = np.ascontiguousarray(dst, dtype=np.int32)
+        check(self.L.brawl_cuda_copy_replicas_batch(self.h, s.size, _p(s), _p(d)))
+
     def swap_replicas_batch(self, a, b):
         a = np.ascontiguousarray(a, dtype=np.int32)
         b = np.ascontiguousarray(b, dtype=np.int32)

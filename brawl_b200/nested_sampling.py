@@ -79,8 +79,7 @@ class NestedSampling:
                 grow = (n_acc < self.n_at * np.float32(0.05)) & (extra < p.n_steps * 100)
                 extra[grow] += p.n_steps
             irnd = np.maximum(np.ceil(self.rng.random(R) * K).astype(np.int64), 1)     # :149-150
-            for r in range(R):
-                self.dev.copy_replica(int(base[r] + irnd[r] - 1), int(base[r] + i_max[r]))   # :151
+            self.dev.copy_replicas_batch(base + irnd - 1, base + i_max)                   # :151, one launch for all runs
             self.energies[np.arange(R), i_max] = self.energies[np.arange(R), irnd - 1]
             # all runs share the step count of the run that needs most (extra steps never hurt:
             # the walk is a valid constrained random walk of any length)

@@ -286,6 +286,9 @@ int brawl_cuda_exchange_replica(brawl_cuda_t *h, int replica, int peer);
 int brawl_cuda_exchange_replicas(brawl_cuda_t *h, int n, const int32_t *replica, const int32_t *peer);
 /* all same-GPU swaps of one replica_exchange call in one launch: replicas a[i] <-> b[i], pairs disjoint */
 int brawl_cuda_swap_replicas_batch(brawl_cuda_t *h, int n_pairs, const int32_t *a, const int32_t *b);
+/* replica dst[i] := replica src[i] for n_pairs pairs in one launch (the walker clone of nested_sampling.f90:151 for a batch
+ * of independent runs); destinations distinct, no destination is also a source, src[i] == dst[i] allowed (no-op) */
+int brawl_cuda_copy_replicas_batch(brawl_cuda_t *h, int n_pairs, const int32_t *src, const int32_t *dst);
 
 /* ---- nested sampling ------------------------------------------------------------------------
  * The constrained random walk of nested_sampling.f90:157-192 for a batch of walkers: walker w

@@ -93,6 +93,26 @@ def test_config_roundtrip_vectorised_converters(bw, orc):
 CASES = [("bcc", n) for n in range(1, 11)] + [("fcc", n) for n in range(1, 7)] + [("simple_cubic", 1), ("simple_cubic", 2)]
 
 
+def test_copy_replicas_batch(bw, orc):
+    """brawl_cuda_copy_replicas_batch (walker cloning of batched nested-sampling runs, nested_sampling.f90:151): all
+    pairs in one launch, same result as copy_replica pair by pair; a replica may be copied onto itself; a destination that
+    is listed twice or is also a source is refused."""
+    sysm = orc.System("fcc", 3, 3, 3, 5, 2, np.zeros(50))
+    R = 8
+    gs = np.stack([random_config(orc, sysm, 60 + r) for r in range(R)])
+    dev = bw.Device("fcc", 3, 3, 3, 5, 2, np.zeros(50), n_replicas=R)
+    dev.set_config(gs)
+    dev.copy_replicas_batch([0, 3, 5, 6], [1, 2, 5, 7])
+    want = gs.copy()
+    want[1], want[2], want[7] = gs[0], gs[3], gs[6]
+    assert np.array_equal(dev.get_config(0, R), want)
+    for src, dst in (([0, 1], [2, 2]), ([0, 2], [2, 3]), ([0], [R])):
+        with pytest.raises(bw.BrawlCudaError):
+            dev.copy_replicas_batch(src, dst)
+    dev.copy_replicas_batch([], [])
+    assert np.array_equal(dev.get_config(0, R), want)
+
+
 def test_compact_lattice_host_buffers(bw, orc):
     """brawl_cuda_set_lattice / get_lattice: the compact host form (1 B per atom, species 0..S-1, device site order) is
     the reference's config grid without the empty cells, in the same z, y, x order -- bcc, fcc and sc, several replicas;
