@@ -22,8 +22,11 @@
 //       tests compare the two instantiations trajectory for trajectory).
 //
 // The partner of a lane is always a site of its own warp's row pair, so the K steps of an epoch need only __syncwarp;
-// the CTA barrier is per EPOCH (gathers of the next epoch read what other warps wrote), the warps drift apart inside
-// an epoch and their shared-memory and ALU phases overlap.  Every step is still a set of pairwise non-interacting swap
+// the CTA-wide barrier is per EPOCH (gathers of the next epoch read what other warps wrote) and split-phase -- an mbarrier
+// in shared memory: a warp arrives after its last step, prepares the next epoch's parameters / addresses / Philox draw,
+// then waits -- so the warps drift apart inside an epoch and their shared-memory and ALU phases overlap.  One launch is
+// one phase; consecutive phases are programmatic dependent launches (griddepcontrol), and the box arrives through the
+// bulk-async copy engine (cp.async.bulk: brw_pbox_load_tma).  Every step is still a set of pairwise non-interacting swap
 // proposals whose choice does not depend on the configuration, each its own inverse: detailed balance holds move by
 // move exactly as before, and the simultaneous decisions equal sequential ones.  What K costs is sampling efficiency:
 // a site is tried K times in a row against an unchanged neighbourhood (measured in DESIGN.md 4.3: relaxation per
