@@ -62,3 +62,26 @@ def test_argument_validation_precedes_device_use(lib):
         brawl_b200.Device("fcc", 4, 4, 4, 2, 7, np.zeros(2 * 2 * 7))
     with pytest.raises(brawl_b200.BrawlCudaError, match="Unsupported number of shells"):
         brawl_b200.Device("simple_cubic", 4, 4, 4, 2, 3, np.zeros(2 * 2 * 3))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port on the host cores; no GPU needed): one JSON line with the keys the driver
+    reads, the same workload string as the CUDA arm, impl == "reference", e2e == value with zero copies."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-trials", "2000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e", "impl"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"]["workload"] == bench.workload_name(bench.N_CELLS) and d["metric"] == bench.METRIC
